@@ -1,0 +1,1 @@
+"""empty stub: recstudio.eval imports torchmetrics.functional as M"""

@@ -1,0 +1,178 @@
+"""The CPU oracle against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py) and SURVEY.md Appendix A."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox, retriever as R, samplers as S, topk_eval as T
+from conftest import GOLDEN, load_golden
+
+STEP_FILES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "step_*_*_*.npz"))
+                    if "full_softmax" not in p)
+
+
+def _cfg(name):
+    return (R.SSM if "_ssm_" in name else R.BPR), (R.EUCLID if name.endswith("_eu") else R.IP)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(*[np.array([c], dtype=np.uint32) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_philox_offset_and_mapping_properties():
+    sm, mt = 148, 2048
+    # counter_offset formula, DistributionTemplates.h:60
+    assert philox.torch_cuda_counter_offset(1, sm, mt) == 4
+    assert philox.torch_cuda_counter_offset(8192 * 1024, sm, mt) == ((8192 * 1024 - 1) // (256 * 1184 * 4) + 1) * 4
+    # element li in round r of thread idx uses counter offset/4 + r: consecutive calls never overlap
+    a = philox.torch_cuda_raw_u32(2022, 0, 5000, sm, mt)
+    off = philox.torch_cuda_counter_offset(5000, sm, mt)
+    b = philox.torch_cuda_raw_u32(2022, off, 5000, sm, mt)
+    assert not np.array_equal(a, b)
+    # a longer call shares its first-round words with a shorter one only if the grid is equal
+    c = philox.torch_cuda_raw_u32(2022, 0, 256 * 1184 * 4 + 10, sm, mt)
+    d = philox.torch_cuda_raw_u32(2022, 0, 256 * 1184 * 4, sm, mt)
+    assert np.array_equal(c[:d.size], d)
+    ids = philox.torch_cuda_randint(2022, 0, 1, 1000, 100000, sm, mt)
+    assert ids.min() >= 1 and ids.max() <= 999 and ids.dtype == np.int64
+    u = philox.torch_cuda_rand(2022, 0, 100000, sm, mt)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+
+
+def test_appendix_a_scores_and_losses():
+    g = load_golden("appendix_a")
+    q, vp, vn = (torch.from_numpy(g[k]) for k in ("q", "vp", "vn"))
+    lqp, lqn = torch.from_numpy(g["lqp"]), torch.from_numpy(g["lqn"])
+    survey = {"ip": (0.9947767, 2.2288237, 2.8037701, 2.0457540), "eu": (1.9598691, 4.0924187, 4.6389341, 4.0754628)}
+    for name, sc in (("ip", R.IP), ("eu", R.EUCLID)):
+        ps, ns = R.score(sc, q, vp), R.score(sc, q, vn)
+        np.testing.assert_array_equal(ps.numpy(), g[f"{name}_pos"])
+        np.testing.assert_array_equal(ns.numpy(), g[f"{name}_neg"])
+        vals = (R.bpr_loss(ps, ns), R.sampled_softmax_loss(ps, torch.zeros_like(ps), ns, torch.zeros_like(ns)),
+                R.sampled_softmax_loss(ps, lqp, ns, lqn), R.softmax_loss(ps, ns))
+        for v, key, s in zip(vals, ("bpr", "ssm0", "ssmq", "softmax"), survey[name]):
+            assert v.item() == g[f"{name}_{key}"].item()
+            assert abs(v.item() - s) < 2e-6
+
+
+@pytest.mark.parametrize("name", STEP_FILES)
+def test_training_step_aten_matches_reference_bitwise(name):
+    g = load_golden(name)
+    loss, scorer = _cfg(name)
+    out = R.training_step_aten(torch.from_numpy(g["w_item"]), torch.from_numpy(g["w_user"]),
+                               torch.from_numpy(g["user"]), torch.from_numpy(g["pos"]), torch.from_numpy(g["neg"]),
+                               loss=loss, scorer=scorer,
+                               log_pos_prob=torch.from_numpy(g["log_pos_prob"]),
+                               log_neg_prob=torch.from_numpy(g["log_neg_prob"]))
+    # same ATen ops in the same order on the same CPU => identical bits
+    assert out["loss"].item() == g["loss"].item()
+    np.testing.assert_array_equal(out["pos_score"].numpy(), g["pos_score"])
+    np.testing.assert_array_equal(out["neg_score"].numpy(), g["neg_score"])
+    np.testing.assert_array_equal(out["d_item"].numpy(), g["d_item"])
+    np.testing.assert_array_equal(out["d_user"].numpy(), g["d_user"])
+    assert np.all(g["d_item"][0] == 0)          # padding row never receives gradient (E2)
+
+
+@pytest.mark.parametrize("name", STEP_FILES)
+def test_closed_form_matches_reference(name):
+    g = load_golden(name)
+    loss, scorer = _cfg(name)
+    cf = R.closed_form_step(g["w_item"], g["w_user"], g["user"], g["pos"], g["neg"], loss=loss, scorer=scorer,
+                            log_pos_prob=g["log_pos_prob"], log_neg_prob=g["log_neg_prob"])
+    assert abs(cf["loss"] - g["loss"].item()) <= 2e-6 * max(1.0, abs(g["loss"].item()))
+    np.testing.assert_allclose(cf["pos_score"], g["pos_score"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(cf["neg_score"], g["neg_score"], rtol=1e-5, atol=1e-5)
+    di = R.dict_to_dense(cf["d_item"], g["d_item"].shape)
+    du = R.dict_to_dense(cf["d_user"], g["d_user"].shape)
+    scale_i, scale_u = np.abs(g["d_item"]).max(), np.abs(g["d_user"]).max()
+    assert np.abs(di - g["d_item"]).max() <= 1e-5 * scale_i
+    assert np.abs(du - g["d_user"]).max() <= 1e-5 * scale_u
+
+
+def test_popular_tables_and_draw():
+    g = load_golden("popular")
+    for tag in ("small", "big"):
+        for mode in (0, 1, 2):
+            prob, table = S.popular_tables(g[f"{tag}_count"], mode)
+            np.testing.assert_array_equal(prob, g[f"{tag}_m{mode}_prob"])
+            np.testing.assert_array_equal(table, g[f"{tag}_m{mode}_table"])
+    prob, table = S.popular_tables(g["small_count"], 0)
+    # SURVEY Appendix A
+    np.testing.assert_allclose(prob, [0.13756868, 0.24648999, 0.09535535, 0, 0.32987529, 1.0], atol=1e-7)
+    np.testing.assert_allclose(table, [0.13756868, 0.38405865, 0.47941402, 0.47941402, 0.80928934, 1.0], atol=1e-7)
+    idx, _ = S.popular_draw(table, prob, g["probe_seeds"])
+    np.testing.assert_array_equal(idx, g["probe_idx"])
+    np.testing.assert_array_equal(idx, [0, 1, 1, 4, 4, 5])
+    prob, table = S.popular_tables(g["big_count"], 0)
+    idx, logq = S.popular_draw(table, prob, g["draw_seeds"].reshape(-1))
+    np.testing.assert_array_equal(idx.reshape(g["draw_idx"].shape), g["draw_idx"])
+    np.testing.assert_array_equal(logq.reshape(g["draw_logq"].shape), g["draw_logq"])
+
+
+def test_uniform_sampler_contract():
+    g = load_golden("uniform_cpu")
+    # reference returns int64 zeros for both log-prob tensors
+    assert g["log_pos"].dtype == np.int64 and g["log_neg"].dtype == np.int64 and not g["log_neg"].any()
+    assert g["neg"].min() >= 1 and g["neg"].max() <= 9
+    assert g["neg2"].shape == (5, 7, 9)
+    lp, neg, ln, off = S.uniform_sampler(2022, 0, 10, 2, 4, np.array([3, 4]), 148, 2048)
+    assert lp.dtype == np.int64 and ln.dtype == np.int64 and neg.dtype == np.int64
+    assert neg.shape == (2, 4) and neg.min() >= 1 and neg.max() <= 9 and off == 4
+
+
+def test_topk_history_mask():
+    g = load_golden("topk_eval")
+    q = torch.from_numpy(g["a_w_user"])[torch.from_numpy(g["a_user"])]
+    sc, ids = T.topk_aten(q, torch.from_numpy(g["a_w_item"])[1:], 3, torch.from_numpy(g["a_hist"]))
+    np.testing.assert_array_equal(ids.numpy(), [[3, 4, 5], [5, 4, 3]])
+    np.testing.assert_array_equal(ids.numpy(), g["a_ids"]); np.testing.assert_array_equal(sc.numpy(), g["a_score"])
+    q = torch.from_numpy(g["r_w_user"])[torch.from_numpy(g["r_user"])]
+    iv = torch.from_numpy(g["r_w_item"])[1:]
+    hist = torch.from_numpy(g["r_hist"])
+    for k, ks, ki in ((10, "r_score", "r_ids"), (100, "r_score100", "r_ids100")):
+        sc, ids = T.topk_aten(q, iv, k, hist)
+        np.testing.assert_array_equal(ids.numpy(), g[ki]); np.testing.assert_array_equal(sc.numpy(), g[ks])
+        es, ei = T.topk_exact(q.numpy(), iv.numpy(), k, g["r_hist"])
+        np.testing.assert_array_equal(ei, g[ki])
+        np.testing.assert_allclose(es, g[ks], rtol=1e-5, atol=1e-5)
+    sc, ids = T.topk_aten(q, iv, 10, None)
+    np.testing.assert_array_equal(ids.numpy(), g["r_ids_nohist"])
+    es, ei = T.topk_exact(q.numpy(), iv.numpy(), 10, None)
+    np.testing.assert_array_equal(ei, g["r_ids_nohist"])
+    # the masked history ids never appear
+    for b in range(ids.shape[0]):
+        assert not np.isin(g["r_ids"][b], g["r_hist"][b][g["r_hist"][b] > 0]).any()
+
+
+def test_rank_metrics():
+    g = load_golden("topk_eval")
+    survey = {"recall": (0.1111111, 0.2222222, 0.5555556), "precision": (0.3333333, 0.2222222, 0.2),
+              "ndcg": (0.3333333, 0.2346394, 0.3781982), "map": (0.3333333, 0.1851852, 0.2685185),
+              "mrr": (0.3333333, 0.3333333, 0.4166667), "hit": (0.3333333, 0.3333333, 0.6666667)}
+    for name, fn in T.METRICS.items():
+        for i, k in enumerate((1, 3, 5)):
+            v = fn(g["m_label"], g["m_target"], k)
+            assert abs(v - g[f"m_{name}_{k}"].item()) < 1e-6, (name, k)
+            assert abs(v - survey[name][i]) < 1e-6
+    label = T.hit_matrix(g["r_ids100"], g["e_target"])
+    for name, fn in T.METRICS.items():
+        for k in (5, 10, 20):
+            assert abs(fn(label, g["e_rating"], k) - g[f"e_{name}_at_{k}"].item()) < 1e-6, (name, k)
+
+
+def test_full_softmax_step():
+    g = load_golden("step_full_softmax")
+    out = R.full_softmax_step_aten(torch.from_numpy(g["w_item"]), torch.from_numpy(g["w_user"]),
+                                   torch.from_numpy(g["user"]), torch.from_numpy(g["pos"]))
+    assert out["loss"].item() == g["loss"].item()
+    np.testing.assert_array_equal(out["d_item"].numpy(), g["d_item"])
+    np.testing.assert_array_equal(out["d_user"].numpy(), g["d_user"])
