@@ -1,0 +1,242 @@
+/*
+ * rsb200.h -- C ABI of librsb200.so, the B200 (sm_100a) implementation of
+ * RecStudio's retriever training-step hot path.
+ *
+ * The reference (ustcml/RecStudio) is pure Python/PyTorch and has NO native
+ * boundary of its own; the entry points below are what a binding for this path
+ * would call.  Each one names the reference code it replaces (paths relative
+ * to the reference root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative RSB200_E* code for an
+ *    argument error, or a positive cudaError_t; rsb200_last_error() returns a
+ *    thread-local message for the last non-zero return on this thread;
+ *  - the CALLER owns every buffer: the library never calls cudaMalloc.  All
+ *    pointers are device pointers on the current device unless marked host;
+ *  - tables are row-major fp32 with d % 4 == 0 and 16-byte aligned rows;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), no
+ *    host synchronisation, no global mutable state: calls are re-entrant
+ *    (the reference may call plugins from one thread per GPU,
+ *    recstudio/utils/data_parallel.py:84-92);
+ *  - ids are int64 where the reference produces int64 (batch ids, sampler
+ *    output) and int32 inside the library (N < 2^31).
+ *  - row 0 of every table is the padding row: it is scored like any other
+ *    row but never receives gradient (nn.Embedding(padding_idx=0),
+ *    recstudio/model/basemodel/baseretriever.py:84,104).
+ */
+#ifndef RSB200_H
+#define RSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSB200_VERSION 100
+
+/* error codes (negative); positive return values are cudaError_t */
+#define RSB200_OK            0
+#define RSB200_EINVAL       -1   /* bad argument (null pointer, bad size, misaligned) */
+#define RSB200_EUNSUPPORTED -2   /* valid but not implemented shape / mode */
+#define RSB200_ENOCUDA      -3   /* no usable CUDA device / wrong architecture */
+#define RSB200_EWORKSPACE   -4   /* workspace too small */
+
+/* enums (plain ints in the ABI) */
+#define RSB200_LOSS_BPR      0   /* recstudio/model/loss_func.py:50-59  BPRLoss(dns=False) */
+#define RSB200_LOSS_SSM      1   /* recstudio/model/loss_func.py:80-90  SampledSoftmaxLoss */
+#define RSB200_SCORE_IP      0   /* recstudio/model/scorer.py:5-17     InnerProductScorer  */
+#define RSB200_SCORE_EUCLID  1   /* recstudio/model/scorer.py:28-34    EuclideanScorer     */
+
+/* phases of rsb200_pair_step (bit mask) */
+#define RSB200_PHASE_COUNT   1   /* group touched rows: histogram + slot assignment      */
+#define RSB200_PHASE_SCAN    2   /* exclusive scan -> CSR offsets + unique-row list       */
+#define RSB200_PHASE_FWD     4   /* fused gather -> score -> loss -> coefficient emit     */
+#define RSB200_PHASE_SCATTER 8   /* segmented (row-grouped) gradient accumulate + loss sum*/
+#define RSB200_PHASE_ALL     15
+
+/* gradient sinks for PHASE_SCATTER */
+#define RSB200_SINK_COMPACT  0   /* rows[R] (int64, ascending, unique) + vals[R,d]: a coalesced sparse-COO gradient */
+#define RSB200_SINK_DENSE    1   /* vals is a dense [num_rows, d] buffer; touched rows are OVERWRITTEN (accumulate=0) or += (accumulate=1); rows[] still written */
+
+/* ------------------------------------------------------------------------- */
+int32_t     rsb200_version(void);
+const char* rsb200_last_error(void);
+/* sm_count / max_threads_per_sm of the CURRENT device (they fix the Philox
+ * element<->counter mapping of torch's CUDA generator, see below). */
+int32_t     rsb200_device_info(int32_t* sm_count, int32_t* max_threads_per_sm, int32_t* cc_major, int32_t* cc_minor);
+
+/* -------------------------------------------------------------------------
+ * S1  UniformSampler.forward        recstudio/ann/sampler.py:86-114
+ * S2  PopularSamplerModel.forward   recstudio/ann/sampler.py:243-258
+ *
+ * Bit-identical to torch.randint(1, num_items, (num_queries, num_neg),
+ * device='cuda') / torch.rand(...) -> searchsorted for the same
+ * (seed, philox_offset) of the CUDA generator: Philox4x32-10,
+ * curand_init(seed, thread, offset), 256-thread blocks,
+ * grid = min(sm_count * (max_threads_per_sm/256), ceil(numel/256)), unroll 4
+ * (ATen/native/cuda/DistributionTemplates.h:50-89,318-346,485-506).
+ * The host must advance the generator by rsb200_philox_counter_offset().
+ * Either output pointer may be NULL.  32-bit draw path only
+ * (num_items - 1 < 2^28) and numel * 8 < 2^31 (torch's 32-bit-indexing case).
+ */
+int64_t rsb200_philox_counter_offset(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm);
+
+int32_t rsb200_sample_uniform(uint64_t seed, uint64_t philox_offset,
+                              int64_t num_items /* table rows incl. padding row 0 */,
+                              int64_t num_queries, int64_t num_neg,
+                              int32_t sm_count, int32_t max_threads_per_sm,
+                              int64_t* neg_out_i64 /* [num_queries, num_neg] or NULL */,
+                              int32_t* neg_out_i32 /* [num_queries, num_neg] or NULL */,
+                              void* stream);
+
+/* guide table: guide[k] = searchsorted(table, k / 2^guide_bits), k in [0, 2^guide_bits],
+ * turns the reference's log2(N)-step bisection into an O(1)-expected search with
+ * identical results.  guide has 2^guide_bits + 1 int32 entries. */
+int32_t rsb200_popular_build_guide(const float* table, int64_t num_items, int32_t guide_bits,
+                                   int32_t* guide_out, void* stream);
+
+int32_t rsb200_sample_popular(uint64_t seed, uint64_t philox_offset,
+                              const float* table /* [num_items] cumsum, sampler.py:240 */,
+                              const float* pop_prob /* [num_items], sampler.py:239,241 */,
+                              int64_t num_items, int64_t num_queries, int64_t num_neg,
+                              int32_t sm_count, int32_t max_threads_per_sm,
+                              const int32_t* guide /* or NULL: plain bisection */, int32_t guide_bits,
+                              int64_t* neg_out_i64, int32_t* neg_out_i32,
+                              float* logq_out /* log(pop_prob[neg]) or NULL */,
+                              void* stream);
+
+/* compute_item_p: out[i] = log(pop_prob[ids[i]])   sampler.py:257-258 */
+int32_t rsb200_popular_logq(const float* pop_prob, int64_t num_items, const int64_t* ids, int64_t numel,
+                            float* out, void* stream);
+
+/* -------------------------------------------------------------------------
+ * R1 + E1 + Q1/Q2 + L1/L2 + E2: the fused retriever training step
+ *   BaseRetriever.forward (sampler branch) + training_step + loss.backward()
+ *   recstudio/model/basemodel/baseretriever.py:142-176,399-404,
+ *   recstudio/model/basemodel/recommender.py:638
+ *
+ * One call = for B interactions (user, pos, neg[n]):
+ *   gather W_user[user], W_item[pos], W_item[neg]  (nn.Embedding fwd)
+ *   score (IP | Euclid), loss (BPR | SampledSoftmax, mean reduction),
+ *   and the gradient of the loss w.r.t. both tables as sparse rows
+ *   (what the reference materialises as embedding_dense_backward).
+ *
+ * All pointers are device pointers.  Workspace arrays are caller-allocated
+ * with the sizes given in the comments (rsb200_pair_workspace_sizes fills them).
+ */
+typedef struct rsb200_pair_args {
+    /* tables */
+    const float*   w_item;      /* [num_items, d] */
+    const float*   w_user;      /* [num_users, d] */
+    /* batch */
+    const int64_t* user;        /* [B] */
+    const int64_t* pos;         /* [B] */
+    const int64_t* neg_i64;     /* [B, n] or NULL ... exactly one of neg_i64 / neg_i32 */
+    const int32_t* neg_i32;     /* [B, n] or NULL */
+    const float*   logq_pos;    /* [B]    or NULL (= 0, UniformSampler)              */
+    const float*   logq_neg;    /* [B, n] or NULL (= 0)                               */
+    /* outputs */
+    float*         loss;        /* [1]  mean loss                                     */
+    float*         pos_score;   /* [B]    or NULL                                     */
+    float*         neg_score;   /* [B, n] or NULL                                     */
+    int64_t*       item_rows;   /* [cap_item] unique touched rows, ascending          */
+    float*         item_vals;   /* COMPACT: [cap_item, d]; DENSE: [num_items, d]      */
+    int64_t*       user_rows;   /* [cap_user]                                         */
+    float*         user_vals;   /* COMPACT: [cap_user, d]; DENSE: [num_users, d]      */
+    uint32_t*      totals;      /* [4] = {item entries, item unique rows, user entries, user unique rows} */
+    /* workspace */
+    uint32_t*      off_item;    /* [num_items + 1]  histogram -> CSR offsets          */
+    uint32_t*      off_user;    /* [num_users + 1]                                    */
+    int32_t*       neg32_buf;   /* [B * n] int32 copy of neg_i64 (unused when neg_i32 is given) */
+    uint32_t*      slot_neg;    /* [B * n]                                            */
+    uint32_t*      slot_pos;    /* [B]                                                */
+    uint32_t*      slot_user;   /* [B]                                                */
+    uint64_t*      ent_item;    /* [B * (n + 1)]  (query, coefficient) entries by row */
+    uint64_t*      ent_user;    /* [B]                                                */
+    uint32_t*      urow_item;   /* [cap_item]                                         */
+    uint32_t*      urow_user;   /* [cap_user]                                         */
+    float*         q_buf;       /* [B, d] gathered queries                            */
+    float*         dq_buf;      /* [B, d] d loss / d query                            */
+    float*         loss_part;   /* [B]                                                */
+    float*         lse;         /* [B]   (SSM)                                        */
+    uint64_t*      scan_tmp;    /* [scan_tmp_elems]                                   */
+    uint32_t*      err_flag;    /* [1] set non-zero if an id was out of range         */
+    /* sizes */
+    int64_t num_items, num_users, B, n, d;
+    int64_t cap_item, cap_user;      /* capacity of *_rows / urow_* (>= min(touches, rows)) */
+    int64_t scan_tmp_elems;
+    float   grad_scale;              /* upstream gradient (loss.backward() => 1.0)     */
+    int32_t loss_kind, score_kind, sink, accumulate;
+    int32_t variant;                 /* 0 = default kernel; other values select experimental variants */
+} rsb200_pair_args;
+
+/* Fills the size fields a caller needs to allocate the workspace of a
+ * (num_items, num_users, B, n, d) problem.  All counts are in ELEMENTS. */
+typedef struct rsb200_pair_sizes {
+    int64_t off_item, off_user, neg32_buf, slot_neg, slot_pos, slot_user, ent_item, ent_user,
+            urow_item, urow_user, q_buf, dq_buf, loss_part, lse, scan_tmp, cap_item, cap_user;
+} rsb200_pair_sizes;
+int32_t rsb200_pair_workspace_sizes(int64_t num_items, int64_t num_users, int64_t B, int64_t n, int64_t d,
+                                    rsb200_pair_sizes* out);
+
+int32_t rsb200_pair_step(const rsb200_pair_args* args, int32_t phases, void* stream);
+/* sizeof(rsb200_pair_args) as compiled into the library (binding sanity check) */
+size_t  rsb200_sizeof_pair_args(void);
+
+/* -------------------------------------------------------------------------
+ * E1 / E2 standalone: nn.Embedding forward / backward
+ *   F.embedding(ids, W)                       baseretriever.py:154,168,211
+ *   embedding_dense_backward (autograd)       recommender.py:638
+ */
+int32_t rsb200_gather_rows(const float* w, int64_t num_rows, int64_t d,
+                           const int64_t* ids, int64_t numel, float* out /* [numel, d] */, void* stream);
+/* dW[ids[i], :] += d_out[i, :] for ids[i] != 0, dW dense [num_rows, d] (caller zero-fills) */
+int32_t rsb200_scatter_add_rows(float* dw, int64_t num_rows, int64_t d,
+                                const int64_t* ids, int64_t numel, const float* d_out, void* stream);
+
+/* -------------------------------------------------------------------------
+ * Q1 / Q2 standalone on ids (no [B,n,d] materialisation):
+ *   score[b, j] = score_func(q[b], W[ids[b, j]])       scorer.py:10-14 / 28-34
+ */
+int32_t rsb200_score_ids(int32_t score_kind, const float* q /* [B,d] */, const float* w, int64_t num_rows,
+                         int64_t d, const int64_t* ids /* [B, n] */, int64_t B, int64_t n,
+                         float* out /* [B, n] */, void* stream);
+
+/* -------------------------------------------------------------------------
+ * L1 / L2 standalone on score tensors (for mixing with reference plugins):
+ *   loss and d loss / d score in one pass.     loss_func.py:55-59, 80-90
+ */
+int32_t rsb200_pair_loss(int32_t loss_kind, const float* pos_score /* [B] */, const float* neg_score /* [B,n] */,
+                         const float* logq_pos, const float* logq_neg, int64_t B, int64_t n,
+                         float* loss /* [1] */, float* d_pos /* [B] */, float* d_neg /* [B,n] */,
+                         float* loss_part /* [B] workspace */, void* stream);
+
+/* -------------------------------------------------------------------------
+ * T1  BaseRetriever.topk (no ANN index, InnerProduct | Euclid)
+ *   recstudio/model/basemodel/baseretriever.py:374-397
+ * Scores every item row 1..num_items-1 against each query, masks the ids in
+ * hist (0 = padding), returns the k best (score desc, id asc on ties),
+ * ids 1-based.  [Be, num_items] is never written to HBM.
+ */
+size_t  rsb200_topk_workspace_bytes(int64_t Be, int64_t num_items, int64_t k);
+int32_t rsb200_topk_full(int32_t score_kind, const float* q /* [Be,d] */, const float* w_item, int64_t num_items,
+                         int64_t d, int64_t Be, int64_t k, const int64_t* hist /* [Be,H] or NULL */, int64_t H,
+                         float* score_out /* [Be,k] */, int64_t* id_out /* [Be,k] */,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* -------------------------------------------------------------------------
+ * L3 + Q1-full  SoftmaxLoss over the whole catalog (forward + backward)
+ *   baseretriever.py:177-186, loss_func.py:39-42
+ */
+size_t  rsb200_fullsoftmax_workspace_bytes(int64_t B, int64_t num_items, int64_t d);
+int32_t rsb200_fullsoftmax_fwd_bwd(const float* q /* [B,d] */, const float* w_item, const int64_t* pos /* [B] */,
+                                   int64_t num_items, int64_t B, int64_t d,
+                                   float* loss /* [1] */, float* dq /* [B,d] */, float* dw /* [num_items,d] dense, overwritten */,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSB200_H */

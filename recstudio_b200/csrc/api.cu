@@ -1,0 +1,168 @@
+// api.cu -- C-ABI entry points of librsb200.so (see include/rsb200.h) and host-side glue.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rsb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached_sm = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached_dev = dev; cached_sm = v;
+    }
+    return cached_sm;
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" int32_t rsb200_version(void) { return RSB200_VERSION; }
+extern "C" size_t rsb200_sizeof_pair_args(void) { return sizeof(rsb200_pair_args); }
+extern "C" const char* rsb200_last_error(void) { return g_err; }
+
+extern "C" int32_t rsb200_device_info(int32_t* sm, int32_t* max_threads_per_sm, int32_t* cc_major, int32_t* cc_minor) {
+    int dev = 0, n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return RSB200_ENOCUDA;
+    }
+    RSB_CUDA(cudaGetDevice(&dev));
+    int v = 0;
+    if (sm) { RSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm = v; }
+    if (max_threads_per_sm) { RSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxThreadsPerMultiProcessor, dev)); *max_threads_per_sm = v; }
+    if (cc_major) { RSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *cc_major = v; }
+    if (cc_minor) { RSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t rsb200_pair_workspace_sizes(int64_t num_items, int64_t num_users, int64_t B, int64_t n, int64_t d,
+                                               rsb200_pair_sizes* o) {
+    RSB_REQUIRE(o != nullptr, RSB200_EINVAL, "null output");
+    RSB_REQUIRE(num_items >= 1 && num_users >= 1 && B >= 0 && n >= 0 && d >= 4 && d % 4 == 0, RSB200_EINVAL,
+                "bad problem shape (num_items=%lld num_users=%lld B=%lld n=%lld d=%lld)", (long long)num_items,
+                (long long)num_users, (long long)B, (long long)n, (long long)d);
+    RSB_REQUIRE(B * (n + 1) < ((int64_t)1 << 31), RSB200_EUNSUPPORTED, "B*(n+1) must be < 2^31");
+    RSB_REQUIRE(num_items < ((int64_t)1 << 31) && num_users < ((int64_t)1 << 31), RSB200_EUNSUPPORTED, "table rows must be < 2^31");
+    o->off_item = num_items + 1;
+    o->off_user = num_users + 1;
+    o->neg32_buf = B * n;
+    o->slot_neg = B * n;
+    o->slot_pos = B;
+    o->slot_user = B;
+    o->ent_item = B * (n + 1);
+    o->ent_user = B;
+    int64_t ci = B * (n + 1) < num_items ? B * (n + 1) : num_items;
+    int64_t cu = B < num_users ? B : num_users;
+    o->cap_item = ci > 0 ? ci : 1;
+    o->cap_user = cu > 0 ? cu : 1;
+    o->urow_item = o->cap_item;
+    o->urow_user = o->cap_user;
+    o->q_buf = B * d;
+    o->dq_buf = B * d;
+    o->loss_part = B;
+    o->lse = B;
+    int64_t a = scan_tmp_elems(num_items), b = scan_tmp_elems(num_users);
+    o->scan_tmp = a > b ? a : b;
+    return 0;
+}
+
+static int32_t check_pair(const rsb200_pair_args* a) {
+    RSB_REQUIRE(a != nullptr, RSB200_EINVAL, "null args");
+    RSB_REQUIRE(a->d >= 4 && a->d % 4 == 0 && a->d <= 512, a->d > 512 ? RSB200_EUNSUPPORTED : RSB200_EINVAL,
+                "embedding dim must be a multiple of 4 in [4, 512], got %lld", (long long)a->d);
+    RSB_REQUIRE(a->B >= 0 && a->n >= 0 && a->num_items >= 1 && a->num_users >= 1, RSB200_EINVAL, "bad sizes");
+    RSB_REQUIRE(a->B * (a->n + 1) < ((int64_t)1 << 31), RSB200_EUNSUPPORTED, "B*(n+1) must be < 2^31");
+    RSB_REQUIRE(a->num_items < ((int64_t)1 << 31) && a->num_users < ((int64_t)1 << 31), RSB200_EUNSUPPORTED, "table rows must be < 2^31");
+    RSB_REQUIRE(a->w_item && a->w_user && a->user && a->pos, RSB200_EINVAL, "null table / batch pointer");
+    RSB_REQUIRE(a->n == 0 || ((a->neg_i64 != nullptr) != (a->neg_i32 != nullptr)), RSB200_EINVAL,
+                "exactly one of neg_i64 / neg_i32 must be given");
+    RSB_REQUIRE(a->n == 0 || a->neg_i32 || a->neg32_buf, RSB200_EINVAL, "neg_i64 needs the neg32_buf workspace");
+    RSB_REQUIRE(aligned16(a->w_item) && aligned16(a->w_user) && aligned16(a->q_buf) && aligned16(a->dq_buf) &&
+                aligned16(a->item_vals) && aligned16(a->user_vals), RSB200_EINVAL, "tables / row buffers must be 16-byte aligned");
+    RSB_REQUIRE(a->loss_kind == RSB200_LOSS_BPR || a->loss_kind == RSB200_LOSS_SSM, RSB200_EINVAL, "bad loss_kind");
+    RSB_REQUIRE(a->score_kind == RSB200_SCORE_IP || a->score_kind == RSB200_SCORE_EUCLID, RSB200_EINVAL, "bad score_kind");
+    RSB_REQUIRE(a->sink == RSB200_SINK_COMPACT || a->sink == RSB200_SINK_DENSE, RSB200_EINVAL, "bad sink");
+    RSB_REQUIRE(a->off_item && a->off_user && a->slot_neg && a->slot_pos && a->slot_user && a->ent_item && a->ent_user &&
+                a->urow_item && a->urow_user && a->q_buf && a->dq_buf && a->loss_part && a->lse && a->scan_tmp &&
+                a->err_flag && a->totals && a->loss, RSB200_EINVAL, "null workspace pointer");
+    return 0;
+}
+
+extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, void* stream) {
+    int32_t rc = check_pair(a);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t B = a->B, n = a->n;
+    const int32_t* neg32 = a->neg_i32 ? a->neg_i32 : a->neg32_buf;
+
+    if (phases & RSB200_PHASE_COUNT) {
+        RSB_CUDA(cudaMemsetAsync(a->off_item, 0, sizeof(uint32_t) * (size_t)(a->num_items + 1), st));
+        RSB_CUDA(cudaMemsetAsync(a->off_user, 0, sizeof(uint32_t) * (size_t)(a->num_users + 1), st));
+        if (a->neg_i32) rc = launch_count<int32_t>(a->neg_i32, B * n, a->num_items, a->off_item, a->slot_neg, nullptr, a->err_flag, st);
+        else            rc = launch_count<int64_t>(a->neg_i64, B * n, a->num_items, a->off_item, a->slot_neg, a->neg32_buf, a->err_flag, st);
+        if (rc) return rc;
+        rc = launch_count<int64_t>(a->pos, B, a->num_items, a->off_item, a->slot_pos, nullptr, a->err_flag, st);
+        if (rc) return rc;
+        rc = launch_count<int64_t>(a->user, B, a->num_users, a->off_user, a->slot_user, nullptr, a->err_flag, st);
+        if (rc) return rc;
+    }
+    if (phases & RSB200_PHASE_SCAN) {
+        rc = launch_scan(a->off_item, a->num_items, a->urow_item, a->cap_item, a->totals, a->scan_tmp, a->scan_tmp_elems, st);
+        if (rc) return rc;
+        rc = launch_scan(a->off_user, a->num_users, a->urow_user, a->cap_user, a->totals + 2, a->scan_tmp, a->scan_tmp_elems, st);
+        if (rc) return rc;
+    }
+    if (phases & RSB200_PHASE_FWD) {
+        FwdParams p;
+        p.w_item = a->w_item; p.w_user = a->w_user; p.user = a->user; p.pos = a->pos; p.neg = neg32;
+        p.logq_pos = a->logq_pos; p.logq_neg = a->logq_neg;
+        p.off_item = a->off_item; p.off_user = a->off_user;
+        p.slot_neg = a->slot_neg; p.slot_pos = a->slot_pos; p.slot_user = a->slot_user;
+        p.ent_item = a->ent_item; p.ent_user = a->ent_user;
+        p.q_buf = a->q_buf; p.dq_buf = a->dq_buf; p.loss_part = a->loss_part; p.lse = a->lse;
+        p.pos_score = a->pos_score; p.neg_score = a->neg_score;
+        p.num_items = (int)a->num_items; p.num_users = (int)a->num_users; p.B = (int)B; p.n = (int)n; p.D = (int)a->d;
+        const double denom = (a->loss_kind == RSB200_LOSS_BPR) ? (double)B * (double)(n > 0 ? n : 1) : (double)B;
+        p.loss_scale = (float)(1.0 / (denom > 0 ? denom : 1.0));
+        p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
+        rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
+        if (rc) return rc;
+    }
+    if (phases & RSB200_PHASE_SCATTER) {
+        ScatterParams s;
+        s.off = a->off_item; s.urow = a->urow_item; s.totals = a->totals; s.ent = a->ent_item; s.src = a->q_buf;
+        s.lse = a->lse; s.w = a->w_item; s.rows_out = a->item_rows; s.vals = a->item_vals; s.D = (int)a->d;
+        s.cap = a->cap_item;
+        s.ssm_scale = (float)((double)a->grad_scale / (double)(B > 0 ? B : 1));
+        s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = a->score_kind == RSB200_SCORE_EUCLID;
+        rc = launch_scatter(s, a->cap_item, st);
+        if (rc) return rc;
+        ScatterParams u = s;
+        u.off = a->off_user; u.urow = a->urow_user; u.totals = a->totals + 2; u.ent = a->ent_user; u.src = a->dq_buf;
+        u.lse = nullptr; u.w = a->w_user; u.rows_out = a->user_rows; u.vals = a->user_vals; u.cap = a->cap_user;
+        u.euclid = 0;
+        rc = launch_scatter(u, a->cap_user, st);
+        if (rc) return rc;
+        rc = launch_loss_sum(a->loss_part, (int)B, a->loss, st);
+        if (rc) return rc;
+    }
+    return 0;
+}

@@ -1,0 +1,167 @@
+// group.cu -- grouping of touched rows for the sparse-row gradient (E2).
+//
+// The reference accumulates embedding gradients with embedding_dense_backward
+// (autograd of F.embedding, recommender.py:638): a dense [N,d] zero-fill plus
+// scatter-add.  Here the touched rows are grouped instead (counting sort keyed
+// by row id, N buckets) so that every gradient row is produced exactly once by
+// one warp in scatter.cu with no atomics on fp32 data:
+//   count : cnt[row]++ (integer atomics), slot[touch] = position inside the row
+//   scan  : off[row] = exclusive prefix sum of cnt (CSR offsets, in place) and
+//           urow[rank] = row for rows with cnt > 0 (ascending unique rows)
+// Touches of the padding row 0 (and invalid ids) get slot = kNoSlot: they are
+// scored but receive no gradient (nn.Embedding(padding_idx=0)).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rsb {
+
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+count_kernel(const IdT* __restrict__ ids, int64_t M, int64_t num_rows, uint32_t* __restrict__ cnt,
+             uint32_t* __restrict__ slot, int32_t* __restrict__ ids32_out, uint32_t* __restrict__ err_flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int64_t id = (int64_t)ids[i];
+    uint32_t s = kNoSlot;
+    if (id > 0 && id < num_rows) {
+        s = atomicAdd(cnt + id, 1u);
+    } else if (id != 0) {
+        *err_flag = 1u;
+    }
+    slot[i] = s;
+    if (ids32_out) ids32_out[i] = (id >= 0 && id < num_rows) ? (int32_t)id : 0;   // i64 -> i32 copy for pair_fwd
+}
+
+// ---------------------------------------------------------------------------- scan
+// 3-phase scan over u32 counts.  Each block owns a tile of kTile elements; the packed
+// u64 carries (sum of counts) in the low and (number of non-empty rows) in the high word.
+constexpr int kScanThreads = 512;
+constexpr int kScanPer = 8;
+constexpr int kTile = kScanThreads * kScanPer;   // 4096
+
+__device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
+    int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one value per thread across the block; returns the exclusive prefix and the block total
+__device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* total) {
+    __shared__ uint64_t warp_sums[kScanThreads / 32];
+    __shared__ uint64_t block_total;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t inc = warp_incl_scan(v);
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint64_t s = (lane < kScanThreads / 32) ? warp_sums[lane] : 0;
+        uint64_t si = warp_incl_scan(s);
+        if (lane < kScanThreads / 32) warp_sums[lane] = si - s;
+        if (lane == kScanThreads / 32 - 1) block_total = si;
+    }
+    __syncthreads();
+    uint64_t excl = inc - v + warp_sums[w];
+    *total = block_total;
+    __syncthreads();   // shared arrays are reused by the next call
+    return excl;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_reduce_kernel(const uint32_t* __restrict__ cnt, int64_t num_rows, uint64_t* __restrict__ block_sums) {
+    int64_t base = (int64_t)blockIdx.x * kTile;
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        int64_t i = base + (int64_t)k * kScanThreads + threadIdx.x;
+        if (i < num_rows) {
+            uint32_t c = cnt[i];
+            acc += (uint64_t)c + ((uint64_t)(c != 0) << 32);
+        }
+    }
+    uint64_t total;
+    block_excl_scan(acc, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the block sums in place; writes totals and off[num_rows]
+__global__ void __launch_bounds__(kScanThreads)
+scan_spine_kernel(uint64_t* __restrict__ block_sums, int64_t nblocks, uint32_t* __restrict__ off_last,
+                  uint32_t* __restrict__ totals /* [2]: entries, unique rows */) {
+    uint64_t carry = 0;
+    for (int64_t base = 0; base < nblocks; base += kScanThreads) {
+        int64_t i = base + threadIdx.x;
+        uint64_t v = (i < nblocks) ? block_sums[i] : 0;
+        uint64_t total;
+        uint64_t ex = block_excl_scan(v, &total);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        *off_last = (uint32_t)carry;
+        totals[0] = (uint32_t)carry;
+        totals[1] = (uint32_t)(carry >> 32);
+    }
+}
+
+// rescan each tile with its block offset; write offsets IN PLACE and the unique-row list
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(uint32_t* __restrict__ cnt_off, int64_t num_rows, const uint64_t* __restrict__ block_sums,
+                  uint32_t* __restrict__ urow, int64_t cap) {
+    // thread t owns kScanPer CONSECUTIVE elements so that its local prefix is a serial sum
+    int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kScanPer;
+    uint32_t c[kScanPer];
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        int64_t i = base + k;
+        c[k] = (i < num_rows) ? cnt_off[i] : 0u;
+        acc += (uint64_t)c[k] + ((uint64_t)(c[k] != 0) << 32);
+    }
+    uint64_t total;
+    uint64_t ex = block_excl_scan(acc, &total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        int64_t i = base + k;
+        if (i < num_rows) {
+            cnt_off[i] = (uint32_t)ex;
+            if (c[k] != 0) {
+                int64_t rank = (int64_t)(ex >> 32);
+                if (rank < cap) urow[rank] = (uint32_t)i;
+            }
+        }
+        ex += (uint64_t)c[k] + ((uint64_t)(c[k] != 0) << 32);
+    }
+}
+
+int64_t scan_tmp_elems(int64_t num_rows) { return cdiv(num_rows, kTile) + 1; }
+
+template <typename IdT>
+int32_t launch_count(const IdT* ids, int64_t M, int64_t num_rows, uint32_t* cnt, uint32_t* slot,
+                     int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st) {
+    if (M == 0) return 0;
+    count_kernel<IdT><<<(unsigned)cdiv(M, 256), 256, 0, st>>>(ids, M, num_rows, cnt, slot, ids32_out, err_flag);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+template int32_t launch_count<int32_t>(const int32_t*, int64_t, int64_t, uint32_t*, uint32_t*, int32_t*, uint32_t*, cudaStream_t);
+template int32_t launch_count<int64_t>(const int64_t*, int64_t, int64_t, uint32_t*, uint32_t*, int32_t*, uint32_t*, cudaStream_t);
+
+int32_t launch_scan(uint32_t* cnt_off, int64_t num_rows, uint32_t* urow, int64_t cap, uint32_t* totals,
+                    uint64_t* tmp, int64_t tmp_elems, cudaStream_t st) {
+    int64_t nblocks = cdiv(num_rows, kTile);
+    RSB_REQUIRE(tmp_elems >= nblocks + 1, RSB200_EWORKSPACE, "scan_tmp too small: %lld < %lld",
+                (long long)tmp_elems, (long long)(nblocks + 1));
+    scan_reduce_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>>(cnt_off, num_rows, tmp);
+    RSB_LAUNCH_CHECK();
+    scan_spine_kernel<<<1, kScanThreads, 0, st>>>(tmp, nblocks, cnt_off + num_rows, totals);
+    RSB_LAUNCH_CHECK();
+    scan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>>(cnt_off, num_rows, tmp, urow, cap);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rsb

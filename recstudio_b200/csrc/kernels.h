@@ -1,0 +1,50 @@
+// kernels.h -- internal launch interfaces shared by the .cu translation units.
+#pragma once
+#include "common.cuh"
+
+namespace rsb {
+
+struct FwdParams {
+    const float* w_item; const float* w_user;
+    const int64_t* user; const int64_t* pos; const int32_t* neg;
+    const float* logq_pos; const float* logq_neg;
+    const uint32_t* off_item; const uint32_t* off_user;
+    const uint32_t* slot_neg; const uint32_t* slot_pos; const uint32_t* slot_user;
+    uint64_t* ent_item; uint64_t* ent_user;
+    float* q_buf; float* dq_buf; float* loss_part; float* lse;
+    float* pos_score; float* neg_score;
+    int num_items, num_users, B, n, D;
+    float coef_scale;   // grad_scale / (B n) for BPR, grad_scale / B for SSM
+    float loss_scale;   // 1 / (B n)              for BPR, 1 / B              for SSM
+};
+
+struct ScatterParams {
+    const uint32_t* off;      // [num_rows + 1] CSR offsets
+    const uint32_t* urow;     // [R] unique touched rows, ascending
+    const uint32_t* totals;   // totals[1] = R
+    const uint64_t* ent;      // entries grouped by row
+    const float* src;         // [B, D]
+    const float* lse;         // [B] or null
+    const float* w;           // table (Euclid only)
+    int64_t* rows_out;        // [R]
+    float* vals;              // compact [R, D] or dense [num_rows, D]
+    int64_t cap;              // capacity of urow / rows_out
+    int D;
+    float ssm_scale;
+    int dense, accumulate, euclid;
+};
+
+// group.cu
+int64_t scan_tmp_elems(int64_t num_rows);
+template <typename IdT>
+int32_t launch_count(const IdT* ids, int64_t M, int64_t num_rows, uint32_t* cnt, uint32_t* slot,
+                     int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st);
+int32_t launch_scan(uint32_t* cnt_off, int64_t num_rows, uint32_t* urow, int64_t cap, uint32_t* totals,
+                    uint64_t* tmp, int64_t tmp_elems, cudaStream_t st);
+// pair_fwd.cu
+int32_t launch_pair_fwd(const FwdParams& p, int loss, int score, int variant, cudaStream_t st);
+// scatter.cu
+int32_t launch_scatter(const ScatterParams& p, int64_t cap_rows, cudaStream_t st);
+int32_t launch_loss_sum(const float* part, int B, float* loss, cudaStream_t st);
+
+}  // namespace rsb

@@ -1,0 +1,183 @@
+// sampler.cu -- S1 UniformSampler / S2 PopularSamplerModel draws, bit-identical to the
+// reference's torch.randint / torch.rand + searchsorted on a CUDA device.
+//   reference: recstudio/ann/sampler.py:86-114 (uniform), :243-258 (popularity)
+//   ATen:      native/cuda/DistributionTemplates.h:50-89 (policy + grid-stride kernel),
+//              :318-346 (random_from_to, 32-bit path), :485-506 (uniform_, (0,1] -> [0,1))
+//
+// ATen thread `idx` (of T = 256*grid threads) in round r draws curand4 once and hands word ii
+// to element li = idx + T*(4r + ii).  Here one thread owns one (r, idx) pair, computes the
+// same Philox block and writes its four elements; stores of a warp are 32 consecutive
+// elements for every ii, i.e. fully coalesced.
+#include "common.cuh"
+
+namespace rsb {
+
+struct DrawPolicy {
+    int64_t T;        // 256 * grid of the ATen kernel
+    int64_t rounds;   // grid-stride iterations per ATen thread
+};
+
+static DrawPolicy make_policy(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm) {
+    int64_t blocks = cdiv(numel, 256);
+    int64_t grid = (int64_t)sm_count * (max_threads_per_sm / 256);
+    if (blocks < grid) grid = blocks;
+    DrawPolicy p;
+    p.T = 256 * grid;
+    p.rounds = (numel - 1) / (p.T * 4) + 1;
+    return p;
+}
+
+__global__ void __launch_bounds__(256)
+uniform_kernel(uint64_t seed, uint64_t ctr_base, int64_t T, int64_t rounds, int64_t numel,
+               uint32_t range, int64_t* __restrict__ out64, int32_t* __restrict__ out32) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T * rounds) return;
+    int64_t r = t / T, idx = t - r * T;
+    uint4 w = Philox::gen(seed, (uint64_t)idx, ctr_base + (uint64_t)r);
+    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    int64_t li = r * 4 * T + idx;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii, li += T) {
+        if (li < numel) {
+            uint32_t v = words[ii] % range + 1u;   // uniform_int_from_to<int64>(V, range, base=1)
+            if (out64) out64[li] = (int64_t)v;
+            if (out32) out32[li] = (int32_t)v;
+        }
+    }
+}
+
+// first i in [lo, hi] with table[i] >= u  (hi is returned if none)
+__device__ __forceinline__ int lower_bound(const float* __restrict__ table, int lo, int hi, float u) {
+    while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        if (__ldg(table + mid) < u) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+popular_kernel(uint64_t seed, uint64_t ctr_base, int64_t T, int64_t rounds, int64_t numel,
+               const float* __restrict__ table, const float* __restrict__ pop_prob, int num_items,
+               const int32_t* __restrict__ guide, int guide_bits,
+               int64_t* __restrict__ out64, int32_t* __restrict__ out32, float* __restrict__ logq) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T * rounds) return;
+    int64_t r = t / T, idx = t - r * T;
+    uint4 w = Philox::gen(seed, (uint64_t)idx, ctr_base + (uint64_t)r);
+    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    int64_t li = r * 4 * T + idx;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii, li += T) {
+        if (li < numel) {
+            float u = curand_uniform_from_u32(words[ii]);   // (0, 1]
+            u = u * 1.0f + 0.0f;                            // rand * range + from
+            if (u == 1.0f) u = 0.0f;                        // reverse bounds -> [0, 1)
+            int lo = 0, hi = num_items - 1;                 // searchsorted result N is clamped to N-1
+            if (guide) {
+                int k = (int)(u * (float)(1 << guide_bits));  // exact: power-of-two scale of a 24-bit float
+                lo = guide[k]; hi = guide[k + 1];
+            }
+            int id = lower_bound(table, lo, hi, u);
+            if (out64) out64[li] = id;
+            if (out32) out32[li] = id;
+            if (logq) logq[li] = logf(__ldg(pop_prob + id));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+guide_kernel(const float* __restrict__ table, int num_items, int guide_bits, int32_t* __restrict__ guide) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int K = 1 << guide_bits;
+    if (k > K) return;
+    float u = (float)k / (float)K;            // exact
+    guide[k] = lower_bound(table, 0, num_items - 1, u);
+}
+
+__global__ void __launch_bounds__(256)
+logq_kernel(const float* __restrict__ pop_prob, int64_t num_items, const int64_t* __restrict__ ids, int64_t numel,
+            float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    int64_t id = ids[i];
+    if (id < 0 || id >= num_items) id = 0;
+    out[i] = logf(__ldg(pop_prob + id));
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" int64_t rsb200_philox_counter_offset(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm) {
+    if (numel <= 0 || sm_count <= 0 || max_threads_per_sm < 256) return 0;
+    DrawPolicy p = make_policy(numel, sm_count, max_threads_per_sm);
+    return p.rounds * 4;
+}
+
+static int32_t check_draw(uint64_t off, int64_t num_items, int64_t nq, int64_t nn, int32_t sm, int32_t mt) {
+    RSB_REQUIRE(nq >= 0 && nn >= 0, RSB200_EINVAL, "negative sampler shape");
+    RSB_REQUIRE(num_items >= 2, RSB200_EINVAL, "num_items must include the padding row and at least one item");
+    RSB_REQUIRE(sm > 0 && mt >= 256, RSB200_EINVAL, "bad device policy (sm_count=%d max_threads_per_sm=%d)", sm, mt);
+    RSB_REQUIRE(off % 4 == 0, RSB200_EINVAL, "philox offset must be a multiple of 4 (torch invariant)");
+    RSB_REQUIRE(nq * nn * 8 < ((int64_t)1 << 31), RSB200_EUNSUPPORTED,
+                "numel*8 >= 2^31: torch splits such draws into 32-bit-indexable sub-iterators; not restated");
+    RSB_REQUIRE(num_items < ((int64_t)1 << 31), RSB200_EUNSUPPORTED, "num_items >= 2^31");
+    return 0;
+}
+
+extern "C" int32_t rsb200_sample_uniform(uint64_t seed, uint64_t philox_offset, int64_t num_items,
+                                         int64_t num_queries, int64_t num_neg, int32_t sm_cnt, int32_t max_tpsm,
+                                         int64_t* neg64, int32_t* neg32, void* stream) {
+    int32_t rc = check_draw(philox_offset, num_items, num_queries, num_neg, sm_cnt, max_tpsm);
+    if (rc) return rc;
+    RSB_REQUIRE(num_items - 1 < ((int64_t)1 << 28), RSB200_EUNSUPPORTED,
+                "range >= 2^28 takes ATen's 64-bit draw path (DistributionTemplates.h:319); not implemented");
+    int64_t numel = num_queries * num_neg;
+    if (numel == 0) return 0;
+    DrawPolicy p = make_policy(numel, sm_cnt, max_tpsm);
+    int64_t threads = p.T * p.rounds;
+    uniform_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+        seed, philox_offset / 4, p.T, p.rounds, numel, (uint32_t)(num_items - 1), neg64, neg32);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t rsb200_popular_build_guide(const float* table, int64_t num_items, int32_t guide_bits,
+                                              int32_t* guide_out, void* stream) {
+    RSB_REQUIRE(table && guide_out, RSB200_EINVAL, "null pointer");
+    RSB_REQUIRE(guide_bits >= 1 && guide_bits <= 24, RSB200_EINVAL, "guide_bits must be in [1, 24]");
+    RSB_REQUIRE(num_items >= 1 && num_items < ((int64_t)1 << 31), RSB200_EINVAL, "bad num_items");
+    int K = 1 << guide_bits;
+    guide_kernel<<<(unsigned)cdiv(K + 1, 256), 256, 0, (cudaStream_t)stream>>>(table, (int)num_items, guide_bits, guide_out);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t rsb200_sample_popular(uint64_t seed, uint64_t philox_offset, const float* table,
+                                         const float* pop_prob, int64_t num_items, int64_t num_queries,
+                                         int64_t num_neg, int32_t sm_cnt, int32_t max_tpsm,
+                                         const int32_t* guide, int32_t guide_bits,
+                                         int64_t* neg64, int32_t* neg32, float* logq, void* stream) {
+    int32_t rc = check_draw(philox_offset, num_items, num_queries, num_neg, sm_cnt, max_tpsm);
+    if (rc) return rc;
+    RSB_REQUIRE(table && (pop_prob || !logq), RSB200_EINVAL, "null table / pop_prob");
+    RSB_REQUIRE(!guide || (guide_bits >= 1 && guide_bits <= 24), RSB200_EINVAL, "guide_bits must be in [1, 24]");
+    int64_t numel = num_queries * num_neg;
+    if (numel == 0) return 0;
+    DrawPolicy p = make_policy(numel, sm_cnt, max_tpsm);
+    int64_t threads = p.T * p.rounds;
+    popular_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+        seed, philox_offset / 4, p.T, p.rounds, numel, table, pop_prob, (int)num_items, guide, guide_bits,
+        neg64, neg32, logq);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t rsb200_popular_logq(const float* pop_prob, int64_t num_items, const int64_t* ids, int64_t numel,
+                                       float* out, void* stream) {
+    RSB_REQUIRE(pop_prob && ids && out, RSB200_EINVAL, "null pointer");
+    if (numel == 0) return 0;
+    logq_kernel<<<(unsigned)cdiv(numel, 256), 256, 0, (cudaStream_t)stream>>>(pop_prob, num_items, ids, numel, out);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,166 @@
+// scatter.cu -- segmented (row-grouped) gradient accumulate: the sparse-row replacement of
+// embedding_dense_backward (E2; autograd of nn.Embedding, recommender.py:638), plus the
+// final loss reduction.
+//
+// Input: the entry list written by pair_fwd.cu, grouped by table row through the CSR
+// offsets of group.cu.  Entry = (query index b | kDirect flag, value).  The gradient row is
+//     g[row] = sum_e  c_e * src[b_e, :]            (src = q_buf for items, dq_buf for users)
+//     c_e    = value                               if the entry is flagged kDirect
+//            = exp(value - lse[b_e]) * ssm_scale   otherwise (SampledSoftmax negatives: the
+//              logit is stored and the softmax denominator is applied here, so the forward
+//              kernel never needs a second sweep over its negatives)
+//     Euclid: g[row] = 2 * (g[row] - (sum_e c_e) * W[row, :])
+// Every unique row is produced by exactly ONE warp: no floating-point atomics, no
+// zero-fill of an [N,d] buffer, and each output row is written once with 16-byte stores.
+// A warp owns 32 consecutive unique rows; because the entry list is sorted by row, their
+// entries are one contiguous range that is streamed with coalesced loads.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rsb {
+
+constexpr int kScatWarps = 8;
+
+template <int VPL>
+__global__ void __launch_bounds__(kScatWarps * 32)
+scatter_kernel(const ScatterParams p) {
+    const int lane = threadIdx.x & 31;
+    const int D = p.D;
+    const uint32_t R = (uint32_t)min((int64_t)p.totals[1], p.cap);
+    const uint32_t nchunks = (R + 31) / 32;
+    const uint32_t warps_total = gridDim.x * kScatWarps;
+    bool act[VPL];
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) act[t] = (lane * 4 + t * 128) < D;
+
+    for (uint32_t chunk = blockIdx.x * kScatWarps + (threadIdx.x >> 5); chunk < nchunks; chunk += warps_total) {
+        const uint32_t u = chunk * 32 + lane;
+        const bool have = u < R;
+        uint32_t r = 0, beg = 0, end = 0;
+        if (have) {
+            r = p.urow[u];
+            beg = __ldg(p.off + r);
+            end = __ldg(p.off + r + 1);
+            p.rows_out[u] = (int64_t)r;
+        }
+        const int nrows = min(32u, R - chunk * 32);
+        const uint32_t e_begin = __shfl_sync(kFull, beg, 0);
+        const uint32_t e_end = __shfl_sync(kFull, end, nrows - 1);
+
+        int cur = 0;                                             // row (0..nrows-1) being accumulated
+        uint32_t cur_end = __shfl_sync(kFull, end, 0);
+        float4 acc[VPL];
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0, 0, 0, 0);
+        float csum = 0.f;
+
+        auto flush = [&](int row_in_chunk) {
+            const uint32_t rr = __shfl_sync(kFull, r, row_in_chunk);
+            const size_t orow = p.dense ? (size_t)rr : (size_t)chunk * 32 + row_in_chunk;
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) {
+                if (act[t]) {
+                    const int col = lane * 4 + t * 128;
+                    float4 a = acc[t];
+                    if (p.euclid) {
+                        float4 wv = ldg128(p.w + (size_t)rr * D + col);
+                        a.x = 2.f * (a.x - csum * wv.x); a.y = 2.f * (a.y - csum * wv.y);
+                        a.z = 2.f * (a.z - csum * wv.z); a.w = 2.f * (a.w - csum * wv.w);
+                    }
+                    float* dst = p.vals + orow * D + col;
+                    if (p.accumulate) {
+                        float4 o = *reinterpret_cast<const float4*>(dst);
+                        a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                    }
+                    stg128_stream(dst, a);
+                }
+                acc[t] = make_float4(0, 0, 0, 0);
+            }
+            csum = 0.f;
+        };
+
+        for (uint32_t eb = e_begin; eb < e_end; eb += 32) {
+            const uint32_t e = eb + lane;
+            uint32_t bq = 0; float c = 0.f;
+            if (e < e_end) {
+                uint64_t en = p.ent[e];
+                uint32_t lo = (uint32_t)en;
+                float val = __uint_as_float((uint32_t)(en >> 32));
+                bq = lo & 0x7FFFFFFFu;
+                c = (lo & kDirect) ? val : expf(val - __ldg(p.lse + bq)) * p.ssm_scale;
+            }
+            const int cnt = min(32u, e_end - eb);
+            for (int t0 = 0; t0 < cnt; t0 += 8) {
+                // issue up to 8 independent source-row loads, then fold them in order
+                float4 v[8][VPL];
+                float cc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int t = t0 + k;
+                    const int tt = t < cnt ? t : cnt - 1;
+                    const uint32_t bt = __shfl_sync(kFull, bq, tt);
+                    cc[k] = (t < cnt) ? __shfl_sync(kFull, c, tt) : 0.f;
+                    const float* srow = p.src + (size_t)bt * D + lane * 4;
+#pragma unroll
+                    for (int x = 0; x < VPL; ++x)
+                        v[k][x] = (act[x] && t < cnt) ? ldg128(srow + x * 128) : make_float4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int t = t0 + k;
+                    if (t < cnt) {                                   // warp-uniform
+                        const uint32_t eidx = eb + t;
+                        while (eidx >= cur_end && cur < nrows - 1) { // crossed into the next row(s)
+                            flush(cur);
+                            ++cur;
+                            cur_end = __shfl_sync(kFull, end, cur);
+                        }
+#pragma unroll
+                        for (int x = 0; x < VPL; ++x) fma4(acc[x], cc[k], v[k][x]);
+                        csum += cc[k];
+                    }
+                }
+            }
+        }
+        if (nrows > 0) {
+            // rows in a chunk always have >= 1 entry, so `cur` is the last row with pending data
+            while (cur < nrows) { flush(cur); ++cur; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+loss_sum_kernel(const float* __restrict__ part, int B, float* __restrict__ loss) {
+    __shared__ double sh[256];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < B; i += 256) a += (double)part[i];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = (float)sh[0];
+}
+
+int32_t launch_scatter(const ScatterParams& p, int64_t cap_rows, cudaStream_t st) {
+    if (cap_rows <= 0) return 0;
+    int64_t chunks = cdiv(cap_rows, 32);
+    int64_t blocks = cdiv(chunks, kScatWarps);
+    int64_t max_blocks = (int64_t)sm_count() * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (p.D <= 128) scatter_kernel<1><<<(unsigned)blocks, kScatWarps * 32, 0, st>>>(p);
+    else if (p.D <= 256) scatter_kernel<2><<<(unsigned)blocks, kScatWarps * 32, 0, st>>>(p);
+    else if (p.D <= 512) scatter_kernel<4><<<(unsigned)blocks, kScatWarps * 32, 0, st>>>(p);
+    else { set_error("embedding dim %d > 512 is not supported", p.D); return RSB200_EUNSUPPORTED; }
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int32_t launch_loss_sum(const float* part, int B, float* loss, cudaStream_t st) {
+    loss_sum_kernel<<<1, 256, 0, st>>>(part, B, loss);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rsb

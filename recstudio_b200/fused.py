@@ -1,0 +1,153 @@
+"""Host side of the fused retriever training step (rsb200_pair_step).
+
+``PairWorkspace`` owns the device buffers (torch tensors, allocated once per
+problem shape); ``pair_step`` fills the C argument block and enqueues the
+phases on the current CUDA stream.  Nothing here computes: all arithmetic is in
+librsb200.so.
+
+Reference path replaced: BaseRetriever.forward (sampler branch) +
+training_step + loss.backward()
+(recstudio/model/basemodel/baseretriever.py:142-176,399-404, recommender.py:638).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (LOSS_BPR, LOSS_SSM, PHASE_ALL, SCORE_EUCLID, SCORE_IP, SINK_COMPACT, SINK_DENSE,  # noqa: F401
+                   PairArgs, PairSizes, check, lib, ptr, stream_ptr)
+
+
+class PairWorkspace:
+    """Device buffers of one (num_items, num_users, B, n, d) problem.
+
+    sink = 'compact': gradients come back as (rows[R] int64 ascending, vals[R, d]) per
+    table -- a coalesced sparse-COO gradient; capacity is the worst case
+    min(touches, rows).  sink = 'dense': the caller passes dense [rows, d] gradient
+    buffers to ``pair_step`` (reference-compatible ``weight.grad``).
+    """
+
+    def __init__(self, num_items: int, num_users: int, B: int, n: int, d: int, device,
+                 sink: str = "compact", want_scores: bool = False, cap_item: Optional[int] = None):
+        _lib.require_cuda()
+        self.device = torch.device(device)
+        self.shape = (num_items, num_users, B, n, d)
+        self.sink = sink
+        sz = PairSizes()
+        check(lib().rsb200_pair_workspace_sizes(num_items, num_users, B, n, d, C.byref(sz)), "pair_workspace_sizes")
+        self.sizes = sz
+        dev = self.device
+        i32, u32, i64, f32 = torch.int32, torch.int32, torch.int64, torch.float32   # torch has no uint32 arithmetic: same bytes
+
+        def buf(nelem, dtype):
+            return torch.empty(max(int(nelem), 1), dtype=dtype, device=dev)
+
+        self.off_item = buf(sz.off_item, u32)
+        self.off_user = buf(sz.off_user, u32)
+        self.neg32_buf = buf(sz.neg32_buf, i32)
+        self.slot_neg = buf(sz.slot_neg, u32)
+        self.slot_pos = buf(sz.slot_pos, u32)
+        self.slot_user = buf(sz.slot_user, u32)
+        self.ent_item = buf(sz.ent_item, i64)
+        self.ent_user = buf(sz.ent_user, i64)
+        self.cap_item = int(cap_item) if cap_item is not None else int(sz.cap_item)
+        self.cap_user = int(sz.cap_user)
+        self.urow_item = buf(self.cap_item, u32)
+        self.urow_user = buf(self.cap_user, u32)
+        self.q_buf = buf(sz.q_buf, f32)
+        self.dq_buf = buf(sz.dq_buf, f32)
+        self.loss_part = buf(sz.loss_part, f32)
+        self.lse = buf(sz.lse, f32)
+        self.scan_tmp = buf(sz.scan_tmp, i64)
+        self.err_flag = torch.zeros(1, dtype=i32, device=dev)
+        self.totals = torch.zeros(4, dtype=i32, device=dev)
+        self.loss = torch.zeros(1, dtype=f32, device=dev)
+        self.item_rows = buf(self.cap_item, i64)
+        self.user_rows = buf(self.cap_user, i64)
+        if sink == "compact":
+            self.item_vals = torch.empty(self.cap_item, d, dtype=f32, device=dev)
+            self.user_vals = torch.empty(self.cap_user, d, dtype=f32, device=dev)
+        else:
+            self.item_vals = None
+            self.user_vals = None
+        self.pos_score = torch.empty(max(B, 1), dtype=f32, device=dev) if want_scores else None
+        self.neg_score = torch.empty(max(B, 1), max(n, 1), dtype=f32, device=dev) if want_scores else None
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
+
+
+def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, user: torch.Tensor,
+              pos: torch.Tensor, neg: torch.Tensor, loss_kind: int, score_kind: int,
+              logq_pos: Optional[torch.Tensor] = None, logq_neg: Optional[torch.Tensor] = None,
+              phases: int = PHASE_ALL, grad_scale: float = 1.0, accumulate: bool = False,
+              dense_item_grad: Optional[torch.Tensor] = None, dense_user_grad: Optional[torch.Tensor] = None,
+              variant: int = 0):
+    """Enqueue the selected phases of the fused step on the current stream.
+
+    Returns the 0-dim loss tensor (a view of ``ws.loss``).  Gradients are left in
+    ``ws.item_rows/item_vals`` and ``ws.user_rows/user_vals`` (first ``ws.totals[1]`` /
+    ``ws.totals[3]`` rows) or in the dense buffers.
+    """
+    num_items, num_users, B, n, d = ws.shape
+    for t, name in ((w_item, "w_item"), (w_user, "w_user"), (user, "user"), (pos, "pos"), (neg, "neg")):
+        if not t.is_cuda or not t.is_contiguous():
+            raise _lib.Rsb200Error("%s must be a contiguous CUDA tensor (no CPU fallback)" % name)
+    if w_item.shape != (num_items, d) or w_user.shape != (num_users, d) or w_item.dtype != torch.float32:
+        raise _lib.Rsb200Error("table shape/dtype does not match the workspace")
+    if user.shape != (B,) or pos.shape != (B,) or tuple(neg.shape) != (B, n):
+        raise _lib.Rsb200Error("batch shape does not match the workspace: user %s pos %s neg %s, expected B=%d n=%d"
+                               % (tuple(user.shape), tuple(pos.shape), tuple(neg.shape), B, n))
+    if user.dtype != torch.int64 or pos.dtype != torch.int64:
+        raise _lib.Rsb200Error("user / pos ids must be int64 (what the reference's batches hold)")
+    a = PairArgs()
+    a.w_item, a.w_user, a.user, a.pos = ptr(w_item), ptr(w_user), ptr(user), ptr(pos)
+    if neg.dtype == torch.int64:
+        a.neg_i64, a.neg_i32 = ptr(neg), 0
+    elif neg.dtype == torch.int32:
+        a.neg_i64, a.neg_i32 = 0, ptr(neg)
+    else:
+        raise _lib.Rsb200Error("neg ids must be int64 or int32")
+    if logq_pos is not None:
+        logq_pos = logq_pos.to(torch.float32).contiguous()     # UniformSampler hands out int64 zeros
+    if logq_neg is not None:
+        logq_neg = logq_neg.to(torch.float32).contiguous()
+    a.logq_pos, a.logq_neg = ptr(logq_pos), ptr(logq_neg)
+    a.loss, a.pos_score, a.neg_score = ptr(ws.loss), ptr(ws.pos_score), ptr(ws.neg_score)
+    dense = ws.sink == "dense"
+    if dense:
+        if dense_item_grad is None or dense_user_grad is None:
+            raise _lib.Rsb200Error("dense sink needs dense_item_grad / dense_user_grad")
+        if tuple(dense_item_grad.shape) != (num_items, d) or tuple(dense_user_grad.shape) != (num_users, d):
+            raise _lib.Rsb200Error("dense gradient buffers have the wrong shape")
+        a.item_vals, a.user_vals = ptr(dense_item_grad), ptr(dense_user_grad)
+    else:
+        a.item_vals, a.user_vals = ptr(ws.item_vals), ptr(ws.user_vals)
+    a.item_rows, a.user_rows, a.totals = ptr(ws.item_rows), ptr(ws.user_rows), ptr(ws.totals)
+    a.off_item, a.off_user, a.neg32_buf = ptr(ws.off_item), ptr(ws.off_user), ptr(ws.neg32_buf)
+    a.slot_neg, a.slot_pos, a.slot_user = ptr(ws.slot_neg), ptr(ws.slot_pos), ptr(ws.slot_user)
+    a.ent_item, a.ent_user = ptr(ws.ent_item), ptr(ws.ent_user)
+    a.urow_item, a.urow_user = ptr(ws.urow_item), ptr(ws.urow_user)
+    a.q_buf, a.dq_buf, a.loss_part, a.lse = ptr(ws.q_buf), ptr(ws.dq_buf), ptr(ws.loss_part), ptr(ws.lse)
+    a.scan_tmp, a.err_flag = ptr(ws.scan_tmp), ptr(ws.err_flag)
+    a.num_items, a.num_users, a.B, a.n, a.d = num_items, num_users, B, n, d
+    a.cap_item, a.cap_user, a.scan_tmp_elems = ws.cap_item, ws.cap_user, ws.scan_tmp.numel()
+    a.grad_scale = float(grad_scale)
+    a.loss_kind, a.score_kind = int(loss_kind), int(score_kind)
+    a.sink, a.accumulate, a.variant = (SINK_DENSE if dense else SINK_COMPACT), int(bool(accumulate)), int(variant)
+    with torch.cuda.device(w_item.device):
+        check(lib().rsb200_pair_step(C.byref(a), int(phases), stream_ptr()), "pair_step")
+    # keep temporaries referenced by the async launch alive until the stream catches up
+    ws._keepalive = (logq_pos, logq_neg, neg, user, pos)
+    return ws.loss[0]
+
+
+def sparse_grads(ws: PairWorkspace):
+    """Host-synchronising read-out of the compact gradients:
+    ((item_rows[R], item_vals[R,d]), (user_rows[Ru], user_vals[Ru,d]))."""
+    tot = ws.totals.tolist()
+    ri, ru = tot[1], tot[3]
+    return (ws.item_rows[:ri], ws.item_vals[:ri]), (ws.user_rows[:ru], ws.user_vals[:ru])
