@@ -52,8 +52,8 @@ extern "C" {
 /* phases of rsb200_pair_step (bit mask) */
 #define RSB200_PHASE_COUNT   1   /* group touched rows: histogram + slot assignment      */
 #define RSB200_PHASE_SCAN    2   /* exclusive scan -> CSR offsets + unique-row list       */
-#define RSB200_PHASE_FWD     4   /* fused gather -> score -> loss -> coefficient emit     */
-#define RSB200_PHASE_SCATTER 8   /* segmented (row-grouped) gradient accumulate + loss sum*/
+#define RSB200_PHASE_FWD     4   /* fused gather -> score -> loss -> coefficient emit + loss sum */
+#define RSB200_PHASE_SCATTER 8   /* segmented (row-grouped) gradient accumulate           */
 #define RSB200_PHASE_ALL     15
 
 /* gradient sinks for PHASE_SCATTER */
@@ -62,6 +62,8 @@ extern "C" {
 
 /* ------------------------------------------------------------------------- */
 int32_t     rsb200_version(void);
+/* number of kernels this library has launched in this process (statistics only) */
+uint64_t    rsb200_launch_count(void);
 const char* rsb200_last_error(void);
 /* sm_count / max_threads_per_sm of the CURRENT device (they fix the Philox
  * element<->counter mapping of torch's CUDA generator, see below). */
@@ -137,6 +139,8 @@ typedef struct rsb200_pair_args {
     const int32_t* neg_i32;     /* [B, n] or NULL */
     const float*   logq_pos;    /* [B]    or NULL (= 0, UniformSampler)              */
     const float*   logq_neg;    /* [B, n] or NULL (= 0)                               */
+    const float*   grad_scale_dev; /* [1] device-resident upstream gradient multiplied into every gradient row
+                                      by PHASE_SCATTER (autograd's grad_output), or NULL (= 1)             */
     /* outputs */
     float*         loss;        /* [1]  mean loss                                     */
     float*         pos_score;   /* [B]    or NULL                                     */
@@ -203,6 +207,14 @@ int32_t rsb200_scatter_add_rows(float* dw, int64_t num_rows, int64_t d,
 int32_t rsb200_score_ids(int32_t score_kind, const float* q /* [B,d] */, const float* w, int64_t num_rows,
                          int64_t d, const int64_t* ids /* [B, n] */, int64_t B, int64_t n,
                          float* out /* [B, n] */, void* stream);
+
+/* Q1 / Q2 standalone on an already gathered [B, n, d] item tensor (per-row branches of
+ * scorer.py:10-14; n = 1 covers ([B,D],[B,D])) and its backward. */
+int32_t rsb200_score_dense(int32_t score_kind, const float* q /* [B,d] */, const float* items /* [B,n,d] */,
+                           int64_t B, int64_t n, int64_t d, float* out /* [B,n] */, void* stream);
+int32_t rsb200_score_dense_bwd(int32_t score_kind, const float* q, const float* items, const float* g /* [B,n] */,
+                               int64_t B, int64_t n, int64_t d, float* dq /* [B,d] */, float* ditems /* [B,n,d] */,
+                               void* stream);
 
 /* -------------------------------------------------------------------------
  * L1 / L2 standalone on score tensors (for mixing with reference plugins):

@@ -90,6 +90,7 @@ def lib():
         L.rsb200_sizeof_pair_args.restype = C.c_size_t
         if L.rsb200_sizeof_pair_args() != C.sizeof(PairArgs):
             raise Rsb200Error('rsb200_pair_args layout mismatch between rsb200.h and librsb200.so: rebuild')
+        L.rsb200_launch_count.restype = C.c_uint64
         L.rsb200_philox_counter_offset.restype = C.c_int64
         L.rsb200_philox_counter_offset.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         L.rsb200_topk_workspace_bytes.restype = C.c_size_t
@@ -108,6 +109,8 @@ def lib():
             "rsb200_gather_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_scatter_add_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_score_ids": [i32, v, v, i64, i64, v, i64, i64, v, v],
+            "rsb200_score_dense": [i32, v, v, i64, i64, i64, v, v],
+            "rsb200_score_dense_bwd": [i32, v, v, v, i64, i64, i64, v, v, v],
             "rsb200_pair_loss": [i32, v, v, v, v, i64, i64, v, v, v, v, v],
             "rsb200_topk_full": [i32, v, v, i64, i64, i64, i64, v, i64, v, v, v, C.c_size_t, v],
             "rsb200_fullsoftmax_fwd_bwd": [v, v, v, i64, i64, i64, v, v, v, v, C.c_size_t, v],

@@ -1,12 +1,16 @@
 // api.cu -- C-ABI entry points of librsb200.so (see include/rsb200.h) and host-side glue.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace rsb {
 
 static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -32,6 +36,7 @@ int sm_count() {
 using namespace rsb;
 
 extern "C" int32_t rsb200_version(void) { return RSB200_VERSION; }
+extern "C" uint64_t rsb200_launch_count(void) { return g_launches.load(); }
 extern "C" size_t rsb200_sizeof_pair_args(void) { return sizeof(rsb200_pair_args); }
 extern "C" const char* rsb200_last_error(void) { return g_err; }
 
@@ -145,11 +150,13 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
         if (rc) return rc;
+        rc = launch_loss_sum(a->loss_part, (int)B, a->loss, st);
+        if (rc) return rc;
     }
     if (phases & RSB200_PHASE_SCATTER) {
         ScatterParams s;
         s.off = a->off_item; s.urow = a->urow_item; s.totals = a->totals; s.ent = a->ent_item; s.src = a->q_buf;
-        s.lse = a->lse; s.w = a->w_item; s.rows_out = a->item_rows; s.vals = a->item_vals; s.D = (int)a->d;
+        s.lse = a->lse; s.w = a->w_item; s.gscale = a->grad_scale_dev; s.rows_out = a->item_rows; s.vals = a->item_vals; s.D = (int)a->d;
         s.cap = a->cap_item;
         s.ssm_scale = (float)((double)a->grad_scale / (double)(B > 0 ? B : 1));
         s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = a->score_kind == RSB200_SCORE_EUCLID;
@@ -160,8 +167,6 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         u.lse = nullptr; u.w = a->w_user; u.rows_out = a->user_rows; u.vals = a->user_vals; u.cap = a->cap_user;
         u.euclid = 0;
         rc = launch_scatter(u, a->cap_user, st);
-        if (rc) return rc;
-        rc = launch_loss_sum(a->loss_part, (int)B, a->loss, st);
         if (rc) return rc;
     }
     return 0;

@@ -40,11 +40,13 @@ void set_error(const char* fmt, ...);   // api.cu (thread-local buffer)
             rsb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
             return (int32_t)_e;                                                           \
         }                                                                                 \
+        rsb::note_launch();                                                               \
     } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+void note_launch();   // api.cu: statistics counter behind rsb200_launch_count()
 int sm_count();   // api.cu: multiProcessorCount of the current device (cached per device)
 
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;      // touch of the padding row / invalid id: no gradient entry

@@ -26,6 +26,7 @@ struct ScatterParams {
     const float* src;         // [B, D]
     const float* lse;         // [B] or null
     const float* w;           // table (Euclid only)
+    const float* gscale;      // [1] device upstream gradient or null
     int64_t* rows_out;        // [R]
     float* vals;              // compact [R, D] or dense [num_rows, D]
     int64_t cap;              // capacity of urow / rows_out

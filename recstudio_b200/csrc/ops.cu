@@ -174,3 +174,84 @@ extern "C" int32_t rsb200_pair_loss(int32_t loss_kind, const float* pos_score, c
     RSB_LAUNCH_CHECK();
     return launch_loss_sum(loss_part, (int)B, loss, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// Q1/Q2 on an already gathered [B, n, d] tensor (standalone scorer plugins) + backward.
+namespace rsb {
+
+template <int SCORE>
+__global__ void __launch_bounds__(256)
+score_dense_kernel(const float* __restrict__ q, const float* __restrict__ items, int64_t B, int64_t n, int D,
+                   float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= B * n) return;
+    const float* qr = q + (size_t)(i / n) * D;
+    const float* vr = items + (size_t)i * D;
+    float a = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+        float4 x = ldg128(qr + c), y = ldg128_stream(vr + c);
+        a += (SCORE == RSB200_SCORE_IP) ? dot4(x, y) : sqdist4(x, y);
+    }
+    a = warp_sum_f(a);
+    if (lane == 0) out[i] = (SCORE == RSB200_SCORE_IP) ? a : -a;
+}
+
+// one warp per query: ditems[b,j,:] = g q (IP) | 2 g (q - v) (EU); dq[b,:] = sum_j g v | 2 g (v - q)
+template <int SCORE>
+__global__ void __launch_bounds__(256)
+score_dense_bwd_kernel(const float* __restrict__ q, const float* __restrict__ items, const float* __restrict__ g,
+                       int64_t B, int64_t n, int D, float* __restrict__ dq, float* __restrict__ ditems) {
+    const int lane = threadIdx.x & 31;
+    int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    for (int c = lane * 4; c < D; c += 128) {
+        float4 x = ldg128(q + (size_t)b * D + c);
+        float4 acc = make_float4(0, 0, 0, 0);
+        for (int64_t j = 0; j < n; ++j) {
+            const float gj = g[(size_t)b * n + j];
+            const size_t o = ((size_t)b * n + j) * D + c;
+            float4 v = ldg128_stream(items + o);
+            float4 dv;
+            if (SCORE == RSB200_SCORE_IP) {
+                dv = make_float4(gj * x.x, gj * x.y, gj * x.z, gj * x.w);
+                fma4(acc, gj, v);
+            } else {
+                float4 df = make_float4(x.x - v.x, x.y - v.y, x.z - v.z, x.w - v.w);
+                dv = make_float4(2.f * gj * df.x, 2.f * gj * df.y, 2.f * gj * df.z, 2.f * gj * df.w);
+                fma4(acc, -2.f * gj, df);
+            }
+            if (ditems) stg128_stream(ditems + o, dv);
+        }
+        if (dq) *reinterpret_cast<float4*>(dq + (size_t)b * D + c) = acc;
+    }
+}
+
+}  // namespace rsb
+
+extern "C" int32_t rsb200_score_dense(int32_t score_kind, const float* q, const float* items, int64_t B, int64_t n,
+                                      int64_t d, float* out, void* stream) {
+    RSB_REQUIRE(q && items && out && aligned16(q) && aligned16(items), RSB200_EINVAL, "null / misaligned pointer");
+    RSB_REQUIRE(d >= 4 && d % 4 == 0 && B >= 0 && n >= 0, RSB200_EINVAL, "bad shape");
+    RSB_REQUIRE(score_kind == RSB200_SCORE_IP || score_kind == RSB200_SCORE_EUCLID, RSB200_EINVAL, "bad score_kind");
+    if (B * n == 0) return 0;
+    unsigned grid = (unsigned)cdiv(B * n, 8);
+    if (score_kind == RSB200_SCORE_IP) score_dense_kernel<RSB200_SCORE_IP><<<grid, 256, 0, (cudaStream_t)stream>>>(q, items, B, n, (int)d, out);
+    else score_dense_kernel<RSB200_SCORE_EUCLID><<<grid, 256, 0, (cudaStream_t)stream>>>(q, items, B, n, (int)d, out);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t rsb200_score_dense_bwd(int32_t score_kind, const float* q, const float* items, const float* g,
+                                          int64_t B, int64_t n, int64_t d, float* dq, float* ditems, void* stream) {
+    RSB_REQUIRE(q && items && g && aligned16(q) && aligned16(items) && aligned16(dq) && aligned16(ditems), RSB200_EINVAL,
+                "null / misaligned pointer");
+    RSB_REQUIRE(d >= 4 && d % 4 == 0 && B >= 0 && n >= 0, RSB200_EINVAL, "bad shape");
+    RSB_REQUIRE(score_kind == RSB200_SCORE_IP || score_kind == RSB200_SCORE_EUCLID, RSB200_EINVAL, "bad score_kind");
+    if (B == 0) return 0;
+    unsigned grid = (unsigned)cdiv(B, 8);
+    if (score_kind == RSB200_SCORE_IP) score_dense_bwd_kernel<RSB200_SCORE_IP><<<grid, 256, 0, (cudaStream_t)stream>>>(q, items, g, B, n, (int)d, dq, ditems);
+    else score_dense_bwd_kernel<RSB200_SCORE_EUCLID><<<grid, 256, 0, (cudaStream_t)stream>>>(q, items, g, B, n, (int)d, dq, ditems);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}

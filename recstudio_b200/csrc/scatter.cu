@@ -28,6 +28,7 @@ scatter_kernel(const ScatterParams p) {
     const int D = p.D;
     const uint32_t R = (uint32_t)min((int64_t)p.totals[1], p.cap);
     const uint32_t nchunks = (R + 31) / 32;
+    const float gs = p.gscale ? __ldg(p.gscale) : 1.0f;
     const uint32_t warps_total = gridDim.x * kScatWarps;
     bool act[VPL];
 #pragma unroll
@@ -67,6 +68,7 @@ scatter_kernel(const ScatterParams p) {
                         a.x = 2.f * (a.x - csum * wv.x); a.y = 2.f * (a.y - csum * wv.y);
                         a.z = 2.f * (a.z - csum * wv.z); a.w = 2.f * (a.w - csum * wv.w);
                     }
+                    a.x *= gs; a.y *= gs; a.z *= gs; a.w *= gs;
                     float* dst = p.vals + orow * D + col;
                     if (p.accumulate) {
                         float4 o = *reinterpret_cast<const float4*>(dst);

@@ -31,7 +31,8 @@ class PairWorkspace:
     """
 
     def __init__(self, num_items: int, num_users: int, B: int, n: int, d: int, device,
-                 sink: str = "compact", want_scores: bool = False, cap_item: Optional[int] = None):
+                 sink: str = "compact", want_scores: bool = False, cap_item: Optional[int] = None,
+                 alloc_vals: bool = True):
         _lib.require_cuda()
         self.device = torch.device(device)
         self.shape = (num_items, num_users, B, n, d)
@@ -67,7 +68,7 @@ class PairWorkspace:
         self.loss = torch.zeros(1, dtype=f32, device=dev)
         self.item_rows = buf(self.cap_item, i64)
         self.user_rows = buf(self.cap_user, i64)
-        if sink == "compact":
+        if sink == "compact" and alloc_vals:
             self.item_vals = torch.empty(self.cap_item, d, dtype=f32, device=dev)
             self.user_vals = torch.empty(self.cap_user, d, dtype=f32, device=dev)
         else:
@@ -85,7 +86,8 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
               logq_pos: Optional[torch.Tensor] = None, logq_neg: Optional[torch.Tensor] = None,
               phases: int = PHASE_ALL, grad_scale: float = 1.0, accumulate: bool = False,
               dense_item_grad: Optional[torch.Tensor] = None, dense_user_grad: Optional[torch.Tensor] = None,
-              variant: int = 0):
+              variant: int = 0, grad_scale_dev: Optional[torch.Tensor] = None,
+              item_vals: Optional[torch.Tensor] = None, user_vals: Optional[torch.Tensor] = None):
     """Enqueue the selected phases of the fused step on the current stream.
 
     Returns the 0-dim loss tensor (a view of ``ws.loss``).  Gradients are left in
@@ -125,7 +127,16 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
             raise _lib.Rsb200Error("dense gradient buffers have the wrong shape")
         a.item_vals, a.user_vals = ptr(dense_item_grad), ptr(dense_user_grad)
     else:
-        a.item_vals, a.user_vals = ptr(ws.item_vals), ptr(ws.user_vals)
+        # explicit per-step value buffers (autograd hand-off) or the workspace's persistent ones
+        iv = item_vals if item_vals is not None else ws.item_vals
+        uv = user_vals if user_vals is not None else ws.user_vals
+        if iv is None or uv is None or iv.shape[0] < ws.cap_item or uv.shape[0] < ws.cap_user:
+            raise _lib.Rsb200Error("compact sink needs item_vals [>=cap_item, d] / user_vals [>=cap_user, d]")
+        a.item_vals, a.user_vals = ptr(iv), ptr(uv)
+    if grad_scale_dev is not None:
+        if not grad_scale_dev.is_cuda or grad_scale_dev.dtype != torch.float32 or grad_scale_dev.numel() != 1:
+            raise _lib.Rsb200Error("grad_scale_dev must be a 1-element float32 CUDA tensor")
+    a.grad_scale_dev = ptr(grad_scale_dev)
     a.item_rows, a.user_rows, a.totals = ptr(ws.item_rows), ptr(ws.user_rows), ptr(ws.totals)
     a.off_item, a.off_user, a.neg32_buf = ptr(ws.off_item), ptr(ws.off_user), ptr(ws.neg32_buf)
     a.slot_neg, a.slot_pos, a.slot_user = ptr(ws.slot_neg), ptr(ws.slot_pos), ptr(ws.slot_user)
@@ -141,7 +152,7 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
     with torch.cuda.device(w_item.device):
         check(lib().rsb200_pair_step(C.byref(a), int(phases), stream_ptr()), "pair_step")
     # keep temporaries referenced by the async launch alive until the stream catches up
-    ws._keepalive = (logq_pos, logq_neg, neg, user, pos)
+    ws._keepalive = (logq_pos, logq_neg, neg, user, pos, grad_scale_dev)
     return ws.loss[0]
 
 

@@ -1,0 +1,386 @@
+"""Drop-in replacements for the reference's plugin surfaces on the retriever hot path.
+
+Every class subclasses the reference class it replaces (``iface.py`` resolves those to
+the real ``recstudio`` classes when importable) so that ``BaseRetriever(config,
+item_encoder=, query_encoder=, scorer=, sampler=, loss=)`` accepts them unchanged
+(recstudio/model/basemodel/baseretriever.py:14-46, recommender.py:48-54):
+
+  FusedEmbedding(nn.Embedding)                E1/E2   baseretriever.py:84,104
+  FusedUniformSampler(Sampler)                S1      recstudio/ann/sampler.py:81-114
+  FusedPopularSampler(Sampler)                S2      recstudio/ann/sampler.py:224-258
+  FusedInnerProductScorer / FusedEuclideanScorer      recstudio/model/scorer.py:5-17,28-34
+  FusedBPRLoss / FusedSampledSoftmaxLoss(PairwiseLoss) recstudio/model/loss_func.py:50-63,80-90
+  FusedRetrieverMixin                          R1/T1   baseretriever.py:142-192,374-404
+
+Each plugin is a correct standalone op (its own CUDA kernel + analytic backward) so any
+mix with reference plugins still works; ``FusedRetrieverMixin.training_step`` takes the
+single fused path (rsb200_pair_step) when it recognises the combination.  There is no
+CPU path: every op raises on non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib, fused, iface, sampling
+from ._lib import LOSS_BPR, LOSS_SSM, SCORE_EUCLID, SCORE_IP, check, lib, ptr, stream_ptr
+
+
+def _need_cuda(t: Tensor, what: str):
+    if not isinstance(t, Tensor) or not t.is_cuda:
+        raise _lib.Rsb200Error("%s must live on a CUDA device: recstudio_b200 has no CPU fallback" % what)
+
+
+# ============================================================================ E1 / E2
+class _GatherFn(torch.autograd.Function):
+    """F.embedding forward (gather) / embedding_dense_backward (scatter-add, row 0 skipped)."""
+
+    @staticmethod
+    def forward(ctx, weight: Tensor, ids: Tensor):
+        _need_cuda(weight, "embedding table")
+        ids_c = ids.to(device=weight.device, dtype=torch.int64).contiguous()
+        out = torch.empty(ids_c.shape + (weight.shape[1],), dtype=torch.float32, device=weight.device)
+        with torch.cuda.device(weight.device):
+            check(lib().rsb200_gather_rows(ptr(weight), weight.shape[0], weight.shape[1], ptr(ids_c), ids_c.numel(),
+                                           ptr(out), stream_ptr()), "gather_rows")
+        ctx.save_for_backward(ids_c)
+        ctx.wshape = tuple(weight.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (ids_c,) = ctx.saved_tensors
+        g = g.contiguous()
+        dw = torch.zeros(ctx.wshape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib().rsb200_scatter_add_rows(ptr(dw), ctx.wshape[0], ctx.wshape[1], ptr(ids_c), ids_c.numel(),
+                                                ptr(g), stream_ptr()), "scatter_add_rows")
+        return dw, None
+
+
+class FusedEmbedding(torch.nn.Embedding):
+    """``nn.Embedding(num, d, padding_idx=0)`` with CUDA gather / scatter kernels.
+
+    It IS an ``nn.Embedding`` (init.py:6,24,37 dispatches on that; ``_get_item_vector``
+    takes its O(1) ``weight[1:]`` path only for nn.Embedding, baseretriever.py:122-123),
+    ``.weight`` stays a live Parameter for ``state_dict`` / optimizers / ``model.to()``.
+    Accepts index tensors of any rank (SASRec calls it on [B, L], sasrec.py:42).
+    """
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: Optional[int] = 0, **kw):
+        if embedding_dim % 4 != 0:
+            raise _lib.Rsb200Error("embedding_dim must be a multiple of 4 (16-byte rows)")
+        if padding_idx not in (0, None):
+            raise _lib.Rsb200Error("only padding_idx=0 (the reference's convention) is supported")
+        super().__init__(num_embeddings, embedding_dim, padding_idx=0, **kw)
+
+    def forward(self, ids: Tensor) -> Tensor:
+        return _GatherFn.apply(self.weight, ids)
+
+
+# ============================================================================ S1 / S2
+class FusedUniformSampler(iface.Sampler):
+    """UniformSampler (sampler.py:81-114).  Indices are bit-identical to the reference's
+    ``torch.randint(1, N, (Q, n), device=cuda)`` for the same generator state, and the
+    log-probabilities are int64 zeros exactly like ``torch.zeros_like(ids)``."""
+
+    def forward(self, query, num_neg: int, pos_items: Optional[Tensor] = None, device=None):
+        if isinstance(query, int):
+            num_queries = query
+            device = pos_items.device if pos_items is not None else device
+            shape = (num_queries,)
+        else:
+            num_queries = int(np.prod(query.shape[:-1]))
+            device = query.device
+            shape = tuple(query.shape[:-1])
+        neg, _ = sampling.uniform_draw(self.num_items + 1, num_queries, num_neg, device)
+        neg = neg.reshape(*shape, -1)
+        neg_prob = torch.zeros_like(neg)
+        if pos_items is not None:
+            return torch.zeros_like(pos_items), neg, neg_prob
+        return neg, neg_prob
+
+    def compute_item_p(self, query, pos_items):
+        return torch.zeros_like(pos_items)
+
+    # fused-path hook: int32 ids only, no log-prob tensors (they are identically zero)
+    def fused_draw(self, num_queries: int, num_neg: int, device):
+        _, neg32 = sampling.uniform_draw(self.num_items + 1, num_queries, num_neg, device, want_i64=False, want_i32=True)
+        return neg32, None
+
+
+class FusedPopularSampler(iface.Sampler):
+    """PopularSamplerModel (sampler.py:224-258) including its two quirks: ``pop_count[0] = 1``
+    (padding id 0 is drawable) and ``pop_prob[-1] = 1.0`` applied after the cumsum.  The
+    tables are built with the very same torch ops as the reference constructor; the draw is
+    ``searchsorted(table, torch.rand(...))`` restated with a guide table (identical results)."""
+
+    def __init__(self, pop_count, scorer=None, mode: int = 0):
+        super().__init__(pop_count.shape[0], scorer)
+        with torch.no_grad():
+            pop_count = torch.tensor(pop_count, dtype=torch.float)
+            if mode == 0:
+                pop_count = torch.log(pop_count + 1)
+            elif mode == 1:
+                pop_count = torch.log(pop_count + 1) + 1e-6
+            elif mode == 2:
+                pop_count = pop_count ** 0.75
+            pop_count[0] = 1
+            self.register_buffer("pop_prob", pop_count / pop_count.sum())
+            self.register_buffer("table", torch.cumsum(self.pop_prob, dim=0))
+            self.pop_prob[-1] = 1.0
+        self._guide = None
+        self._guide_bits = 0
+
+    def _guide_for(self, device):
+        _need_cuda(self.table, "sampler table (call model.to(cuda))")
+        if self._guide is None or self._guide.device != self.table.device:
+            self._guide, self._guide_bits = sampling.build_guide(self.table)
+        return self._guide, self._guide_bits
+
+    def forward(self, query, num_neg: int, pos_items: Optional[Tensor] = None):
+        num_queries = int(np.prod(query.shape[:-1]))
+        guide, bits = self._guide_for(query.device)
+        neg, _, neg_prob = sampling.popular_draw(self.table, self.pop_prob, num_queries, num_neg, guide, bits)
+        neg = neg.reshape(*query.shape[:-1], -1)
+        neg_prob = neg_prob.reshape(*query.shape[:-1], -1)
+        if pos_items is not None:
+            return self.compute_item_p(query, pos_items), neg, neg_prob
+        return neg, neg_prob
+
+    def compute_item_p(self, query, pos_items):
+        return sampling.popular_logq(self.pop_prob, pos_items)
+
+    def fused_draw(self, num_queries: int, num_neg: int, device):
+        guide, bits = self._guide_for(device)
+        _, neg32, logq = sampling.popular_draw(self.table, self.pop_prob, num_queries, num_neg, guide, bits,
+                                               want_i64=False, want_i32=True)
+        return neg32, logq
+
+
+# ============================================================================ Q1 / Q2
+class _ScoreDenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query: Tensor, items: Tensor, kind: int):
+        q2 = query.reshape(-1, query.shape[-1]).contiguous()
+        B, d = q2.shape
+        it = items.reshape(B, -1, d).contiguous()
+        n = it.shape[1]
+        out = torch.empty(B, n, dtype=torch.float32, device=q2.device)
+        with torch.cuda.device(q2.device):
+            check(lib().rsb200_score_dense(kind, ptr(q2), ptr(it), B, n, d, ptr(out), stream_ptr()), "score_dense")
+        ctx.save_for_backward(q2, it)
+        ctx.kind, ctx.qshape, ctx.ishape = kind, query.shape, items.shape
+        return out.reshape(items.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        q2, it = ctx.saved_tensors
+        B, n, d = it.shape
+        g2 = g.reshape(B, n).contiguous()
+        dq = torch.empty_like(q2)
+        di = torch.empty_like(it)
+        with torch.cuda.device(q2.device):
+            check(lib().rsb200_score_dense_bwd(ctx.kind, ptr(q2), ptr(it), ptr(g2), B, n, d, ptr(dq), ptr(di),
+                                               stream_ptr()), "score_dense_bwd")
+        return dq.reshape(ctx.qshape), di.reshape(ctx.ishape), None
+
+
+def _score_forward(kind: int, query: Tensor, items: Tensor) -> Tensor:
+    """Shape dispatch of InnerProductScorer.forward (scorer.py:9-17): equal leading size =>
+    per-row branch (CUDA kernel), else the full-score [B,D]x[N,D]^T branch (a plain library
+    GEMM: cuBLAS through torch.matmul)."""
+    _need_cuda(query, "query")
+    _need_cuda(items, "items")
+    if query.size(0) == items.size(0):
+        if query.dim() == items.dim() or query.dim() + 1 == items.dim():
+            return _ScoreDenseFn.apply(query, items, kind)
+        raise _lib.Rsb200Error("unsupported scorer shapes %s x %s" % (tuple(query.shape), tuple(items.shape)))
+    if kind == SCORE_IP:
+        return torch.matmul(query, items.T)
+    out = 2 * torch.matmul(query, items.T)
+    out = out - torch.sum(torch.square(items), dim=-1)
+    out = out - torch.sum(torch.square(query), dim=-1, keepdim=True)
+    return out
+
+
+class FusedInnerProductScorer(iface.InnerProductScorer):
+    fused_kind = SCORE_IP
+
+    def forward(self, query, items):
+        return _score_forward(SCORE_IP, query, items)
+
+
+class FusedEuclideanScorer(iface.EuclideanScorer):
+    fused_kind = SCORE_EUCLID
+
+    def forward(self, query, items):
+        return _score_forward(SCORE_EUCLID, query, items)
+
+
+# ============================================================================ L1 / L2
+class _PairLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos_score: Tensor, neg_score: Tensor, lqp, lqn, kind: int):
+        _need_cuda(pos_score, "pos_score")
+        if pos_score.dim() != 1 or neg_score.dim() != 2 or neg_score.shape[0] != pos_score.shape[0]:
+            raise _lib.Rsb200Error("fused pairwise losses take pos_score [B] and neg_score [B, n] "
+                                   "(got %s, %s)" % (tuple(pos_score.shape), tuple(neg_score.shape)))
+        ps, ns = pos_score.contiguous().float(), neg_score.contiguous().float()
+        B, n = ns.shape
+        dev = ps.device
+        lqp = None if lqp is None else lqp.to(torch.float32).contiguous()
+        lqn = None if lqn is None else lqn.to(torch.float32).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        d_pos = torch.empty_like(ps)
+        d_neg = torch.empty_like(ns)
+        part = torch.empty(B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().rsb200_pair_loss(kind, ptr(ps), ptr(ns), ptr(lqp), ptr(lqn), B, n, ptr(loss), ptr(d_pos),
+                                         ptr(d_neg), ptr(part), stream_ptr()), "pair_loss")
+        ctx.save_for_backward(d_pos, d_neg)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        d_pos, d_neg = ctx.saved_tensors
+        return g * d_pos, g * d_neg, None, None, None
+
+
+class FusedBPRLoss(iface.PairwiseLoss):
+    """BPRLoss(dns=False) (loss_func.py:50-59): -mean_{b,j} logsigmoid(s+_b - s-_bj)."""
+    fused_kind = LOSS_BPR
+
+    def __init__(self, dns: bool = False):
+        super().__init__()
+        if dns:
+            raise _lib.Rsb200Error("BPRLoss(dns=True) is outside the fused path; use the reference class")
+        self.dns = False
+
+    def forward(self, label, pos_score, log_pos_prob, neg_score, log_neg_prob):
+        return _PairLossFn.apply(pos_score, neg_score, None, None, LOSS_BPR)
+
+
+class FusedSampledSoftmaxLoss(iface.PairwiseLoss):
+    """SampledSoftmaxLoss (loss_func.py:80-90) for 1-D positives."""
+    fused_kind = LOSS_SSM
+
+    def forward(self, label, pos_score, log_pos_prob, neg_score, log_neg_prob):
+        return _PairLossFn.apply(pos_score, neg_score, log_pos_prob, log_neg_prob, LOSS_SSM)
+
+
+# ============================================================================ R1: the fused step
+class _FusedStepFn(torch.autograd.Function):
+    """forward = PHASE_COUNT|SCAN|FWD (loss + gradient coefficients), backward = PHASE_SCATTER
+    (gradient rows), scaled by autograd's grad_output read on the device (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, w_item: Tensor, w_user: Tensor, host, ws, user, pos, neg32, lqp, lqn, loss_kind, score_kind):
+        loss = fused.pair_step(ws, w_item, w_user, user, pos, neg32, loss_kind, score_kind, logq_pos=lqp,
+                               logq_neg=lqn, phases=_lib.PHASE_COUNT | _lib.PHASE_SCAN | _lib.PHASE_FWD,
+                               dense_item_grad=w_item, dense_user_grad=w_user)   # sink buffers unused before SCATTER
+        ctx.host, ctx.ws = host, ws
+        ctx.args = (user, pos, neg32, lqp, lqn, loss_kind, score_kind)
+        ctx.save_for_backward(w_item, w_user)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        w_item, w_user = ctx.saved_tensors
+        ws, host = ctx.ws, ctx.host
+        user, pos, neg32, lqp, lqn, loss_kind, score_kind = ctx.args
+        g = g.reshape(1).to(torch.float32).contiguous()
+        mode = host.fused_grad
+        common = dict(logq_pos=lqp, logq_neg=lqn, phases=_lib.PHASE_SCATTER, grad_scale_dev=g)
+        if mode == "dense":       # reference-compatible: dense [N, d] gradients for dense optimizers
+            gi, gu = torch.zeros_like(w_item), torch.zeros_like(w_user)
+            fused.pair_step(ws, w_item, w_user, user, pos, neg32, loss_kind, score_kind, dense_item_grad=gi,
+                            dense_user_grad=gu, **common)
+            return gi, gu, None, None, None, None, None, None, None, None, None
+        d = w_item.shape[1]
+        iv = torch.empty(ws.cap_item, d, dtype=torch.float32, device=w_item.device)
+        uv = torch.empty(ws.cap_user, d, dtype=torch.float32, device=w_item.device)
+        fused.pair_step(ws, w_item, w_user, user, pos, neg32, loss_kind, score_kind, item_vals=iv, user_vals=uv, **common)
+        if mode == "rows":        # consumed by a row optimizer straight from the workspace (no host sync)
+            ws.row_grads = (ws.item_rows, iv, ws.user_rows, uv, ws.totals)
+            return None, None, None, None, None, None, None, None, None, None, None
+        tot = ws.totals.tolist()  # sparse COO hand-off needs the row counts on the host
+        ri, ru = tot[1], tot[3]
+        gi = torch.sparse_coo_tensor(ws.item_rows[:ri].unsqueeze(0).clone(), iv[:ri], size=w_item.shape, is_coalesced=True)
+        gu = torch.sparse_coo_tensor(ws.user_rows[:ru].unsqueeze(0).clone(), uv[:ru], size=w_user.shape, is_coalesced=True)
+        return gi, gu, None, None, None, None, None, None, None, None, None
+
+
+_FUSABLE_SAMPLERS = (FusedUniformSampler, FusedPopularSampler)
+_LOSS_KIND = {FusedBPRLoss: LOSS_BPR, FusedSampledSoftmaxLoss: LOSS_SSM}
+_SCORE_KIND = {FusedInnerProductScorer: SCORE_IP, FusedEuclideanScorer: SCORE_EUCLID}
+
+
+class FusedRetrieverMixin:
+    """Mix in FRONT of ``BaseRetriever`` (or ``MiniRetriever``): ``training_step`` takes the
+    single fused CUDA path when the plugin combination is one the kernels implement
+    (Embedding x {Uniform, Popular} x {IP, Euclid} x {BPR, SampledSoftmax},
+    ``sampling_method == 'none'``, 1-D ``item_id``, no history exclusion); anything else
+    falls through to the reference's own ``training_step`` on top of the standalone plugins.
+
+    ``fused_grad``: 'dense'  -> dense ``weight.grad`` (what the reference's dense Adam expects),
+                    'sparse' -> coalesced sparse-COO ``weight.grad`` (sgd / adagrad / sparse_adam),
+                    'rows'   -> gradients stay in the workspace for a row optimizer (no host sync).
+    """
+    fused_grad = "dense"
+
+    def _fused_combo(self, batch):
+        cfg = self.config["train"] if hasattr(self, "config") else {}
+        if cfg.get("sampling_method", "none") != "none" or cfg.get("excluding_hist", False):
+            return None
+        if type(self.sampler) not in _FUSABLE_SAMPLERS:
+            return None
+        lk, sk = _LOSS_KIND.get(type(self.loss_fn)), _SCORE_KIND.get(type(self.score_func))
+        if lk is None or sk is None:
+            return None
+        if not isinstance(self.item_encoder, torch.nn.Embedding) or not isinstance(self.query_encoder, torch.nn.Embedding):
+            return None
+        if len(getattr(self, "item_fields", [self.fiid])) != 1:
+            return None
+        if self.fuid not in batch or batch[self.fiid].dim() != 1:
+            return None
+        if not self.item_encoder.weight.is_cuda:
+            raise _lib.Rsb200Error("the fused retriever needs its tables on a CUDA device (no CPU fallback)")
+        return lk, sk
+
+    def _fused_ws(self, B: int, n: int):
+        cache = self.__dict__.setdefault("_fused_ws_cache", {})
+        wi, wu = self.item_encoder.weight, self.query_encoder.weight
+        key = (B, n, wi.shape, wu.shape, wi.device, self.fused_grad)
+        if key not in cache:
+            cache.clear()       # one live workspace per model: batch shape is stable within an epoch
+            cache[key] = fused.PairWorkspace(wi.shape[0], wu.shape[0], B, n, wi.shape[1], wi.device,
+                                             sink="dense" if self.fused_grad == "dense" else "compact", alloc_vals=False)
+        return cache[key]
+
+    def training_step(self, batch):
+        combo = self._fused_combo(batch)
+        if combo is None:
+            return super().training_step(batch)
+        loss_kind, score_kind = combo
+        wi, wu = self.item_encoder.weight, self.query_encoder.weight
+        user = batch[self.fuid].to(wi.device, non_blocking=True).contiguous()
+        pos = batch[self.fiid].to(wi.device, non_blocking=True).contiguous()
+        B, n = pos.numel(), int(self.neg_count)
+        ws = self._fused_ws(B, n)
+        neg32, lqn = self.sampler.fused_draw(B, n, wi.device)
+        lqp = self.sampler.compute_item_p(None, pos) if (lqn is not None and loss_kind == LOSS_SSM) else None
+        if loss_kind != LOSS_SSM:
+            lqn = None
+        return _FusedStepFn.apply(wi, wu, self, ws, user, pos, neg32, lqp, lqn, loss_kind, score_kind)
+
+    def fused_last_neg_id(self):
+        """int32 [B, n] negatives drawn by the last fused training_step (for inspection / parity tests)."""
+        cache = self.__dict__.get("_fused_ws_cache", {})
+        for ws in cache.values():
+            return ws._keepalive[2]
+        return None
