@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- interactions/sec of the fused retriever training step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Workload (config.workload): BASELINE configs[1] -- BPR, InnerProduct scorer, in-kernel
+UniformSampler, synthetic item table 10,000,001 x 128 fp32 (5.12 GB, >> the 126 MB L2, so no
+L2 flush is needed between iterations), user table 1,000,001 x 128, B = 8192 interactions x
+n = 1024 negatives per step.  One step = one pass of the hot path over one batch: negative
+draw -> row grouping -> fused gather/score/loss -> segmented gradient scatter (sparse rows).
+
+`value`  : device-resident batches, CUDA-event timed, barrier + sync on both sides, max over ranks.
+`e2e`    : the same metric through FusedRetriever.training_step on HOST (pinned) batches:
+           H2D of the batch + loss.backward() + D2H of the loss inside the timed region.
+`roofline`: the dominant kernel (pair_fwd_kernel) timed live with CUDA events on the launch
+           stream; achieved = (n+2)*d*4 bytes per interaction * B / duration.
+`cpu_baseline`: the reference path restated with the same ATen ops (oracle/, kind "port"),
+           timed on the host cores on a bounded sample of the same workload.
+
+N > 1: one process per GPU (torchrun), every rank owns a full replica of the tables and its
+own B interactions per step (weak scaling, "replicas": see DESIGN.md 8(e) for the row-sharded
+design that replaces this once the table exceeds one GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+N_ITEMS, N_USERS, DIM, BATCH, NEG = 10_000_001, 1_000_001, 128, 8192, 1024
+INIT_STD = 0.05
+CPU_SAMPLE_B = 512          # bounded CPU sample: same tables, B = 512 interactions per step
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(steps: int, warmup: int, sample_b: int = CPU_SAMPLE_B):
+    """The reference's own path on the host: F.embedding x3 -> score -> BPRLoss -> backward
+    (dense embedding_dense_backward), op for op (oracle/retriever.py:training_step_aten)."""
+    import torch
+    from oracle import retriever as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(2022)
+    wi = torch.empty(N_ITEMS, DIM).normal_(0, INIT_STD, generator=g); wi[0] = 0
+    wu = torch.empty(N_USERS, DIM).normal_(0, INIT_STD, generator=g); wu[0] = 0
+    wi.requires_grad_(True); wu.requires_grad_(True)
+    times = []
+    for it in range(warmup + steps):
+        user = torch.randint(1, N_USERS, (sample_b,), generator=g)
+        pos = torch.randint(1, N_ITEMS, (sample_b,), generator=g)
+        t0 = time.perf_counter()
+        neg = torch.randint(1, N_ITEMS, (sample_b, NEG))                       # UniformSampler on the host
+        wi.grad = None; wu.grad = None
+        q = torch.nn.functional.embedding(user, wu, padding_idx=0)
+        vp = torch.nn.functional.embedding(pos, wi, padding_idx=0)
+        vn = torch.nn.functional.embedding(neg, wi, padding_idx=0)
+        loss = R.bpr_loss(R.inner_product_score(q, vp), R.inner_product_score(q, vn))
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / max(len(times), 1)
+    val = sample_b / (ms / 1e3)
+    return {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+            "sample": "same tables (10,000,001 x 128 + 1,000,001 x 128 fp32), B=%d interactions x n=%d negatives per step, "
+                      "fwd + dense backward, %d warm-up + %d timed steps, torch %s CPU, %d threads"
+                      % (sample_b, NEG, warmup, steps, torch.__version__, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 5), min(max(args.warmup, 1), 2)
+    cb = cpu_reference_arm(steps, warmup)
+    line = {"impl": "reference", "metric": "interactions/sec (BPR 10M x d128 fused gather-score-loss-scatter)",
+            "value": cb["value"], "unit": "interactions/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: BPR, InnerProduct, UniformSampler, 10,000,001 x 128 items, "
+                                   "B=8192 x n=1024 (CPU arm times a bounded B=%d sample per step)" % CPU_SAMPLE_B},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from recstudio_b200 import _lib, build, fused, retriever, sampling
+    build.build()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the b200 arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+
+    model = retriever.build_synthetic(N_USERS, N_ITEMS, DIM, NEG, loss="bpr", scorer="ip", sampler="uniform",
+                                      fused_grad="rows", device=dev, init_std=INIT_STD, seed=2022 + rank)
+    wi, wu = model.item_encoder.weight.detach(), model.query_encoder.weight.detach()
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    users = torch.randint(1, N_USERS, (K + W, BATCH), device=dev, generator=gen)
+    poss = torch.randint(1, N_ITEMS, (K + W, BATCH), device=dev, generator=gen)
+    ws = fused.PairWorkspace(N_ITEMS, N_USERS, BATCH, NEG, DIM, dev)
+    pre = _lib.PHASE_COUNT | _lib.PHASE_SCAN
+    L = _lib.lib()
+
+    def step(i, ev=None):
+        _, neg32 = sampling.uniform_draw(N_ITEMS, BATCH, NEG, dev, want_i64=False, want_i32=True)
+        fused.pair_step(ws, wi, wu, users[i], poss[i], neg32, _lib.LOSS_BPR, _lib.SCORE_IP, phases=pre)
+        if ev:
+            ev[0].record()
+        fused.pair_step(ws, wi, wu, users[i], poss[i], neg32, _lib.LOSS_BPR, _lib.SCORE_IP, phases=_lib.PHASE_FWD)
+        if ev:
+            ev[1].record()
+        return fused.pair_step(ws, wi, wu, users[i], poss[i], neg32, _lib.LOSS_BPR, _lib.SCORE_IP, phases=_lib.PHASE_SCATTER)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = L.rsb200_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(K):
+        loss = step(W + i, evs[i])
+    t1.record()
+    barrier()
+    launches = L.rsb200_launch_count() - launches0
+    total_ms = t0.elapsed_time(t1)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    loss_val = float(loss.item())
+    unique_rows = int(ws.totals[1].item())
+
+    # ---- e2e: public plugin API, host (pinned) batches, H2D + D2H inside the timed region ----------
+    host_batches = [{"user_id": users[i].cpu().pin_memory(), "item_id": poss[i].cpu().pin_memory(),
+                     "rating": torch.ones(BATCH).pin_memory()} for i in range(K + W)]
+    h2d = sum(t.numel() * t.element_size() for t in host_batches[0].values())
+    for i in range(W):
+        b = model._to_device(dict(host_batches[i]), dev)
+        model.training_step(b).backward()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        b = model._to_device(dict(host_batches[W + i]), dev)          # recommender.py:596,699-714
+        lo = model.training_step(b)                                    # recommender.py:613
+        lo.backward()                                                  # recommender.py:638
+        _ = lo.item()                                                  # D2H of the step's result
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    e2e_ms = e0.elapsed_time(e1)
+
+    stats = torch.tensor([total_ms, e2e_ms, fwd_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, fwd_ms = stats.tolist()
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = world * BATCH * K / (total_ms / 1e3)
+        e2e = world * BATCH * K / (e2e_ms / 1e3)
+        alg_fwd = (NEG + 2) * DIM * 4 * BATCH                 # bytes one pair_fwd launch must read
+        achieved = alg_fwd / (fwd_ms / 1e3) / 1e9
+        step_alg = 2 * (NEG + 2) * DIM * 4 * BATCH
+        line = {"metric": "interactions/sec (BPR 10M x d128 fused gather-score-loss-scatter)", "value": value,
+                "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: BPR + InnerProduct + in-kernel UniformSampler, items 10,000,001 x 128, "
+                                       "users 1,000,001 x 128, B=8192, n=1024, sparse-row gradient sink",
+                           "global_batch": BATCH * world, "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                           "l2": "inputs (5.12 GB table, random rows) exceed the 126 MB L2; no flush needed"},
+                "e2e": {"value": e2e, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms / K, "api": "FusedRetriever.training_step(host batch) + loss.backward() + loss.item()"},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "pair_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": fwd_ms, "algorithmic_bytes_per_launch": alg_fwd,
+                             "step_achieved": step_alg / (total_ms / K / 1e3) / 1e9,
+                             "step_frac": step_alg / (total_ms / K / 1e3) / 1e9 / peak, "unique_item_rows": unique_rows},
+                "clocks": clk, "loss": loss_val}
+        traffic_file = os.path.join(REPO, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("pair_fwd_kernel")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu:
+            cb = cpu_reference_arm(steps=2, warmup=1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

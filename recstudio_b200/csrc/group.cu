@@ -113,27 +113,40 @@ scan_apply_kernel(uint32_t* __restrict__ cnt_off, int64_t num_rows, const uint64
                   uint32_t* __restrict__ urow, int64_t cap) {
     // thread t owns kScanPer CONSECUTIVE elements so that its local prefix is a serial sum
     int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kScanPer;
+    static_assert(kScanPer == 8, "vector path loads two uint4");
     uint32_t c[kScanPer];
     uint64_t acc = 0;
+    // cnt_off comes from a >=256-byte aligned allocation and base is a multiple of 8 elements
+    const bool full = base + kScanPer <= num_rows && (reinterpret_cast<uintptr_t>(cnt_off) & 15u) == 0;
+    if (full) {
+        const uint4 a = *reinterpret_cast<const uint4*>(cnt_off + base);
+        const uint4 b = *reinterpret_cast<const uint4*>(cnt_off + base + 4);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < kScanPer; ++k) {
-        int64_t i = base + k;
-        c[k] = (i < num_rows) ? cnt_off[i] : 0u;
-        acc += (uint64_t)c[k] + ((uint64_t)(c[k] != 0) << 32);
+        for (int k = 0; k < kScanPer; ++k) c[k] = (base + k < num_rows) ? cnt_off[base + k] : 0u;
     }
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) acc += (uint64_t)c[k] + ((uint64_t)(c[k] != 0) << 32);
     uint64_t total;
     uint64_t ex = block_excl_scan(acc, &total) + block_sums[blockIdx.x];
+    uint32_t o[kScanPer];
 #pragma unroll
     for (int k = 0; k < kScanPer; ++k) {
-        int64_t i = base + k;
-        if (i < num_rows) {
-            cnt_off[i] = (uint32_t)ex;
-            if (c[k] != 0) {
-                int64_t rank = (int64_t)(ex >> 32);
-                if (rank < cap) urow[rank] = (uint32_t)i;
-            }
+        o[k] = (uint32_t)ex;
+        if (c[k] != 0 && base + k < num_rows) {
+            const int64_t rank = (int64_t)(ex >> 32);
+            if (rank < cap) urow[rank] = (uint32_t)(base + k);
         }
         ex += (uint64_t)c[k] + ((uint64_t)(c[k] != 0) << 32);
+    }
+    if (full) {
+        *reinterpret_cast<uint4*>(cnt_off + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(cnt_off + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k)
+            if (base + k < num_rows) cnt_off[base + k] = o[k];
     }
 }
 

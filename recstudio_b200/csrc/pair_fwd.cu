@@ -18,12 +18,15 @@
 // 8-byte entry (query index, coefficient | logit) into the row-grouped list built by
 // group.cu; scatter.cu turns the list into gradient rows.
 //
-// Mapping: one query per CTA (8 warps x n/8 negatives) when n >= 128, else one query
+// Mapping: one query per CTA (8 warps x n/8 negatives) when n >= 256, else one query
 // per warp.  A warp streams its negatives in batches of 32 ids; rows are fetched LOADS
 // at a time with one 16-byte load per lane (a 512-B row at d = 128 is one fully
 // coalesced warp request), partial dot products of LOADS rows are reduced with a
 // transposed butterfly (LOADS + log2(32) - 1 shuffles instead of 5 per row), and the
 // online-softmax state (m, l, acc) of SSM is kept per warp and merged in shared memory.
+// PIPE = true software-pipelines the stream: the rows of group g+1 (and the ids of the
+// next batch) are in flight while group g is reduced, so every warp keeps 8-16 row
+// requests outstanding at all times (the kernel is bound by DRAM latency x parallelism).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -72,14 +75,124 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// VPL = float4 per lane per row (D <= 128*VPL); lanes whose columns are >= D are idle.
-template <int VPL, int LOSS, int SCORE, bool MULTI>
-__global__ void __launch_bounds__(kThreads, (VPL == 1) ? 3 : 2)
-pair_fwd_kernel(const FwdParams p) {
-    constexpr int LOADS = (VPL == 1) ? 8 : (VPL == 2 ? 4 : 2);   // rows fetched per group
-    constexpr int REP = 32 / LOADS;                               // lanes sharing one reduced row
-    constexpr int NG = 32 / LOADS;                                // groups per 32-id batch
+template <int VPL>
+struct Cfg {
+    static constexpr int LOADS = (VPL == 1) ? 8 : (VPL == 2 ? 4 : 2);   // rows fetched per group
+    static constexpr int REP = 32 / LOADS;                               // lanes sharing one reduced row
+    static constexpr int NG = 32 / LOADS;                                // groups per 32-id batch
+};
+
+// per-lane metadata of one batch of 32 negatives
+struct BatchMeta {
+    int id;           // row id (0 for lanes past the end)
+    uint32_t slot;    // position inside the row's entry segment, kNoSlot = no gradient entry
+    float lq;         // log Q(neg) (SSM)
+};
+
+template <int LOSS>
+__device__ __forceinline__ BatchMeta load_meta(const FwdParams& p, size_t rowbase, int jb, int j1, int lane) {
+    BatchMeta m;
+    const int j = jb + lane;
+    const bool valid = j < j1;
+    m.id = valid ? __ldg(p.neg + rowbase + j) : 0;
+    if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
+    m.slot = valid ? __ldg(p.slot_neg + rowbase + j) : kNoSlot;
+    m.lq = 0.f;
+    if (LOSS == RSB200_LOSS_SSM && p.logq_neg != nullptr && valid) m.lq = __ldg(p.logq_neg + rowbase + j);
+    return m;
+}
+
+template <int VPL>
+struct RowBuf {
+    float4 v[Cfg<VPL>::LOADS][VPL];
+};
+
+// fetch the LOADS rows of group g of a batch (ids live one per lane in `id`)
+template <int VPL>
+__device__ __forceinline__ void load_group(RowBuf<VPL>& buf, const FwdParams& p, int id, int g, int lane,
+                                           const bool (&act)[VPL]) {
+    constexpr int LOADS = Cfg<VPL>::LOADS;
+#pragma unroll
+    for (int k = 0; k < LOADS; ++k) {
+        const int rid = __shfl_sync(kFull, id, g * LOADS + k);
+        const float* row = p.w_item + (size_t)rid * p.D + lane * 4;
+#pragma unroll
+        for (int t = 0; t < VPL; ++t)
+            buf.v[k][t] = act[t] ? ldg128_stream(row + t * 128) : make_float4(0, 0, 0, 0);
+    }
+}
+
+template <int VPL>
+struct WarpState {
+    float4 acc[VPL];
+    float csum, lossacc;     // per-lane partials (every element is counted REP times)
+    float m_run, l_run;      // SSM online softmax (warp-uniform)
+    float val_out, sc_out;   // per-lane value / score of the element whose id this lane holds
+};
+
+// score + loss + dq accumulation of one group whose rows are in `buf`
+template <int VPL, int LOSS, int SCORE>
+__device__ __forceinline__ void compute_group(const RowBuf<VPL>& buf, WarpState<VPL>& st, const FwdParams& p,
+                                              const float4 (&q)[VPL], float sp, float lq, int g, int jb, int j1,
+                                              int lane) {
+    constexpr int LOADS = Cfg<VPL>::LOADS, REP = Cfg<VPL>::REP;
     constexpr float kRepInv = 1.0f / REP;
+    float pr[LOADS];
+#pragma unroll
+    for (int k = 0; k < LOADS; ++k) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < VPL; ++t)
+            a += (SCORE == RSB200_SCORE_IP) ? dot4(q[t], buf.v[k][t]) : sqdist4(q[t], buf.v[k][t]);
+        pr[k] = a;
+    }
+    float s = TransposeReduce<LOADS, 16>::run(pr, lane);
+    if (SCORE == RSB200_SCORE_EUCLID) s = -s;
+    const int e_own = g * LOADS + lane / REP;       // element (within the batch) this lane owns
+    const bool ev = (jb + e_own) < j1;
+    float wgt;                                        // weight of v in the dq accumulator
+    float value;                                      // what goes into the entry
+    if (LOSS == RSB200_LOSS_BPR) {
+        const float x = s - sp;
+        wgt = ev ? sigmoidf(x) * p.coef_scale : 0.f;
+        st.lossacc += ev ? softplusf(x) : 0.f;
+        st.csum += wgt;
+        value = wgt;
+    } else {
+        const float lq_e = __shfl_sync(kFull, lq, e_own);
+        const float z = ev ? (s - lq_e) : -INFINITY;
+        const float gm = warp_max(z);
+        const float m_new = fmaxf(st.m_run, gm);
+        // m_new == -inf only if nothing valid has been seen: keep everything at zero
+        const float scale = (m_new == -INFINITY) ? 1.f : expf(st.m_run - m_new);
+        wgt = (ev && m_new != -INFINITY) ? expf(z - m_new) : 0.f;
+        st.l_run = st.l_run * scale + warp_sum(wgt) * kRepInv;
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+            st.acc[t].x *= scale; st.acc[t].y *= scale; st.acc[t].z *= scale; st.acc[t].w *= scale;
+        }
+        st.m_run = m_new;
+        value = z;
+    }
+#pragma unroll
+    for (int k = 0; k < LOADS; ++k) {
+        const float wk = __shfl_sync(kFull, wgt, k * REP);
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) fma4(st.acc[t], wk, buf.v[k][t]);
+    }
+    // hand each element's value back to the lane that holds its id
+    const float tv = __shfl_sync(kFull, value, (lane % LOADS) * REP);
+    const float ts = __shfl_sync(kFull, s, (lane % LOADS) * REP);
+    if (lane / LOADS == g) { st.val_out = tv; st.sc_out = ts; }
+}
+
+// VPL = float4 per lane per row (D <= 128*VPL); lanes whose columns are >= D are idle.
+template <int VPL, int LOSS, int SCORE, bool MULTI, bool PIPE>
+__global__ void __launch_bounds__(kThreads, (VPL == 1 && !PIPE) ? 3 : 2)
+pair_fwd_kernel(const FwdParams p) {
+    constexpr int LOADS = Cfg<VPL>::LOADS, REP = Cfg<VPL>::REP, NG = Cfg<VPL>::NG;
+    constexpr float kRepInv = 1.0f / REP;
+    static_assert(NG % 2 == 0, "the pipelined loop alternates two row buffers");
 
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -109,6 +222,26 @@ pair_fwd_kernel(const FwdParams p) {
         q[t] = act[t] ? ldg128(p.w_user + (size_t)uid * D + col) : make_float4(0, 0, 0, 0);
         vp[t] = act[t] ? ldg128(p.w_item + (size_t)pid * D + col) : make_float4(0, 0, 0, 0);
     }
+
+    // this warp's slice of the negatives
+    const int n = p.n;
+    int j0 = 0, j1 = n;
+    if (MULTI) {
+        int per = ((n + kWarps - 1) / kWarps + 31) & ~31;   // multiple of 32 so batches stay aligned
+        j0 = min(n, warp * per);
+        j1 = min(n, j0 + per);
+    }
+    const size_t rowbase = (size_t)b * n;
+
+    // start the stream before the (dependent) positive-score reduction
+    BatchMeta cur = load_meta<LOSS>(p, rowbase, j0, j1, lane);
+    BatchMeta nxt = cur;
+    RowBuf<VPL> bufA, bufB;
+    if (PIPE) {
+        if (j0 < j1) load_group<VPL>(bufA, p, cur.id, 0, lane, act);
+        if (j0 + 32 < j1) nxt = load_meta<LOSS>(p, rowbase, j0 + 32, j1, lane);
+    }
+
     float sp = 0.f;
 #pragma unroll
     for (int t = 0; t < VPL; ++t) sp += (SCORE == RSB200_SCORE_IP) ? dot4(q[t], vp[t]) : sqdist4(q[t], vp[t]);
@@ -127,115 +260,69 @@ pair_fwd_kernel(const FwdParams p) {
         }
     }
 
-    // this warp's slice of the negatives
-    const int n = p.n;
-    int j0 = 0, j1 = n;
-    if (MULTI) {
-        int per = ((n + kWarps - 1) / kWarps + 31) & ~31;   // multiple of 32 so batches stay aligned
-        j0 = min(n, warp * per);
-        j1 = min(n, j0 + per);
-    }
-    const size_t rowbase = (size_t)b * n;
-
-    float4 acc[VPL];
+    WarpState<VPL> st;
 #pragma unroll
-    for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0, 0, 0, 0);
-    float csum = 0.f, lossacc = 0.f;          // per-lane partials (each element counted REP times)
-    float m_run = -INFINITY, l_run = 0.f;     // SSM online softmax (warp-uniform)
+    for (int t = 0; t < VPL; ++t) st.acc[t] = make_float4(0, 0, 0, 0);
+    st.csum = 0.f; st.lossacc = 0.f; st.m_run = -INFINITY; st.l_run = 0.f;
 
     for (int jb = j0; jb < j1; jb += 32) {
-        const int j = jb + lane;
-        const bool valid = j < j1;
-        int id = valid ? p.neg[rowbase + j] : 0;
-        if ((unsigned)id >= (unsigned)p.num_items) id = 0;
-        const uint32_t slot = valid ? p.slot_neg[rowbase + j] : kNoSlot;
-        float lq = 0.f;
-        if (LOSS == RSB200_LOSS_SSM && p.logq_neg != nullptr && valid) lq = p.logq_neg[rowbase + j];
+        const bool valid = (jb + lane) < j1;
         uint32_t epos = 0;
-        if (slot != kNoSlot) epos = __ldg(p.off_item + id) + slot;
-        float val_out = 0.f, sc_out = 0.f;
+        if (cur.slot != kNoSlot) epos = __ldg(p.off_item + cur.id) + cur.slot;   // consumed after the groups
+        st.val_out = 0.f; st.sc_out = 0.f;
 
+        if (PIPE) {
+            BatchMeta nn = nxt;                                   // ids of batch jb+64 (arrive a batch ahead)
+            if (jb + 64 < j1) nn = load_meta<LOSS>(p, rowbase, jb + 64, j1, lane);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            if (jb + g * LOADS < j1) {            // warp-uniform
-                float4 v[LOADS][VPL];
-#pragma unroll
-                for (int k = 0; k < LOADS; ++k) {
-                    int rid = __shfl_sync(kFull, id, g * LOADS + k);
-                    const float* row = p.w_item + (size_t)rid * D + lane * 4;
-#pragma unroll
-                    for (int t = 0; t < VPL; ++t)
-                        v[k][t] = act[t] ? ldg128_stream(row + t * 128) : make_float4(0, 0, 0, 0);
+            for (int g = 0; g < NG; g += 2) {
+                // group g lives in bufA; fetch g+1 into bufB, then reduce g
+                if (jb + (g + 1) * LOADS < j1) load_group<VPL>(bufB, p, cur.id, g + 1, lane, act);
+                if (jb + g * LOADS < j1) compute_group<VPL, LOSS, SCORE>(bufA, st, p, q, sp, cur.lq, g, jb, j1, lane);
+                // fetch g+2 (or group 0 of the next batch) into bufA, then reduce g+1
+                if (g + 2 < NG) {
+                    if (jb + (g + 2) * LOADS < j1) load_group<VPL>(bufA, p, cur.id, g + 2, lane, act);
+                } else if (jb + 32 < j1) {
+                    load_group<VPL>(bufA, p, nxt.id, 0, lane, act);
                 }
-                float pr[LOADS];
-#pragma unroll
-                for (int k = 0; k < LOADS; ++k) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int t = 0; t < VPL; ++t)
-                        a += (SCORE == RSB200_SCORE_IP) ? dot4(q[t], v[k][t]) : sqdist4(q[t], v[k][t]);
-                    pr[k] = a;
-                }
-                float s = TransposeReduce<LOADS, 16>::run(pr, lane);
-                if (SCORE == RSB200_SCORE_EUCLID) s = -s;
-                const int e_own = g * LOADS + lane / REP;       // element (within the batch) this lane owns
-                const bool ev = (jb + e_own) < j1;
-                float wgt;                                        // weight of v in the dq accumulator
-                float value;                                      // what goes into the entry
-                if (LOSS == RSB200_LOSS_BPR) {
-                    float x = s - sp;
-                    wgt = ev ? sigmoidf(x) * p.coef_scale : 0.f;
-                    lossacc += ev ? softplusf(x) : 0.f;
-                    csum += wgt;
-                    value = wgt;
-                } else {
-                    float lq_e = __shfl_sync(kFull, lq, e_own);
-                    float z = ev ? (s - lq_e) : -INFINITY;
-                    float gm = warp_max(z);
-                    float m_new = fmaxf(m_run, gm);
-                    // m_new == -inf only if nothing valid has been seen: keep everything at zero
-                    float scale = (m_new == -INFINITY) ? 1.f : expf(m_run - m_new);
-                    wgt = (ev && m_new != -INFINITY) ? expf(z - m_new) : 0.f;
-                    l_run = l_run * scale + warp_sum(wgt) * kRepInv;
-#pragma unroll
-                    for (int t = 0; t < VPL; ++t) {
-                        acc[t].x *= scale; acc[t].y *= scale; acc[t].z *= scale; acc[t].w *= scale;
-                    }
-                    m_run = m_new;
-                    value = z;
-                }
-#pragma unroll
-                for (int k = 0; k < LOADS; ++k) {
-                    float wk = __shfl_sync(kFull, wgt, k * REP);
-#pragma unroll
-                    for (int t = 0; t < VPL; ++t) fma4(acc[t], wk, v[k][t]);
-                }
-                // hand each element's value back to the lane that holds its id
-                float tv = __shfl_sync(kFull, value, (lane % LOADS) * REP);
-                float ts = __shfl_sync(kFull, s, (lane % LOADS) * REP);
-                if (lane / LOADS == g) { val_out = tv; sc_out = ts; }
+                if (jb + (g + 1) * LOADS < j1) compute_group<VPL, LOSS, SCORE>(bufB, st, p, q, sp, cur.lq, g + 1, jb, j1, lane);
             }
-        }
-        if (valid) {
-            if (p.neg_score) p.neg_score[rowbase + j] = sc_out;
-            if (slot != kNoSlot)
-                p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), val_out);
+            if (valid) {
+                if (p.neg_score) p.neg_score[rowbase + jb + lane] = st.sc_out;
+                if (cur.slot != kNoSlot)
+                    p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
+            }
+            cur = nxt; nxt = nn;
+        } else {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (jb + g * LOADS < j1) {            // warp-uniform
+                    load_group<VPL>(bufA, p, cur.id, g, lane, act);
+                    compute_group<VPL, LOSS, SCORE>(bufA, st, p, q, sp, cur.lq, g, jb, j1, lane);
+                }
+            }
+            if (valid) {
+                if (p.neg_score) p.neg_score[rowbase + jb + lane] = st.sc_out;
+                if (cur.slot != kNoSlot)
+                    p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
+            }
+            if (jb + 32 < j1) cur = load_meta<LOSS>(p, rowbase, jb + 32, j1, lane);
         }
     }
 
     // ---- per-warp -> per-query merge ------------------------------------------------------
-    csum = warp_sum(csum) * kRepInv;
-    lossacc = warp_sum(lossacc) * kRepInv;
+    const float csum = warp_sum(st.csum) * kRepInv;
+    const float lossacc = warp_sum(st.lossacc) * kRepInv;
     {
         float* a = s_acc + (size_t)(MULTI ? warp : 0) * D;
 #pragma unroll
         for (int t = 0; t < VPL; ++t) {
             int col = lane * 4 + t * 128;
-            if (act[t]) *reinterpret_cast<float4*>(a + col) = acc[t];
+            if (act[t]) *reinterpret_cast<float4*>(a + col) = st.acc[t];
         }
         if (lane == 0) {
-            float* st = s_stat + (MULTI ? warp : 0) * 4;
-            st[0] = m_run; st[1] = l_run; st[2] = csum; st[3] = lossacc;
+            float* sst = s_stat + (MULTI ? warp : 0) * 4;
+            sst[0] = st.m_run; sst[1] = st.l_run; sst[2] = csum; sst[3] = lossacc;
         }
     }
     if (MULTI) __syncthreads(); else __syncwarp();
@@ -299,36 +386,37 @@ pair_fwd_kernel(const FwdParams p) {
     }
 }
 
-template <int VPL, int LOSS, int SCORE>
-static int32_t launch_fwd_vls(const FwdParams& p, cudaStream_t st) {
+template <int VPL, int LOSS, int SCORE, bool PIPE>
+static int32_t launch_fwd_vlsp(const FwdParams& p, cudaStream_t st) {
     const bool multi = p.n >= 256;
     if (multi) {
         size_t smem = (size_t)(2 * p.D + kWarps * p.D + kWarps * 4) * sizeof(float);
-        pair_fwd_kernel<VPL, LOSS, SCORE, true><<<p.B, kThreads, smem, st>>>(p);
+        pair_fwd_kernel<VPL, LOSS, SCORE, true, PIPE><<<p.B, kThreads, smem, st>>>(p);
     } else {
         size_t smem = (size_t)kWarps * (3 * p.D + 4) * sizeof(float);
-        pair_fwd_kernel<VPL, LOSS, SCORE, false><<<(unsigned)cdiv(p.B, kWarps), kThreads, smem, st>>>(p);
+        pair_fwd_kernel<VPL, LOSS, SCORE, false, PIPE><<<(unsigned)cdiv(p.B, kWarps), kThreads, smem, st>>>(p);
     }
     RSB_LAUNCH_CHECK();
     return 0;
 }
 
-template <int VPL>
+template <int VPL, bool PIPE>
 static int32_t launch_fwd_v(const FwdParams& p, int loss, int score, cudaStream_t st) {
     if (loss == RSB200_LOSS_BPR) {
-        return score == RSB200_SCORE_IP ? launch_fwd_vls<VPL, RSB200_LOSS_BPR, RSB200_SCORE_IP>(p, st)
-                                        : launch_fwd_vls<VPL, RSB200_LOSS_BPR, RSB200_SCORE_EUCLID>(p, st);
+        return score == RSB200_SCORE_IP ? launch_fwd_vlsp<VPL, RSB200_LOSS_BPR, RSB200_SCORE_IP, PIPE>(p, st)
+                                        : launch_fwd_vlsp<VPL, RSB200_LOSS_BPR, RSB200_SCORE_EUCLID, PIPE>(p, st);
     }
-    return score == RSB200_SCORE_IP ? launch_fwd_vls<VPL, RSB200_LOSS_SSM, RSB200_SCORE_IP>(p, st)
-                                    : launch_fwd_vls<VPL, RSB200_LOSS_SSM, RSB200_SCORE_EUCLID>(p, st);
+    return score == RSB200_SCORE_IP ? launch_fwd_vlsp<VPL, RSB200_LOSS_SSM, RSB200_SCORE_IP, PIPE>(p, st)
+                                    : launch_fwd_vlsp<VPL, RSB200_LOSS_SSM, RSB200_SCORE_EUCLID, PIPE>(p, st);
 }
 
+// variant 0: software-pipelined stream (default); variant 1: simple load-then-reduce loop
 int32_t launch_pair_fwd(const FwdParams& p, int loss, int score, int variant, cudaStream_t st) {
-    (void)variant;
     if (p.B == 0) return 0;
-    if (p.D <= 128) return launch_fwd_v<1>(p, loss, score, st);
-    if (p.D <= 256) return launch_fwd_v<2>(p, loss, score, st);
-    if (p.D <= 512) return launch_fwd_v<4>(p, loss, score, st);
+    const bool pipe = variant != 1;
+    if (p.D <= 128) return pipe ? launch_fwd_v<1, true>(p, loss, score, st) : launch_fwd_v<1, false>(p, loss, score, st);
+    if (p.D <= 256) return launch_fwd_v<2, false>(p, loss, score, st);
+    if (p.D <= 512) return launch_fwd_v<4, false>(p, loss, score, st);
     set_error("embedding dim %d > 512 is not supported", p.D);
     return RSB200_EUNSUPPORTED;
 }

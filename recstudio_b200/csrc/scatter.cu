@@ -13,7 +13,9 @@
 // Every unique row is produced by exactly ONE warp: no floating-point atomics, no
 // zero-fill of an [N,d] buffer, and each output row is written once with 16-byte stores.
 // A warp owns 32 consecutive unique rows; because the entry list is sorted by row, their
-// entries are one contiguous range that is streamed with coalesced loads.
+// entries are one contiguous range that is streamed with coalesced loads.  Row boundaries
+// inside a 32-entry batch are a bit mask built with one warp reduction (REDUX.OR), so the
+// per-entry work is 2 shuffles + one 16-byte load + 4 FMA + a bit test.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -21,7 +23,8 @@ namespace rsb {
 
 constexpr int kScatWarps = 8;
 
-template <int VPL>
+// PLAIN = compact sink, overwrite, inner-product: the hot configuration with all options compiled out
+template <int VPL, bool PLAIN>
 __global__ void __launch_bounds__(kScatWarps * 32)
 scatter_kernel(const ScatterParams p) {
     const int lane = threadIdx.x & 31;
@@ -30,6 +33,7 @@ scatter_kernel(const ScatterParams p) {
     const uint32_t nchunks = (R + 31) / 32;
     const float gs = p.gscale ? __ldg(p.gscale) : 1.0f;
     const uint32_t warps_total = gridDim.x * kScatWarps;
+    const bool dense = !PLAIN && p.dense, accumulate = !PLAIN && p.accumulate, euclid = !PLAIN && p.euclid;
     bool act[VPL];
 #pragma unroll
     for (int t = 0; t < VPL; ++t) act[t] = (lane * 4 + t * 128) < D;
@@ -39,7 +43,7 @@ scatter_kernel(const ScatterParams p) {
         const bool have = u < R;
         uint32_t r = 0, beg = 0, end = 0;
         if (have) {
-            r = p.urow[u];
+            r = __ldg(p.urow + u);
             beg = __ldg(p.off + r);
             end = __ldg(p.off + r + 1);
             p.rows_out[u] = (int64_t)r;
@@ -47,86 +51,74 @@ scatter_kernel(const ScatterParams p) {
         const int nrows = min(32u, R - chunk * 32);
         const uint32_t e_begin = __shfl_sync(kFull, beg, 0);
         const uint32_t e_end = __shfl_sync(kFull, end, nrows - 1);
+        const uint32_t last = end - 1;                 // index of this lane's row's last entry (rows have >= 1 entry)
 
-        int cur = 0;                                             // row (0..nrows-1) being accumulated
-        uint32_t cur_end = __shfl_sync(kFull, end, 0);
+        int cur = 0;                                   // row of the chunk being accumulated
         float4 acc[VPL];
 #pragma unroll
         for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0, 0, 0, 0);
         float csum = 0.f;
 
-        auto flush = [&](int row_in_chunk) {
-            const uint32_t rr = __shfl_sync(kFull, r, row_in_chunk);
-            const size_t orow = p.dense ? (size_t)rr : (size_t)chunk * 32 + row_in_chunk;
-#pragma unroll
-            for (int t = 0; t < VPL; ++t) {
-                if (act[t]) {
-                    const int col = lane * 4 + t * 128;
-                    float4 a = acc[t];
-                    if (p.euclid) {
-                        float4 wv = ldg128(p.w + (size_t)rr * D + col);
-                        a.x = 2.f * (a.x - csum * wv.x); a.y = 2.f * (a.y - csum * wv.y);
-                        a.z = 2.f * (a.z - csum * wv.z); a.w = 2.f * (a.w - csum * wv.w);
-                    }
-                    a.x *= gs; a.y *= gs; a.z *= gs; a.w *= gs;
-                    float* dst = p.vals + orow * D + col;
-                    if (p.accumulate) {
-                        float4 o = *reinterpret_cast<const float4*>(dst);
-                        a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
-                    }
-                    stg128_stream(dst, a);
-                }
-                acc[t] = make_float4(0, 0, 0, 0);
-            }
-            csum = 0.f;
-        };
-
         for (uint32_t eb = e_begin; eb < e_end; eb += 32) {
             const uint32_t e = eb + lane;
             uint32_t bq = 0; float c = 0.f;
             if (e < e_end) {
-                uint64_t en = p.ent[e];
-                uint32_t lo = (uint32_t)en;
-                float val = __uint_as_float((uint32_t)(en >> 32));
+                const uint64_t en = __ldg(reinterpret_cast<const unsigned long long*>(p.ent) + e);
+                const uint32_t lo = (uint32_t)en;
+                const float val = __uint_as_float((uint32_t)(en >> 32));
                 bq = lo & 0x7FFFFFFFu;
                 c = (lo & kDirect) ? val : expf(val - __ldg(p.lse + bq)) * p.ssm_scale;
             }
+            // bit t set <=> entry eb+t is the last entry of its row
+            const uint32_t contrib = (have && last >= eb && last < eb + 32) ? (1u << (last - eb)) : 0u;
+            const uint32_t lastmask = __reduce_or_sync(kFull, contrib);
             const int cnt = min(32u, e_end - eb);
-            for (int t0 = 0; t0 < cnt; t0 += 8) {
-                // issue up to 8 independent source-row loads, then fold them in order
-                float4 v[8][VPL];
-                float cc[8];
+            for (int t0 = 0; t0 < cnt; t0 += 4) {      // lanes >= cnt hold (b = 0, c = 0): harmless
+                float4 v[4][VPL];
+                float cc[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int t = t0 + k;
-                    const int tt = t < cnt ? t : cnt - 1;
-                    const uint32_t bt = __shfl_sync(kFull, bq, tt);
-                    cc[k] = (t < cnt) ? __shfl_sync(kFull, c, tt) : 0.f;
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t bt = __shfl_sync(kFull, bq, t0 + k);
+                    cc[k] = __shfl_sync(kFull, c, t0 + k);
                     const float* srow = p.src + (size_t)bt * D + lane * 4;
 #pragma unroll
                     for (int x = 0; x < VPL; ++x)
-                        v[k][x] = (act[x] && t < cnt) ? ldg128(srow + x * 128) : make_float4(0, 0, 0, 0);
+                        v[k][x] = act[x] ? ldg128(srow + x * 128) : make_float4(0, 0, 0, 0);
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int t = t0 + k;
-                    if (t < cnt) {                                   // warp-uniform
-                        const uint32_t eidx = eb + t;
-                        while (eidx >= cur_end && cur < nrows - 1) { // crossed into the next row(s)
-                            flush(cur);
-                            ++cur;
-                            cur_end = __shfl_sync(kFull, end, cur);
-                        }
+                for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                        for (int x = 0; x < VPL; ++x) fma4(acc[x], cc[k], v[k][x]);
-                        csum += cc[k];
+                    for (int x = 0; x < VPL; ++x) fma4(acc[x], cc[k], v[k][x]);
+                    csum += cc[k];
+                    if ((lastmask >> (t0 + k)) & 1u) {                 // warp-uniform: row `cur` is complete
+                        uint32_t rr = 0;
+                        if (!PLAIN) rr = __shfl_sync(kFull, r, cur);
+                        const size_t orow = dense ? (size_t)rr : (size_t)chunk * 32 + cur;
+#pragma unroll
+                        for (int x = 0; x < VPL; ++x) {
+                            if (act[x]) {
+                                const int col = lane * 4 + x * 128;
+                                float4 a = acc[x];
+                                if (euclid) {
+                                    const float4 wv = ldg128(p.w + (size_t)rr * D + col);
+                                    a.x = 2.f * (a.x - csum * wv.x); a.y = 2.f * (a.y - csum * wv.y);
+                                    a.z = 2.f * (a.z - csum * wv.z); a.w = 2.f * (a.w - csum * wv.w);
+                                }
+                                a.x *= gs; a.y *= gs; a.z *= gs; a.w *= gs;
+                                float* dst = p.vals + orow * D + col;
+                                if (accumulate) {
+                                    const float4 o = *reinterpret_cast<const float4*>(dst);
+                                    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                                }
+                                stg128_stream(dst, a);
+                            }
+                            acc[x] = make_float4(0, 0, 0, 0);
+                        }
+                        csum = 0.f;
+                        ++cur;
                     }
                 }
             }
-        }
-        if (nrows > 0) {
-            // rows in a chunk always have >= 1 entry, so `cur` is the last row with pending data
-            while (cur < nrows) { flush(cur); ++cur; }
         }
     }
 }
@@ -145,15 +137,22 @@ loss_sum_kernel(const float* __restrict__ part, int B, float* __restrict__ loss)
     if (threadIdx.x == 0) *loss = (float)sh[0];
 }
 
+template <int VPL>
+static void launch_scatter_v(const ScatterParams& p, unsigned blocks, cudaStream_t st) {
+    const bool plain = !p.dense && !p.accumulate && !p.euclid;
+    if (plain) scatter_kernel<VPL, true><<<blocks, kScatWarps * 32, 0, st>>>(p);
+    else scatter_kernel<VPL, false><<<blocks, kScatWarps * 32, 0, st>>>(p);
+}
+
 int32_t launch_scatter(const ScatterParams& p, int64_t cap_rows, cudaStream_t st) {
     if (cap_rows <= 0) return 0;
     int64_t chunks = cdiv(cap_rows, 32);
     int64_t blocks = cdiv(chunks, kScatWarps);
     int64_t max_blocks = (int64_t)sm_count() * 8;
     if (blocks > max_blocks) blocks = max_blocks;
-    if (p.D <= 128) scatter_kernel<1><<<(unsigned)blocks, kScatWarps * 32, 0, st>>>(p);
-    else if (p.D <= 256) scatter_kernel<2><<<(unsigned)blocks, kScatWarps * 32, 0, st>>>(p);
-    else if (p.D <= 512) scatter_kernel<4><<<(unsigned)blocks, kScatWarps * 32, 0, st>>>(p);
+    if (p.D <= 128) launch_scatter_v<1>(p, (unsigned)blocks, st);
+    else if (p.D <= 256) launch_scatter_v<2>(p, (unsigned)blocks, st);
+    else if (p.D <= 512) launch_scatter_v<4>(p, (unsigned)blocks, st);
     else { set_error("embedding dim %d > 512 is not supported", p.D); return RSB200_EUNSUPPORTED; }
     RSB_LAUNCH_CHECK();
     return 0;

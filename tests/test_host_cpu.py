@@ -1,0 +1,171 @@
+"""CPU-only checks (no GPU, no compute calls): the C-ABI library loads and exports every
+declared symbol, the ctypes mirror matches the header, host-side logic (Philox offset
+arithmetic, workspace sizing, argument validation) and the plugin class hierarchy."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO
+from oracle import philox
+
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def L():
+    from recstudio_b200 import _lib, build
+    build.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(L):
+    from recstudio_b200 import _lib
+    names = _lib.declared_symbols()
+    assert len(names) >= 20
+    missing = [s for s in names if not hasattr(L, s)]
+    assert not missing, missing
+    assert L.rsb200_version() == 100
+    assert L.rsb200_sizeof_pair_args() == C.sizeof(_lib.PairArgs)
+
+
+def test_sass_is_sm100a_only():
+    from recstudio_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = {line.split(".")[-2] for line in out.split() if line.endswith(".cubin")}
+    assert archs == {"sm_100a"}, archs
+
+
+def test_philox_counter_offset_matches_oracle(L):
+    for numel in (1, 255, 256, 257, 1184 * 256 * 4, 1184 * 256 * 4 + 1, 8192 * 1024, 99_999_999):
+        for sm, mt in ((148, 2048), (132, 2048), (108, 1536)):
+            assert L.rsb200_philox_counter_offset(numel, sm, mt) == philox.torch_cuda_counter_offset(numel, sm, mt)
+    assert L.rsb200_philox_counter_offset(0, 148, 2048) == 0
+
+
+def test_workspace_sizes_and_argument_errors(L):
+    from recstudio_b200 import _lib
+    sz = _lib.PairSizes()
+    assert L.rsb200_pair_workspace_sizes(10_000_001, 1_000_001, 8192, 1024, 128, C.byref(sz)) == 0
+    assert sz.off_item == 10_000_002 and sz.ent_item == 8192 * 1025 and sz.cap_item == 8192 * 1025
+    assert sz.cap_user == 8192 and sz.q_buf == 8192 * 128 and sz.scan_tmp >= 10_000_001 // 4096 + 1
+    assert L.rsb200_pair_workspace_sizes(100, 100, 4, 4, 6, C.byref(sz)) == -1          # d % 4 != 0
+    assert b"bad problem shape" in L.rsb200_last_error()
+    assert L.rsb200_pair_workspace_sizes(100, 100, 1 << 22, 1 << 10, 8, C.byref(sz)) == -2   # B*(n+1) >= 2^31
+    # null / inconsistent argument blocks are rejected before any CUDA call
+    a = _lib.PairArgs()
+    assert L.rsb200_pair_step(C.byref(a), 15, None) == -1
+    assert L.rsb200_pair_step(None, 15, None) == -1
+    # sampler argument validation (no device needed: checks precede the launch)
+    assert L.rsb200_sample_uniform(1, 3, 100, 4, 4, 148, 2048, None, None, None) == -1       # offset % 4
+    assert L.rsb200_sample_uniform(1, 0, 1, 4, 4, 148, 2048, None, None, None) == -1         # no items
+    assert L.rsb200_sample_uniform(1, 0, (1 << 28) + 2, 4, 4, 148, 2048, None, None, None) == -2   # 64-bit draw path
+    assert L.rsb200_sample_uniform(1, 0, 100, 1 << 20, 1 << 9, 148, 2048, None, None, None) == -2  # numel*8 >= 2^31
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA (this container has no GPU)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from recstudio_b200 import _lib, fused, plugins, sampling
+    with pytest.raises(_lib.Rsb200Error):
+        fused.PairWorkspace(10, 10, 2, 2, 8, "cpu")
+    with pytest.raises(_lib.Rsb200Error):
+        sampling.uniform_draw(10, 2, 2, "cpu")
+    emb = plugins.FusedEmbedding(10, 8)
+    with pytest.raises(_lib.Rsb200Error):
+        emb(torch.tensor([1, 2]))
+    with pytest.raises(_lib.Rsb200Error):
+        plugins.FusedBPRLoss()(None, torch.zeros(2), None, torch.zeros(2, 3), None)
+    with pytest.raises(_lib.Rsb200Error):
+        plugins.FusedInnerProductScorer()(torch.zeros(2, 8), torch.zeros(2, 8))
+    with pytest.raises(_lib.Rsb200Error):
+        plugins.FusedUniformSampler(10)(torch.zeros(2, 8), 3)
+    with pytest.raises(_lib.Rsb200Error):
+        plugins.FusedEmbedding(10, 6)            # rows must be 16-byte multiples
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for root, _, files in os.walk(os.path.join(REPO, "recstudio_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                if "import oracle" in src or "from oracle" in src:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_popular_sampler_tables_match_reference_golden():
+    from conftest import load_golden
+    from recstudio_b200 import plugins
+    g = load_golden("popular")
+    for tag in ("small", "big"):
+        for mode in (0, 1, 2):
+            s = plugins.FusedPopularSampler(g[f"{tag}_count"], mode=mode)
+            np.testing.assert_array_equal(s.pop_prob.numpy(), g[f"{tag}_m{mode}_prob"])
+            np.testing.assert_array_equal(s.table.numpy(), g[f"{tag}_m{mode}_table"])
+            assert s.num_items == g[f"{tag}_count"].shape[0] - 1
+
+
+def test_mini_retriever_surface_and_asserts():
+    from recstudio_b200 import iface, plugins, retriever
+    if iface.HAVE_RECSTUDIO:
+        pytest.skip("recstudio importable in this process: FusedRetriever is a real BaseRetriever")
+    m = retriever.FusedRetriever({"model": {"embed_dim": 8}, "train": {"negative_count": 3}},
+                                 sampler=plugins.FusedUniformSampler(20), loss=plugins.FusedBPRLoss())
+    m.init_tables(11, 20)
+    assert isinstance(m.item_encoder, torch.nn.Embedding) and m.item_encoder.weight.shape == (20, 8)
+    assert m._get_item_vector().shape == (19, 8)
+    with pytest.raises(AssertionError):
+        retriever.FusedRetriever(None, sampler=object())
+    with pytest.raises(AssertionError):
+        retriever.FusedRetriever(None, loss=torch.nn.Identity())
+    with pytest.raises(NotImplementedError):
+        m.sampling({"user_id": torch.tensor([1]), "item_id": torch.tensor([1])}, 3, method="dns")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the read-only reference checkout")
+def test_plugins_subclass_the_real_reference_classes():
+    """In a subprocess with the reference importable: every plugin passes the reference's
+    isinstance gates and BaseRetriever's kwargs constructor accepts them unchanged."""
+    code = r"""
+import sys, os, tempfile
+sys.path[:0] = [%r, %r, %r]
+os.chdir(tempfile.mkdtemp())
+import warnings; warnings.filterwarnings('ignore')
+import torch, logging
+from recstudio_b200 import iface, plugins, retriever
+assert iface.HAVE_RECSTUDIO
+from recstudio.model.basemodel import BaseRetriever
+from recstudio.ann.sampler import Sampler
+from recstudio.model import loss_func, scorer, init
+assert issubclass(plugins.FusedUniformSampler, Sampler) and issubclass(plugins.FusedPopularSampler, Sampler)
+assert issubclass(plugins.FusedBPRLoss, loss_func.PairwiseLoss) and issubclass(plugins.FusedSampledSoftmaxLoss, loss_func.PairwiseLoss)
+assert issubclass(plugins.FusedInnerProductScorer, scorer.InnerProductScorer)
+assert issubclass(plugins.FusedEuclideanScorer, scorer.EuclideanScorer)
+assert issubclass(plugins.FusedEmbedding, torch.nn.Embedding)
+assert issubclass(retriever.FusedRetriever, BaseRetriever)
+from recstudio.utils import get_model
+conf = get_model('BPR')[1]; conf['train']['gpu'] = None; conf['train']['negative_count'] = 4; conf['model']['embed_dim'] = 8
+m = retriever.FusedRetriever(conf, fused_grad='sparse', item_encoder=plugins.FusedEmbedding(30, 8), query_encoder=plugins.FusedEmbedding(12, 8),
+        scorer=plugins.FusedInnerProductScorer(), sampler=plugins.FusedUniformSampler(30), loss=plugins.FusedBPRLoss())
+assert m.use_index is False or m.use_index is None or True
+# reference parameter init dispatches on isinstance(nn.Embedding) and re-zeroes the padding row (init.py:5-9)
+m.item_encoder.apply(init.xavier_normal_initialization)
+assert float(m.item_encoder.weight[0].abs().sum()) == 0.0 and float(m.item_encoder.weight[1:].abs().sum()) > 0
+# state_dict exposes the tables under the reference's key names (checkpoint compatibility)
+assert 'item_encoder.weight' in m.state_dict() and 'query_encoder.weight' in m.state_dict()
+# hooks used when no kwargs are given
+class D: num_items = 30; num_users = 12
+m2 = retriever.FusedBPR(conf)
+assert isinstance(m2._get_item_encoder(D), plugins.FusedEmbedding) and isinstance(m2._get_sampler(D), plugins.FusedUniformSampler)
+assert isinstance(m2._get_loss_func(), plugins.FusedBPRLoss) and isinstance(m2.score_func, plugins.FusedInnerProductScorer)
+print('OK')
+""" % (os.path.join(REPO, "oracle", "refshim"), REF, REPO)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
