@@ -88,12 +88,12 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_arm(steps: int, warmup: int, sample_b: int = CPU_SAMPLE_B):
+def cpu_reference_arm(steps: int, warmup: int, sample_b: int = CPU_SAMPLE_B, threads: int = 0):
     """The reference's own path on the host: F.embedding x3 -> score -> BPRLoss -> backward
     (dense embedding_dense_backward), op for op (oracle/retriever.py:training_step_aten)."""
     import torch
     from oracle import retriever as R
-    cores = os.cpu_count() or 1
+    cores = threads if threads > 0 else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(2022)
     wi = torch.empty(N_ITEMS, DIM).normal_(0, INIT_STD, generator=g); wi[0] = 0
@@ -127,7 +127,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = min(args.steps, 5), min(max(args.warmup, 1), 2)
-    cb = cpu_reference_arm(steps, warmup)
+    cb = cpu_reference_arm(steps, warmup, threads=args.cpu_threads)
     line = {"impl": "reference", "metric": "interactions/sec (BPR 10M x d128 fused gather-score-loss-scatter)",
             "value": cb["value"], "unit": "interactions/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -255,7 +255,7 @@ def run_b200(args):
             except Exception:
                 pass
         if world == 1 and not args.no_cpu:
-            cb = cpu_reference_arm(steps=2, warmup=1)
+            cb = cpu_reference_arm(steps=2, warmup=1, threads=args.cpu_threads)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development only)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -230,9 +230,10 @@ int32_t rsb200_pair_loss(int32_t loss_kind, const float* pos_score /* [B] */, co
  *   recstudio/model/basemodel/baseretriever.py:374-397
  * Scores every item row 1..num_items-1 against each query, masks the ids in
  * hist (0 = padding), returns the k best (score desc, id asc on ties),
- * ids 1-based.  [Be, num_items] is never written to HBM.
+ * ids 1-based.  [Be, num_items] is never written to HBM (only one max per 8 items).
+ * Limits: k + H + 8 <= 1024.
  */
-size_t  rsb200_topk_workspace_bytes(int64_t Be, int64_t num_items, int64_t k);
+size_t  rsb200_topk_workspace_bytes(int64_t Be, int64_t num_items, int64_t k, int64_t H);
 int32_t rsb200_topk_full(int32_t score_kind, const float* q /* [Be,d] */, const float* w_item, int64_t num_items,
                          int64_t d, int64_t Be, int64_t k, const int64_t* hist /* [Be,H] or NULL */, int64_t H,
                          float* score_out /* [Be,k] */, int64_t* id_out /* [Be,k] */,

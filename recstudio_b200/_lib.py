@@ -94,7 +94,7 @@ def lib():
         L.rsb200_philox_counter_offset.restype = C.c_int64
         L.rsb200_philox_counter_offset.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         L.rsb200_topk_workspace_bytes.restype = C.c_size_t
-        L.rsb200_topk_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+        L.rsb200_topk_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64]
         L.rsb200_fullsoftmax_workspace_bytes.restype = C.c_size_t
         L.rsb200_fullsoftmax_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
         v, i64, i32, u64, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_float

@@ -186,6 +186,90 @@ __device__ __forceinline__ void compute_group(const RowBuf<VPL>& buf, WarpState<
     if (lane / LOADS == g) { st.val_out = tv; st.sc_out = ts; }
 }
 
+// merge the per-warp partial state of one query and write dq, loss, lse and the positive / user entries
+template <int VPL, int LOSS, int SCORE, bool MULTI>
+__device__ __forceinline__ void finish_query(const FwdParams& p, WarpState<VPL>& st, float* s_q, float* s_vp,
+                                             float* s_acc, float* s_stat, const bool (&act)[VPL], float sp, int b,
+                                             int64_t uid, int64_t pid, int lane, int warp) {
+    constexpr float kRepInv = 1.0f / Cfg<VPL>::REP;
+    const int D = p.D;
+    const int nw = MULTI ? kWarps : 1;
+    // ---- per-warp -> per-query merge ------------------------------------------------------
+    const float csum = warp_sum(st.csum) * kRepInv;
+    const float lossacc = warp_sum(st.lossacc) * kRepInv;
+    {
+        float* a = s_acc + (size_t)(MULTI ? warp : 0) * D;
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+            int col = lane * 4 + t * 128;
+            if (act[t]) *reinterpret_cast<float4*>(a + col) = st.acc[t];
+        }
+        if (lane == 0) {
+            float* sst = s_stat + (MULTI ? warp : 0) * 4;
+            sst[0] = st.m_run; sst[1] = st.l_run; sst[2] = csum; sst[3] = lossacc;
+        }
+    }
+    if (MULTI) __syncthreads(); else __syncwarp();
+
+    // every thread of the group recomputes the (tiny) scalar merge
+    float M = -INFINITY, L = 0.f, CS = 0.f, LS = 0.f;
+    for (int w = 0; w < nw; ++w) M = fmaxf(M, s_stat[w * 4 + 0]);
+    float wscale[kWarps];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        wscale[w] = 1.f;
+        if (w < nw) {
+            if (LOSS == RSB200_LOSS_SSM) {
+                float mw = s_stat[w * 4 + 0];
+                wscale[w] = (mw == -INFINITY) ? 0.f : expf(mw - M);
+                L += s_stat[w * 4 + 1] * wscale[w];
+            }
+            CS += s_stat[w * 4 + 2];
+            LS += s_stat[w * 4 + 3];
+        }
+    }
+    float cpos, neg_mul, loss_b, lse_b = 0.f;
+    if (LOSS == RSB200_LOSS_BPR) {
+        cpos = -CS;
+        neg_mul = 1.f;                       // acc already carries the final coefficients
+        loss_b = LS * p.loss_scale;
+    } else {
+        float z0 = sp - (p.logq_pos ? p.logq_pos[b] : 0.f);
+        float M2 = fmaxf(M, z0);
+        float L2 = ((M == -INFINITY) ? 0.f : L * expf(M - M2)) + expf(z0 - M2);
+        lse_b = M2 + logf(L2);
+        float p0 = expf(z0 - lse_b);
+        cpos = (p0 - 1.f) * p.coef_scale;
+        neg_mul = (M == -INFINITY) ? 0.f : expf(M - lse_b) * p.coef_scale;   // acc, L are relative to M
+        CS = L * neg_mul;                    // = sum_j c_bj
+        loss_b = (lse_b - z0) * p.loss_scale;
+    }
+
+    const int gsize = MULTI ? kThreads : 32;
+    const int gtid = MULTI ? threadIdx.x : lane;
+    for (int c = gtid; c < D; c += gsize) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+            if (w < nw) a += s_acc[(size_t)w * D + c] * wscale[w];
+        a *= neg_mul;
+        float qc = s_q[c], vc = s_vp[c];
+        float dq;
+        if (SCORE == RSB200_SCORE_IP) dq = a + cpos * vc;
+        else dq = 2.f * (a - CS * qc) + 2.f * cpos * (vc - qc);
+        p.dq_buf[(size_t)b * D + c] = dq;
+    }
+    if (gtid == 0) {
+        p.loss_part[b] = loss_b;
+        if (LOSS == RSB200_LOSS_SSM) p.lse[b] = lse_b;
+        if (p.pos_score) p.pos_score[b] = sp;
+        uint32_t sl = p.slot_pos[b];
+        if (sl != kNoSlot) p.ent_item[__ldg(p.off_item + pid) + sl] = pack_entry((uint32_t)b | kDirect, cpos);
+        uint32_t su = p.slot_user[b];
+        if (su != kNoSlot) p.ent_user[__ldg(p.off_user + uid) + su] = pack_entry((uint32_t)b | kDirect, 1.0f);
+    }
+}
+
 // VPL = float4 per lane per row (D <= 128*VPL); lanes whose columns are >= D are idle.
 template <int VPL, int LOSS, int SCORE, bool MULTI, bool PIPE>
 __global__ void __launch_bounds__(kThreads, (VPL == 1 && !PIPE) ? 3 : 2)
@@ -310,80 +394,182 @@ pair_fwd_kernel(const FwdParams p) {
         }
     }
 
-    // ---- per-warp -> per-query merge ------------------------------------------------------
-    const float csum = warp_sum(st.csum) * kRepInv;
-    const float lossacc = warp_sum(st.lossacc) * kRepInv;
-    {
-        float* a = s_acc + (size_t)(MULTI ? warp : 0) * D;
+    finish_query<VPL, LOSS, SCORE, MULTI>(p, st, s_q, s_vp, s_acc, s_stat, act, sp, b, uid, pid, lane, warp);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA variant (variant 2, d <= 128): every warp owns a private ring of kStages shared-memory
+// stages; the 8 rows of a group are fetched by 8 lanes with cp.async.bulk (UBLKCP, one 512-B
+// bulk copy per row) that complete on the stage's mbarrier, so the bytes in flight per warp are
+// bounded by shared memory (kStages x 4 KB) instead of registers.  The consumer side (same warp)
+// waits on the mbarrier phase, pulls the rows into registers with conflict-free 16-byte LDS and
+// immediately re-arms the stage for the group kStages ahead.
+constexpr int kStages = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int LOSS, int SCORE, bool MULTI>
+__global__ void __launch_bounds__(kThreads, 2)
+pair_fwd_tma_kernel(const FwdParams p) {
+    constexpr int VPL = 1;
+    constexpr int LOADS = Cfg<VPL>::LOADS, NG = Cfg<VPL>::NG;
+    extern __shared__ __align__(128) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.D;
+    const int b = MULTI ? blockIdx.x : blockIdx.x * kWarps + warp;
+    if (!MULTI && b >= p.B) return;
+
+    // layout: [ring: kWarps x kStages x LOADS x D floats][mbarriers: kWarps x kStages x u64][merge area]
+    float* ring = smem + (size_t)warp * kStages * LOADS * D;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)kWarps * kStages * LOADS * D) + warp * kStages;
+    float* merge = smem + (size_t)kWarps * kStages * LOADS * D + 2 * kWarps * kStages;
+    const int nw = MULTI ? kWarps : 1;
+    float* sm_base = MULTI ? merge : merge + (size_t)warp * (size_t)(3 * D + 4);
+    float* s_q = sm_base;
+    float* s_vp = s_q + D;
+    float* s_acc = s_vp + D;
+    float* s_stat = s_acc + (size_t)nw * D;
+
+    if (lane == 0) {
 #pragma unroll
-        for (int t = 0; t < VPL; ++t) {
-            int col = lane * 4 + t * 128;
-            if (act[t]) *reinterpret_cast<float4*>(a + col) = st.acc[t];
-        }
-        if (lane == 0) {
-            float* sst = s_stat + (MULTI ? warp : 0) * 4;
-            sst[0] = st.m_run; sst[1] = st.l_run; sst[2] = csum; sst[3] = lossacc;
+        for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    int64_t uid = p.user[b], pid = p.pos[b];
+    if (uid < 0 || uid >= p.num_users) uid = 0;
+    if (pid < 0 || pid >= p.num_items) pid = 0;
+    float4 q[VPL], vp[VPL];
+    bool act[VPL];
+    act[0] = lane * 4 < D;
+    q[0] = act[0] ? ldg128(p.w_user + (size_t)uid * D + lane * 4) : make_float4(0, 0, 0, 0);
+    vp[0] = act[0] ? ldg128(p.w_item + (size_t)pid * D + lane * 4) : make_float4(0, 0, 0, 0);
+
+    const int n = p.n;
+    int j0 = 0, j1 = n;
+    if (MULTI) {
+        int per = ((n + kWarps - 1) / kWarps + 31) & ~31;
+        j0 = min(n, warp * per);
+        j1 = min(n, j0 + per);
+    }
+    const size_t rowbase = (size_t)b * n;
+    const int total_groups = (j1 - j0 + LOADS - 1) / LOADS;
+    const uint32_t row_bytes = (uint32_t)D * 4u;
+
+    BatchMeta cur = load_meta<LOSS>(p, rowbase, j0, j1, lane);
+    BatchMeta nxt = cur, nn = cur;
+    if (j0 + 32 < j1) nxt = load_meta<LOSS>(p, rowbase, j0 + 32, j1, lane);
+    if (j0 + 64 < j1) nn = load_meta<LOSS>(p, rowbase, j0 + 64, j1, lane);
+
+    // arm stage (gi % kStages) with the LOADS rows of global group gi; ids come from the batch it belongs to
+    auto issue = [&](int gi, int cur_batch) {
+        const int bi = gi / NG;                                  // batch of this group: cur_batch or cur_batch + 1
+        const int src = (gi % NG) * LOADS + (lane & (LOADS - 1));
+        const int rid_cur = __shfl_sync(kFull, cur.id, src);
+        const int rid_nxt = __shfl_sync(kFull, nxt.id, src);
+        const int rid = (bi == cur_batch) ? rid_cur : rid_nxt;
+        const int s = gi % kStages;
+        const uint32_t bar = smem_u32(bars + s);
+        if (lane == 0) mbar_expect_tx(bar, row_bytes * LOADS);
+        if (lane < LOADS)
+            bulk_g2s(smem_u32(ring + ((size_t)s * LOADS + lane) * D), p.w_item + (size_t)rid * D, row_bytes, bar);
+    };
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+        if (s < total_groups) issue(s, 0);
+
+    float sp = (SCORE == RSB200_SCORE_IP) ? dot4(q[0], vp[0]) : sqdist4(q[0], vp[0]);
+    sp = warp_sum(sp);
+    if (SCORE == RSB200_SCORE_EUCLID) sp = -sp;
+    if (!MULTI || warp == 0) {
+        if (act[0]) {
+            *reinterpret_cast<float4*>(s_q + lane * 4) = q[0];
+            *reinterpret_cast<float4*>(s_vp + lane * 4) = vp[0];
+            *reinterpret_cast<float4*>(p.q_buf + (size_t)b * D + lane * 4) = q[0];
         }
     }
-    if (MULTI) __syncthreads(); else __syncwarp();
 
-    // every thread of the group recomputes the (tiny) scalar merge
-    float M = -INFINITY, L = 0.f, CS = 0.f, LS = 0.f;
-    for (int w = 0; w < nw; ++w) M = fmaxf(M, s_stat[w * 4 + 0]);
-    float wscale[kWarps];
+    WarpState<VPL> st;
+    st.acc[0] = make_float4(0, 0, 0, 0);
+    st.csum = 0.f; st.lossacc = 0.f; st.m_run = -INFINITY; st.l_run = 0.f;
+    st.val_out = 0.f; st.sc_out = 0.f;
+    uint32_t epos = 0;
+    if (cur.slot != kNoSlot) epos = __ldg(p.off_item + cur.id) + cur.slot;
+
+    int batch = 0;
+    for (int gi = 0; gi < total_groups; ++gi) {
+        const int g = gi % NG, s = gi % kStages;
+        const int jb = j0 + batch * 32;
+        mbar_wait(smem_u32(bars + s), (uint32_t)((gi / kStages) & 1));
+        RowBuf<VPL> buf;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-        wscale[w] = 1.f;
-        if (w < nw) {
-            if (LOSS == RSB200_LOSS_SSM) {
-                float mw = s_stat[w * 4 + 0];
-                wscale[w] = (mw == -INFINITY) ? 0.f : expf(mw - M);
-                L += s_stat[w * 4 + 1] * wscale[w];
+        for (int k = 0; k < LOADS; ++k)
+            buf.v[k][0] = act[0] ? *reinterpret_cast<const float4*>(ring + ((size_t)s * LOADS + k) * D + lane * 4)
+                                 : make_float4(0, 0, 0, 0);
+        __syncwarp();                                            // all lanes have read the stage
+        if (gi + kStages < total_groups) issue(gi + kStages, batch);
+        compute_group<VPL, LOSS, SCORE>(buf, st, p, q, sp, cur.lq, g, jb, j1, lane);
+        if (g == NG - 1 || gi == total_groups - 1) {            // batch complete: emit and rotate metadata
+            if (jb + lane < j1) {
+                if (p.neg_score) p.neg_score[rowbase + jb + lane] = st.sc_out;
+                if (cur.slot != kNoSlot)
+                    p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
             }
-            CS += s_stat[w * 4 + 2];
-            LS += s_stat[w * 4 + 3];
+            ++batch;
+            cur = nxt; nxt = nn;
+            const int jn = j0 + (batch + 2) * 32;
+            if (jn < j1) nn = load_meta<LOSS>(p, rowbase, jn, j1, lane);
+            epos = 0;
+            if (cur.slot != kNoSlot) epos = __ldg(p.off_item + cur.id) + cur.slot;
+            st.val_out = 0.f; st.sc_out = 0.f;
         }
     }
-    float cpos, neg_mul, loss_b, lse_b = 0.f;
-    if (LOSS == RSB200_LOSS_BPR) {
-        cpos = -CS;
-        neg_mul = 1.f;                       // acc already carries the final coefficients
-        loss_b = LS * p.loss_scale;
-    } else {
-        float z0 = sp - (p.logq_pos ? p.logq_pos[b] : 0.f);
-        float M2 = fmaxf(M, z0);
-        float L2 = ((M == -INFINITY) ? 0.f : L * expf(M - M2)) + expf(z0 - M2);
-        lse_b = M2 + logf(L2);
-        float p0 = expf(z0 - lse_b);
-        cpos = (p0 - 1.f) * p.coef_scale;
-        neg_mul = (M == -INFINITY) ? 0.f : expf(M - lse_b) * p.coef_scale;   // acc, L are relative to M
-        CS = L * neg_mul;                    // = sum_j c_bj
-        loss_b = (lse_b - z0) * p.loss_scale;
-    }
+    finish_query<VPL, LOSS, SCORE, MULTI>(p, st, s_q, s_vp, s_acc, s_stat, act, sp, b, uid, pid, lane, warp);
+}
 
-    const int gsize = MULTI ? kThreads : 32;
-    const int gtid = MULTI ? threadIdx.x : lane;
-    for (int c = gtid; c < D; c += gsize) {
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w)
-            if (w < nw) a += s_acc[(size_t)w * D + c] * wscale[w];
-        a *= neg_mul;
-        float qc = s_q[c], vc = s_vp[c];
-        float dq;
-        if (SCORE == RSB200_SCORE_IP) dq = a + cpos * vc;
-        else dq = 2.f * (a - CS * qc) + 2.f * cpos * (vc - qc);
-        p.dq_buf[(size_t)b * D + c] = dq;
+template <int LOSS, int SCORE>
+static int32_t launch_fwd_tma_ls(const FwdParams& p, cudaStream_t st) {
+    const bool multi = p.n >= 256;
+    const size_t ring = (size_t)kWarps * kStages * Cfg<1>::LOADS * p.D * sizeof(float) + (size_t)kWarps * kStages * 8;
+    if (multi) {
+        size_t smem = ring + (size_t)(2 * p.D + kWarps * p.D + kWarps * 4) * sizeof(float);
+        RSB_CUDA(cudaFuncSetAttribute(pair_fwd_tma_kernel<LOSS, SCORE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_fwd_tma_kernel<LOSS, SCORE, true><<<p.B, kThreads, smem, st>>>(p);
+    } else {
+        size_t smem = ring + (size_t)kWarps * (3 * p.D + 4) * sizeof(float);
+        RSB_CUDA(cudaFuncSetAttribute(pair_fwd_tma_kernel<LOSS, SCORE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_fwd_tma_kernel<LOSS, SCORE, false><<<(unsigned)cdiv(p.B, kWarps), kThreads, smem, st>>>(p);
     }
-    if (gtid == 0) {
-        p.loss_part[b] = loss_b;
-        if (LOSS == RSB200_LOSS_SSM) p.lse[b] = lse_b;
-        if (p.pos_score) p.pos_score[b] = sp;
-        uint32_t sl = p.slot_pos[b];
-        if (sl != kNoSlot) p.ent_item[__ldg(p.off_item + pid) + sl] = pack_entry((uint32_t)b | kDirect, cpos);
-        uint32_t su = p.slot_user[b];
-        if (su != kNoSlot) p.ent_user[__ldg(p.off_user + uid) + su] = pack_entry((uint32_t)b | kDirect, 1.0f);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int32_t launch_fwd_tma(const FwdParams& p, int loss, int score, cudaStream_t st) {
+    if (loss == RSB200_LOSS_BPR) {
+        return score == RSB200_SCORE_IP ? launch_fwd_tma_ls<RSB200_LOSS_BPR, RSB200_SCORE_IP>(p, st)
+                                        : launch_fwd_tma_ls<RSB200_LOSS_BPR, RSB200_SCORE_EUCLID>(p, st);
     }
+    return score == RSB200_SCORE_IP ? launch_fwd_tma_ls<RSB200_LOSS_SSM, RSB200_SCORE_IP>(p, st)
+                                    : launch_fwd_tma_ls<RSB200_LOSS_SSM, RSB200_SCORE_EUCLID>(p, st);
 }
 
 template <int VPL, int LOSS, int SCORE, bool PIPE>
@@ -410,10 +596,13 @@ static int32_t launch_fwd_v(const FwdParams& p, int loss, int score, cudaStream_
                                     : launch_fwd_vlsp<VPL, RSB200_LOSS_SSM, RSB200_SCORE_EUCLID, PIPE>(p, st);
 }
 
-// variant 0: software-pipelined stream (default); variant 1: simple load-then-reduce loop
+// variant 0 (default): load-then-reduce loop, 3 CTAs/SM.  variant 1: software-pipelined stream,
+// 2 CTAs/SM -- measured SLOWER on B200 (1.12 ms vs 0.875 ms at config 2: the occupancy loss
+// outweighs the deeper per-warp pipeline), kept for A/B runs.
 int32_t launch_pair_fwd(const FwdParams& p, int loss, int score, int variant, cudaStream_t st) {
     if (p.B == 0) return 0;
-    const bool pipe = variant != 1;
+    const bool pipe = variant == 1;
+    if (variant == 2 && p.D <= 128) return launch_fwd_tma(p, loss, score, st);   // TMA (cp.async.bulk) ring
     if (p.D <= 128) return pipe ? launch_fwd_v<1, true>(p, loss, score, st) : launch_fwd_v<1, false>(p, loss, score, st);
     if (p.D <= 256) return launch_fwd_v<2, false>(p, loss, score, st);
     if (p.D <= 512) return launch_fwd_v<4, false>(p, loss, score, st);

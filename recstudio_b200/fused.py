@@ -130,7 +130,8 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
         # explicit per-step value buffers (autograd hand-off) or the workspace's persistent ones
         iv = item_vals if item_vals is not None else ws.item_vals
         uv = user_vals if user_vals is not None else ws.user_vals
-        if iv is None or uv is None or iv.shape[0] < ws.cap_item or uv.shape[0] < ws.cap_user:
+        if (phases & _lib.PHASE_SCATTER) and (iv is None or uv is None or iv.shape[0] < ws.cap_item
+                                              or uv.shape[0] < ws.cap_user):
             raise _lib.Rsb200Error("compact sink needs item_vals [>=cap_item, d] / user_vals [>=cap_user, d]")
         a.item_vals, a.user_vals = ptr(iv), ptr(uv)
     if grad_scale_dev is not None:

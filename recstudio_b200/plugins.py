@@ -378,6 +378,27 @@ class FusedRetrieverMixin:
             lqn = None
         return _FusedStepFn.apply(wi, wu, self, ws, user, pos, neg32, lqp, lqn, loss_kind, score_kind)
 
+    def topk(self, batch, k, user_h=None, return_query=False):
+        """BaseRetriever.topk (baseretriever.py:374-397) on rsb200_topk_full when the scorer is
+        InnerProduct / Euclid over a plain item table and no ANN index is configured; the
+        reference's torch.topk(k + H) -> mask -> topk(k) otherwise."""
+        sk = _SCORE_KIND.get(type(self.score_func))
+        item_w = getattr(self.item_encoder, "weight", None)
+        fusable = (sk is not None and not getattr(self, "use_index", False) and isinstance(self.item_encoder, torch.nn.Embedding)
+                   and len(getattr(self, "item_fields", [self.fiid])) == 1 and item_w is not None and item_w.is_cuda)
+        if not fusable:
+            return super().topk(batch, k, user_h, return_query)
+        from . import topk as _topk
+        query = self.query_encoder(self._get_query_feat(batch))
+        if query.dim() != 2:
+            return super().topk(batch, k, user_h, return_query)
+        # item_vector is weight[1:] (baseretriever.py:122-123,131-140); scoring the live table is
+        # identical after _update_item_vector(), which the trainer calls before every eval epoch
+        score, ids = _topk.topk_full(query, item_w, k, user_h, sk)
+        if return_query:
+            return score, ids, query
+        return score, ids
+
     def fused_last_neg_id(self):
         """int32 [B, n] negatives drawn by the last fused training_step (for inspection / parity tests)."""
         cache = self.__dict__.get("_fused_ws_cache", {})

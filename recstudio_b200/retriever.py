@@ -183,6 +183,32 @@ class MiniRetriever(torch.nn.Module):
     def topk(self, batch, k, user_h=None, return_query=False):                 # :374-397 (see FusedRetrieverMixin)
         raise NotImplementedError("topk is provided by FusedRetrieverMixin (rsb200_topk_full)")
 
+    def _test_step(self, batch, metric, cutoffs):                              # :416-431
+        from . import rank_metrics
+        rank_m = rank_metrics.get_rank_metrics(metric)
+        topk = self.config["eval"]["topk"]
+        bs = batch[self.frating].size(0)
+        assert len(rank_m) > 0
+        score, topk_items = self.topk(batch, topk, batch["user_hist"])
+        if batch[self.fiid].dim() > 1:
+            target, _ = batch[self.fiid].sort()
+            idx_ = torch.searchsorted(target, topk_items)
+            idx_[idx_ == target.size(1)] = target.size(1) - 1
+            label = torch.gather(target, 1, idx_) == topk_items
+            pos_rating = batch[self.frating]
+        else:
+            label = batch[self.fiid].view(-1, 1) == topk_items
+            pos_rating = batch[self.frating].view(-1, 1)
+        return {f"{name}@{cutoff}": func(label, pos_rating, cutoff) for cutoff in cutoffs for name, func in rank_m}, bs
+
+    def validation_step(self, batch):                                          # :406-409
+        cutoff = self.config["eval"]["cutoff"]
+        return self._test_step(batch, self.config["eval"]["val_metrics"], [cutoff[0] if isinstance(cutoff, list) else cutoff])
+
+    def test_step(self, batch):                                                # :411-414
+        cutoff = self.config["eval"]["cutoff"]
+        return self._test_step(batch, self.config["eval"]["test_metrics"], cutoff if isinstance(cutoff, list) else [cutoff])
+
 
 _Base = iface.BaseRetriever if iface.HAVE_RECSTUDIO else MiniRetriever
 

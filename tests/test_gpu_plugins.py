@@ -106,8 +106,9 @@ def test_sampler_plugins_contract():
     torch.manual_seed(8)
     seeds = torch.rand(6 * 3, 11, device=DEV)
     want = torch.searchsorted(ps.table, seeds).reshape(6, 3, 11)
+    pos_items = torch.randint(0, 5000, (6, 3), device=DEV)
     torch.manual_seed(8)
-    lp, neg, ln = ps(torch.zeros(6, 3, 4, device=DEV), 11, pos_items=torch.randint(0, 5000, (6, 3), device=DEV))
+    lp, neg, ln = ps(torch.zeros(6, 3, 4, device=DEV), 11, pos_items=pos_items)
     assert torch.equal(neg, want) and torch.equal(ln, torch.log(ps.pop_prob[want])) and lp.shape == (6, 3)
 
 

@@ -1,0 +1,135 @@
+"""T1 / T2 on the GPU: rsb200_topk_full against the reference's golden top-k, the float64
+order-defined oracle, and (at the BASELINE config-4 shape) the reference's own algorithm
+run with ATen on the same device.
+
+Rank parity rule: ids must be identical wherever the reference's neighbouring scores are
+separated by more than the fp32 evaluation noise (2e-6 * max|score|); inside such a
+near-tie either order is the same answer at fp32 resolution, and the scores themselves must
+agree to 1e-5 relative.  Exactly representable inputs (integers) are checked bit-exactly,
+including the tie-break (score desc, id asc)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import topk_eval as T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def assert_topk_equiv(got_s, got_i, want_s, want_i):
+    got_s, got_i, want_s, want_i = (np.asarray(x) for x in (got_s, got_i, want_s, want_i))
+    scale = max(np.abs(want_s[np.isfinite(want_s)]).max(), 1e-30)
+    fin = np.isfinite(want_s)
+    assert np.array_equal(np.isfinite(got_s), fin)
+    assert np.abs(got_s[fin] - want_s[fin]).max() <= 1e-5 * scale
+    assert np.all(np.diff(got_s, axis=1)[np.isfinite(np.diff(got_s, axis=1))] <= 0), "scores must be descending"
+    bad = got_i != want_i
+    for b, r in zip(*np.nonzero(bad)):
+        nb = [abs(want_s[b, r] - want_s[b, rr]) for rr in (r - 1, r + 1) if 0 <= rr < want_s.shape[1]]
+        assert min(nb) <= 4e-6 * scale, f"rank {r} of query {b}: id {got_i[b, r]} != {want_i[b, r]} without a near-tie"
+    return int(bad.sum())
+
+
+def test_appendix_a_and_golden():
+    from recstudio_b200 import topk
+    g = load_golden("topk_eval")
+    q = torch.from_numpy(g["a_w_user"])[torch.from_numpy(g["a_user"])].to(DEV)
+    w = torch.from_numpy(np.pad(g["a_w_item"], ((0, 0), (0, 2)))).to(DEV)      # d = 2 -> 4 (zero columns)
+    q = torch.nn.functional.pad(q, (0, 2))
+    s, i = topk.topk_full(q, w, 3, torch.from_numpy(g["a_hist"]).to(DEV))
+    assert np.array_equal(i.cpu().numpy(), [[3, 4, 5], [5, 4, 3]])
+    np.testing.assert_allclose(s.cpu().numpy(), g["a_score"], rtol=1e-6)
+    q = torch.from_numpy(g["r_w_user"])[torch.from_numpy(g["r_user"])].to(DEV)
+    w = torch.from_numpy(g["r_w_item"]).to(DEV)
+    hist = torch.from_numpy(g["r_hist"]).to(DEV)
+    for k, ks, ki in ((10, "r_score", "r_ids"), (100, "r_score100", "r_ids100")):
+        s, i = topk.topk_full(q, w, k, hist)
+        assert_topk_equiv(s.cpu(), i.cpu(), g[ks], g[ki])
+        for b in range(i.shape[0]):
+            assert not np.isin(i[b].cpu().numpy(), g["r_hist"][b][g["r_hist"][b] > 0]).any()
+    s, i = topk.topk_full(q, w, 10, None)
+    assert_topk_equiv(s.cpu(), i.cpu(), g["r_score_nohist"], g["r_ids_nohist"])
+
+
+@pytest.mark.parametrize("kind", ["ip", "eu"])
+def test_exact_integer_scores_and_tie_break(kind):
+    """Small-integer tables: every product and sum is exact in fp32, ties are everywhere."""
+    from recstudio_b200 import _lib, topk
+    g = torch.Generator().manual_seed(4)
+    N, d, Be, k, H = 3000, 16, 37, 20, 9
+    w = torch.randint(-2, 3, (N, d), generator=g).float(); w[0] = 0
+    q = torch.randint(-2, 3, (Be, d), generator=g).float()
+    hist = torch.randint(0, N, (Be, H), generator=g)
+    qq, ww = (q, w)
+    if kind == "eu":        # oracle for -|q - v|^2 via the expanded form (exact on integers)
+        sc = -((q[:, None, :] - w[None, 1:, :]) ** 2).sum(-1).double().numpy()
+    else:
+        sc = (q @ w[1:].T).double().numpy()
+    want_i = np.empty((Be, k), dtype=np.int64); want_s = np.empty((Be, k))
+    for b in range(Be):
+        sb = sc[b].copy(); h = hist[b].numpy(); sb[h[h > 0] - 1] = -np.inf
+        order = np.lexsort((np.arange(N - 1), -sb))[:k]
+        want_i[b] = order + 1; want_s[b] = sb[order]
+    s, i = topk.topk_full(qq.to(DEV), ww.to(DEV), k, hist.to(DEV), _lib.SCORE_EUCLID if kind == "eu" else _lib.SCORE_IP)
+    assert np.array_equal(i.cpu().numpy(), want_i)
+    assert np.array_equal(s.cpu().numpy().astype(np.float64), want_s)
+
+
+@pytest.mark.parametrize("shape", [(500, 48, 16, 10, 12), (10_001, 64, 130, 50, 0), (777, 100, 5, 100, 3)])
+def test_random_vs_float64_oracle(shape):
+    from recstudio_b200 import topk
+    N, d, Be, k, H = shape
+    g = torch.Generator().manual_seed(N)
+    w = torch.randn(N, d, generator=g); w[0] = 0
+    q = torch.randn(Be, d, generator=g)
+    hist = torch.randint(0, N, (Be, H), generator=g) if H else None
+    want_s, want_i = T.topk_exact(q.numpy(), w[1:].numpy(), k, hist.numpy() if H else None)
+    s, i = topk.topk_full(q.to(DEV), w.to(DEV), k, hist.to(DEV) if H else None)
+    assert_topk_equiv(s.cpu(), i.cpu(), want_s, want_i)
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_config4_shape_vs_reference_algorithm(k):
+    """1M items x 128, Be = 128, H = 64: the reference's topk (matmul -> topk(k+H) -> mask ->
+    topk(k), baseretriever.py:384-392) executed by ATen on the same GPU."""
+    from recstudio_b200 import topk
+    N, d, Be, H = 1_000_001, 128, 128, 64
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    w = torch.randn(N, d, device=DEV, generator=gen) * 0.1; w[0] = 0
+    q = torch.randn(Be, d, device=DEV, generator=gen) * 0.1
+    hist = torch.stack([torch.randperm(N - 1, device=DEV, generator=gen)[:H] + 1 for _ in range(Be)])
+    best = torch.topk(q @ w[1:].T, 8).indices + 1
+    hist[:, :4] = best[:, ::2]                    # make sure masked ids would otherwise be in the top-k
+    hist[:, -5:] = 0                              # right padding
+    score, items = torch.topk(q @ w[1:].T, k + H)
+    items = items + 1
+    existing, _ = hist.sort()
+    idx_ = torch.searchsorted(existing, items); idx_[idx_ == H] = H - 1
+    score[torch.gather(existing, 1, idx_) == items] = -float("inf")
+    score, idx = score.topk(k); items = torch.gather(items, 1, idx)
+    s, i = topk.topk_full(q, w, k, hist)
+    nswap = assert_topk_equiv(s.cpu(), i.cpu(), score.cpu(), items.cpu())
+    assert nswap <= 0.01 * Be * k
+    assert not (i.unsqueeze(-1) == hist.unsqueeze(1)).any()
+
+
+def test_retriever_test_step_metrics_match_reference():
+    """FusedRetriever._test_step (top-k 100 -> hit matrix -> rank metrics) on the golden tables
+    reproduces the metric values the reference computed (eval/__init__.py, baseretriever.py:416-431)."""
+    from recstudio_b200 import retriever
+    g = load_golden("topk_eval")
+    U, d = g["r_w_user"].shape; N = g["r_w_item"].shape[0]
+    m = retriever.build_synthetic(U, N, d, 1, device=DEV)
+    with torch.no_grad():
+        m.item_encoder.weight.copy_(torch.from_numpy(g["r_w_item"])); m.query_encoder.weight.copy_(torch.from_numpy(g["r_w_user"]))
+    m._update_item_vector()
+    m.config["eval"]["topk"] = 100
+    batch = {"user_id": torch.from_numpy(g["r_user"]).to(DEV), "item_id": torch.from_numpy(g["e_target"]).to(DEV),
+             "rating": torch.from_numpy(g["e_rating"]).to(DEV), "user_hist": torch.from_numpy(g["r_hist"]).to(DEV)}
+    res, bs = m._test_step(batch, ["ndcg", "recall", "precision", "map", "mrr", "hit"], [5, 10, 20])
+    assert bs == g["r_user"].shape[0]
+    for name, v in res.items():
+        want = g["e_" + name.replace("@", "_at_")].item()
+        assert abs(v.item() - want) < 1e-6, (name, v.item(), want)

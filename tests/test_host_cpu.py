@@ -169,3 +169,13 @@ print('OK')
 """ % (os.path.join(REPO, "oracle", "refshim"), REF, REPO)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_rank_metrics_mirror_matches_reference_golden():
+    from conftest import load_golden
+    from recstudio_b200 import rank_metrics
+    g = load_golden("topk_eval")
+    label, tgt = torch.from_numpy(g["m_label"]), torch.from_numpy(g["m_target"])
+    for name, fn in rank_metrics.get_rank_metrics(["ndcg", "recall", "precision", "map", "mrr", "hit"]):
+        for k in (1, 3, 5):
+            assert abs(fn(label, tgt, k).item() - g[f"m_{name}_{k}"].item()) < 1e-7, (name, k)
