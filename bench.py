@@ -93,7 +93,12 @@ def cpu_reference_arm(steps: int, warmup: int, sample_b: int = CPU_SAMPLE_B, thr
     (dense embedding_dense_backward), op for op (oracle/retriever.py:training_step_aten)."""
     import torch
     from oracle import retriever as R
-    cores = threads if threads > 0 else (os.cpu_count() or 1)
+    # The reference runs with torch.set_num_threads(train.num_threads = 10) (basemodel.yaml:48,
+    # quickstart/run.py:26).  Measured on the 128-core B200 host this is also the FASTEST setting for
+    # this path (10 threads 225 int/s, 32 threads 190, 128 threads 92: the dense 5 GB backward does
+    # not scale), so the default is the reference's own; --cpu-threads overrides it.
+    host_cores = os.cpu_count() or 1
+    cores = threads if threads > 0 else min(10, host_cores)
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(2022)
     wi = torch.empty(N_ITEMS, DIM).normal_(0, INIT_STD, generator=g); wi[0] = 0
@@ -118,8 +123,8 @@ def cpu_reference_arm(steps: int, warmup: int, sample_b: int = CPU_SAMPLE_B, thr
     val = sample_b / (ms / 1e3)
     return {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port", "ms_per_step": ms,
             "sample": "same tables (10,000,001 x 128 + 1,000,001 x 128 fp32), B=%d interactions x n=%d negatives per step, "
-                      "fwd + dense backward, %d warm-up + %d timed steps, torch %s CPU, %d threads"
-                      % (sample_b, NEG, warmup, steps, torch.__version__, cores)}
+                      "fwd + dense backward, %d warm-up + %d timed steps, torch %s CPU, %d threads (reference default) of %d host cores"
+                      % (sample_b, NEG, warmup, steps, torch.__version__, cores, host_cores)}
 
 
 def run_reference(args):

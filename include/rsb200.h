@@ -200,6 +200,18 @@ int32_t rsb200_gather_rows(const float* w, int64_t num_rows, int64_t d,
 int32_t rsb200_scatter_add_rows(float* dw, int64_t num_rows, int64_t d,
                                 const int64_t* ids, int64_t numel, const float* d_out, void* stream);
 
+/* Sum value rows that target the same table row: (ids[M], vals[M,d]) -> (rows_out[R] ascending
+ * unique, vals_out[R,d]) (sink COMPACT) or vals_out dense [num_rows,d] (sink DENSE, overwrite or
+ * accumulate).  Owner-side accumulate of the row-sharded table (the reference's
+ * embedding_dense_backward into one dense gradient, recommender.py:638).  skip_row0 != 0 drops
+ * ids equal to 0 (padding row).  Workspace: off[num_rows+1] u32, slot[M] u32, ent[M] u64,
+ * urow[cap] u32 (cap >= min(M, num_rows)), scan_tmp[scan_tmp_elems >= num_rows/4096 + 2] u64. */
+int32_t rsb200_rows_coalesce(const int64_t* ids, const float* vals, int64_t M, int64_t num_rows, int64_t d,
+                             int32_t skip_row0, int64_t* rows_out, float* vals_out, int32_t sink, int32_t accumulate,
+                             uint32_t* totals /* [2] = {entries, unique rows} */, uint32_t* off, uint32_t* slot,
+                             uint64_t* ent, uint32_t* urow, int64_t cap, uint64_t* scan_tmp, int64_t scan_tmp_elems,
+                             uint32_t* err_flag, void* stream);
+
 /* -------------------------------------------------------------------------
  * Q1 / Q2 standalone on ids (no [B,n,d] materialisation):
  *   score[b, j] = score_func(q[b], W[ids[b, j]])       scorer.py:10-14 / 28-34

@@ -108,6 +108,7 @@ def lib():
             "rsb200_pair_step": [C.POINTER(PairArgs), i32, v],
             "rsb200_gather_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_scatter_add_rows": [v, i64, i64, v, i64, v, v],
+            "rsb200_rows_coalesce": [v, v, i64, i64, i64, i32, v, v, i32, i32, v, v, v, v, v, i64, v, i64, v, v],
             "rsb200_score_ids": [i32, v, v, i64, i64, v, i64, i64, v, v],
             "rsb200_score_dense": [i32, v, v, i64, i64, i64, v, v],
             "rsb200_score_dense_bwd": [i32, v, v, v, i64, i64, i64, v, v, v],

@@ -310,8 +310,12 @@ class _FusedStepFn(torch.autograd.Function):
             return None, None, None, None, None, None, None, None, None, None, None
         tot = ws.totals.tolist()  # sparse COO hand-off needs the row counts on the host
         ri, ru = tot[1], tot[3]
-        gi = torch.sparse_coo_tensor(ws.item_rows[:ri].unsqueeze(0).clone(), iv[:ri], size=w_item.shape, is_coalesced=True)
-        gu = torch.sparse_coo_tensor(ws.user_rows[:ru].unsqueeze(0).clone(), uv[:ru], size=w_user.shape, is_coalesced=True)
+        ii, ui = ws.item_rows[:ri].unsqueeze(0).clone(), ws.user_rows[:ru].unsqueeze(0).clone()
+        gi = torch.sparse_coo_tensor(ii, iv[:ri], size=w_item.shape, is_coalesced=True, check_invariants=False)
+        gu = torch.sparse_coo_tensor(ui, uv[:ru], size=w_user.shape, is_coalesced=True, check_invariants=False)
+        # AccumulateGrad shallow-copies sparse gradients and loses the coalesced flag (rows ARE unique and
+        # ascending); _restore_coalesced (a post-accumulate hook) puts it back when .grad is exactly this tensor
+        host._fused_sparse_ptrs = {ii.data_ptr(), ui.data_ptr()}
         return gi, gu, None, None, None, None, None, None, None, None, None
 
 
@@ -362,12 +366,22 @@ class FusedRetrieverMixin:
                                              sink="dense" if self.fused_grad == "dense" else "compact", alloc_vals=False)
         return cache[key]
 
+    def _restore_coalesced(self, param):
+        g = param.grad
+        if g is not None and g.is_sparse and not g.is_coalesced() and \
+                g._indices().data_ptr() in self.__dict__.get("_fused_sparse_ptrs", ()):
+            g._coalesced_(True)
+
     def training_step(self, batch):
         combo = self._fused_combo(batch)
         if combo is None:
             return super().training_step(batch)
         loss_kind, score_kind = combo
         wi, wu = self.item_encoder.weight, self.query_encoder.weight
+        if self.fused_grad == "sparse" and not self.__dict__.get("_fused_hooks", False):
+            wi.register_post_accumulate_grad_hook(self._restore_coalesced)
+            wu.register_post_accumulate_grad_hook(self._restore_coalesced)
+            self.__dict__["_fused_hooks"] = True
         user = batch[self.fuid].to(wi.device, non_blocking=True).contiguous()
         pos = batch[self.fiid].to(wi.device, non_blocking=True).contiguous()
         B, n = pos.numel(), int(self.neg_count)

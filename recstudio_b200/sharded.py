@@ -1,0 +1,195 @@
+"""Row-sharded item table across the GPUs of one box (BASELINE config 5).
+
+The reference has no table sharding at all (its only multi-GPU mode replicates every
+parameter each step, recstudio/utils/data_parallel.py:151).  Here each rank owns a contiguous
+block of item rows; one training step of a rank is:
+
+  1. draw its own negatives (global ids) and collect the UNIQUE item rows its batch touches;
+  2. remote-row lookup: all-to-all the ids to their owners, owners gather the rows
+     (rsb200_gather_rows), all-to-all the rows back                     [the exchange step]
+  3. run the unchanged fused step (rsb200_pair_step) on the compact local table of fetched rows;
+  4. all-to-all the gradient rows back to their owners, which sum the contributions of all
+     ranks per owned row (rsb200_rows_coalesce).
+  The (small) user table is replicated; its gradient rows are all-gathered so every replica
+  applies the same update.
+
+Because unique ids come out sorted and ownership is contiguous, ids are already grouped by
+owner: no permutation is needed on either side.  The exchange plan (who sends how many rows to
+whom) is plain torch tensor code with no device assumptions, so the same functions run under
+``gloo`` on CPU tensors in the tests; the arithmetic (gather / fused step / coalesce) is CUDA only
+and is injected through ``ops``.
+
+This is the literal design of the north star (row lookup over NVLink).  Shipping queries instead
+of rows moves ~60x fewer bytes and is the planned replacement.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------------------- plan
+def rows_per_rank(num_rows: int, world: int) -> int:
+    return (num_rows + world - 1) // world
+
+
+def owner_counts(sorted_ids: torch.Tensor, per_rank: int, world: int) -> torch.Tensor:
+    """How many of the ascending ``sorted_ids`` each rank owns (contiguous ownership)."""
+    bounds = torch.arange(1, world + 1, device=sorted_ids.device, dtype=sorted_ids.dtype) * per_rank
+    ends = torch.searchsorted(sorted_ids, bounds, right=False)
+    return torch.diff(ends, prepend=ends.new_zeros(1))
+
+
+def exchange_counts(send_counts: torch.Tensor, group=None) -> torch.Tensor:
+    recv = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv, send_counts, group=group)
+    return recv
+
+
+def all_to_all_var(x: torch.Tensor, send_counts, recv_counts, group=None) -> torch.Tensor:
+    """all_to_all_single with per-peer row counts (host lists)."""
+    out = x.new_empty((int(sum(recv_counts)),) + tuple(x.shape[1:]))
+    dist.all_to_all_single(out, x.contiguous(), output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts),
+                           group=group)
+    return out
+
+
+# --------------------------------------------------------------------------------------- CUDA ops
+class CudaOps:
+    """The arithmetic of the sharded step: CUDA kernels only."""
+
+    @staticmethod
+    def gather_rows(weight: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda()
+        out = torch.empty(ids.numel(), weight.shape[1], dtype=torch.float32, device=weight.device)
+        with torch.cuda.device(weight.device):
+            _lib.check(_lib.lib().rsb200_gather_rows(_lib.ptr(weight), weight.shape[0], weight.shape[1], _lib.ptr(ids),
+                                                     ids.numel(), _lib.ptr(out), _lib.stream_ptr()), "gather_rows")
+        return out
+
+    @staticmethod
+    def coalesce_rows(ids: torch.Tensor, vals: torch.Tensor, num_rows: int, skip_row0: bool = False):
+        """(ids[M], vals[M,d]) -> (unique ascending rows[R], summed vals[R,d])"""
+        _lib.require_cuda()
+        dev, M, d = vals.device, ids.numel(), vals.shape[1]
+        cap = max(1, min(M, num_rows))
+        i32 = torch.int32
+        off = torch.empty(num_rows + 1, dtype=i32, device=dev)
+        slot = torch.empty(max(M, 1), dtype=i32, device=dev)
+        ent = torch.empty(max(M, 1), dtype=torch.int64, device=dev)
+        urow = torch.empty(cap, dtype=i32, device=dev)
+        tmp = torch.empty(num_rows // 4096 + 3, dtype=torch.int64, device=dev)
+        totals = torch.zeros(2, dtype=i32, device=dev)
+        err = torch.zeros(1, dtype=i32, device=dev)
+        rows = torch.empty(cap, dtype=torch.int64, device=dev)
+        out = torch.empty(cap, d, dtype=torch.float32, device=dev)
+        ids = ids.contiguous(); vals = vals.contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().rsb200_rows_coalesce(
+                _lib.ptr(ids), _lib.ptr(vals), M, num_rows, d, int(skip_row0), _lib.ptr(rows), _lib.ptr(out),
+                _lib.SINK_COMPACT, 0, _lib.ptr(totals), _lib.ptr(off), _lib.ptr(slot), _lib.ptr(ent), _lib.ptr(urow), cap,
+                _lib.ptr(tmp), tmp.numel(), _lib.ptr(err), _lib.stream_ptr()), "rows_coalesce")
+        r = int(totals[1].item())
+        if int(err.item()):
+            raise _lib.Rsb200Error("rows_coalesce: row id out of range")
+        return rows[:r], out[:r]
+
+
+# --------------------------------------------------------------------------------------- table
+class ShardedRows:
+    """One rank's block of a row-sharded fp32 table and the two exchanges around it."""
+
+    def __init__(self, num_rows: int, dim: int, device, group=None, ops=CudaOps, init_std: float = 0.0, seed: int = 0):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.num_rows, self.dim = num_rows, dim
+        self.per_rank = rows_per_rank(num_rows, self.world)
+        self.row0 = self.rank * self.per_rank
+        self.local_rows = max(0, min(self.per_rank, num_rows - self.row0))
+        self.ops = ops
+        self.weight = torch.zeros(max(self.local_rows, 1), dim, dtype=torch.float32, device=device)
+        if init_std > 0:
+            g = torch.Generator(device=device).manual_seed(seed + self.rank)
+            self.weight.normal_(0, init_std, generator=g)
+        if self.rank == 0:
+            self.weight[0] = 0            # global row 0 is the padding row
+
+    # unique ascending global ids -> their rows, fetched from the owners
+    def lookup(self, uniq_ids: torch.Tensor):
+        send = owner_counts(uniq_ids, self.per_rank, self.world)
+        recv = exchange_counts(send, self.group)
+        send_l, recv_l = send.tolist(), recv.tolist()
+        want = all_to_all_var(uniq_ids, send_l, recv_l, self.group)              # ids other ranks ask me for
+        rows = self.ops.gather_rows(self.weight, want - self.row0)
+        got = all_to_all_var(rows, recv_l, send_l, self.group)                   # rows in uniq_ids order
+        return got, (send_l, recv_l)
+
+    # gradient rows for ascending global ids -> summed per owned row on the owner
+    def push(self, ids: torch.Tensor, vals: torch.Tensor):
+        send = owner_counts(ids, self.per_rank, self.world)
+        recv = exchange_counts(send, self.group)
+        send_l, recv_l = send.tolist(), recv.tolist()
+        r_ids = all_to_all_var(ids, send_l, recv_l, self.group)
+        r_vals = all_to_all_var(vals, send_l, recv_l, self.group)
+        return self.ops.coalesce_rows(r_ids - self.row0, r_vals, max(self.local_rows, 1), skip_row0=False)
+
+
+def sharded_training_step(items: ShardedRows, w_user: torch.Tensor, user: torch.Tensor, pos: torch.Tensor,
+                          neg: torch.Tensor, loss_kind: int, score_kind: int, logq_pos: Optional[torch.Tensor] = None,
+                          logq_neg: Optional[torch.Tensor] = None, fused_step=None):
+    """One data-parallel step of a rank over the row-sharded item table.
+
+    ``neg`` holds GLOBAL item ids [B, n].  Returns (global mean loss, (owned item rows, summed grads) with
+    LOCAL row ids, (user rows, grads) identical on every rank).  ``fused_step(w_item, w_user, user, pos, neg32,
+    lqp, lqn, grad_scale) -> (loss, item_rows, item_vals, user_rows, user_vals)`` is the single-GPU fused step;
+    gradients are scaled by 1/world so that the sum over ranks is the gradient of the global mean loss.
+    """
+    world = items.world
+    touched = torch.cat([neg.reshape(-1).to(torch.int64), pos.to(torch.int64)])
+    uniq, inverse = torch.unique(touched, sorted=True, return_inverse=True)
+    rows, _ = items.lookup(uniq)
+    # compact local table: position 0 is a dummy padding row, fetched row i sits at position i + 1
+    w_local = torch.cat([rows.new_zeros(1, items.dim), rows], dim=0)
+    neg_c = (inverse[:neg.numel()].reshape(neg.shape) + 1)
+    pos_c = (inverse[neg.numel():] + 1)
+    # global id 0 (padding) must keep the padding semantics: map it to compact position 0
+    if uniq.numel() > 0 and int(uniq[0].item()) == 0:
+        neg_c = torch.where(neg == 0, torch.zeros_like(neg_c), neg_c)
+        pos_c = torch.where(pos == 0, torch.zeros_like(pos_c), pos_c)
+    loss, i_rows, i_vals, u_rows, u_vals = fused_step(w_local, w_user, user, pos_c.contiguous(), neg_c.to(torch.int32).contiguous(),
+                                                      logq_pos, logq_neg, 1.0 / world)
+    g_ids = uniq[i_rows - 1]                                  # ascending compact positions -> ascending global ids
+    own_rows, own_vals = items.push(g_ids, i_vals)
+    # replicated user table: every rank needs every rank's user-gradient rows
+    # (padded to the batch size so that the all_gather is fixed-size; padding rows carry id 0 = dropped)
+    B = user.numel()
+    pr = u_rows.new_zeros(B); pr[:u_rows.numel()] = u_rows
+    pv = u_vals.new_zeros(B, u_vals.shape[1]); pv[:u_rows.numel()] = u_vals
+    all_rows = [torch.empty_like(pr) for _ in range(world)]
+    all_vals = [torch.empty_like(pv) for _ in range(world)]
+    dist.all_gather(all_rows, pr, group=items.group)
+    dist.all_gather(all_vals, pv, group=items.group)
+    ur, uv = items.ops.coalesce_rows(torch.cat(all_rows), torch.cat(all_vals), w_user.shape[0], skip_row0=True)
+    loss = loss.detach().clone() / world
+    dist.all_reduce(loss, group=items.group)
+    return loss, (own_rows, own_vals), (ur, uv)
+
+
+def make_fused_step(B: int, n: int, d: int, num_users: int, device):
+    """The single-GPU fused step bound to a workspace sized for the worst-case compact table."""
+    from . import fused
+
+    def step(w_local, w_user, user, pos_c, neg32, lqp, lqn, grad_scale):
+        ws = fused.PairWorkspace(w_local.shape[0], num_users, B, n, d, device)
+        loss = fused.pair_step(ws, w_local.contiguous(), w_user, user, pos_c, neg32, step.loss_kind, step.score_kind,
+                               logq_pos=lqp, logq_neg=lqn, grad_scale=grad_scale)
+        (ri, vi), (ru, vu) = fused.sparse_grads(ws)
+        return loss, ri, vi, ru, vu
+    step.loss_kind, step.score_kind = _lib.LOSS_BPR, _lib.SCORE_IP
+    return step
