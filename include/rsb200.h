@@ -46,6 +46,7 @@ extern "C" {
 /* enums (plain ints in the ABI) */
 #define RSB200_LOSS_BPR      0   /* recstudio/model/loss_func.py:50-59  BPRLoss(dns=False) */
 #define RSB200_LOSS_SSM      1   /* recstudio/model/loss_func.py:80-90  SampledSoftmaxLoss */
+#define RSB200_LOSS_FULL     2   /* recstudio/model/loss_func.py:39-42  SoftmaxLoss (rsb200_pair_loss only: neg_score = all_score) */
 #define RSB200_SCORE_IP      0   /* recstudio/model/scorer.py:5-17     InnerProductScorer  */
 #define RSB200_SCORE_EUCLID  1   /* recstudio/model/scorer.py:28-34    EuclideanScorer     */
 

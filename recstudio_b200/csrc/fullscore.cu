@@ -17,8 +17,7 @@
 //     The contraction runs on the fp32 pipe on purpose: ranks must match the reference's
 //     fp32 scores and the north star keeps tensor cores for the attention block only.
 //
-// L3  SoftmaxLoss over the whole catalog: placeholder (returns RSB200_EUNSUPPORTED) until the
-//     fused logsumexp / backward kernels land.
+// L3 (full softmax) lives in fullsoftmax.cu.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -280,11 +279,4 @@ extern "C" int32_t rsb200_topk_full(int32_t score_kind, const float* q, const fl
     }
     RSB_LAUNCH_CHECK();
     return 0;
-}
-
-extern "C" size_t rsb200_fullsoftmax_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
-extern "C" int32_t rsb200_fullsoftmax_fwd_bwd(const float*, const float*, const int64_t*, int64_t, int64_t, int64_t,
-                                              float*, float*, float*, void*, size_t, void*) {
-    set_error("rsb200_fullsoftmax_fwd_bwd: not implemented yet");
-    return RSB200_EUNSUPPORTED;
 }

@@ -95,6 +95,19 @@ pair_loss_kernel(const float* __restrict__ pos, const float* __restrict__ neg, c
         }
         ls = warp_sum_f(ls); cs = warp_sum_f(cs);
         if (lane == 0) { loss_part[b] = ls * inv; if (d_pos) d_pos[b] = -cs; }
+    } else if (LOSS == 2) {
+        // SoftmaxLoss on a materialised all_score row (loss_func.py:41-42): lse(all) - pos
+        const float invB = 1.0f / (float)B;
+        float m = -INFINITY;
+        for (int64_t j = lane; j < n; j += 32) m = fmaxf(m, nr[j]);
+        m = warp_max_f(m);
+        float l = 0.f;
+        for (int64_t j = lane; j < n; j += 32) l += expf(nr[j] - m);
+        l = warp_sum_f(l);
+        const float lse = m + logf(l);
+        if (dn)
+            for (int64_t j = lane; j < n; j += 32) dn[j] = expf(nr[j] - lse) * invB;
+        if (lane == 0) { loss_part[b] = (lse - sp) * invB; if (d_pos) d_pos[b] = -invB; }
     } else {
         const float invB = 1.0f / (float)B;
         const float z0 = sp - (lqp ? lqp[b] : 0.f);
@@ -164,11 +177,13 @@ extern "C" int32_t rsb200_pair_loss(int32_t loss_kind, const float* pos_score, c
                                     const float* logq_pos, const float* logq_neg, int64_t B, int64_t n, float* loss,
                                     float* d_pos, float* d_neg, float* loss_part, void* stream) {
     RSB_REQUIRE(pos_score && (neg_score || n == 0) && loss && loss_part, RSB200_EINVAL, "null pointer");
-    RSB_REQUIRE(loss_kind == RSB200_LOSS_BPR || loss_kind == RSB200_LOSS_SSM, RSB200_EINVAL, "bad loss_kind");
+    RSB_REQUIRE(loss_kind == RSB200_LOSS_BPR || loss_kind == RSB200_LOSS_SSM || loss_kind == RSB200_LOSS_FULL, RSB200_EINVAL, "bad loss_kind");
     RSB_REQUIRE(B >= 1 && n >= 0 && B < ((int64_t)1 << 31), RSB200_EINVAL, "bad shape");
     unsigned grid = (unsigned)cdiv(B, 8);
     if (loss_kind == RSB200_LOSS_BPR)
         pair_loss_kernel<RSB200_LOSS_BPR><<<grid, 256, 0, (cudaStream_t)stream>>>(pos_score, neg_score, logq_pos, logq_neg, B, n, d_pos, d_neg, loss_part);
+    else if (loss_kind == RSB200_LOSS_FULL)
+        pair_loss_kernel<RSB200_LOSS_FULL><<<grid, 256, 0, (cudaStream_t)stream>>>(pos_score, neg_score, logq_pos, logq_neg, B, n, d_pos, d_neg, loss_part);
     else
         pair_loss_kernel<RSB200_LOSS_SSM><<<grid, 256, 0, (cudaStream_t)stream>>>(pos_score, neg_score, logq_pos, logq_neg, B, n, d_pos, d_neg, loss_part);
     RSB_LAUNCH_CHECK();

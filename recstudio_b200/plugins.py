@@ -273,6 +273,48 @@ class FusedSampledSoftmaxLoss(iface.PairwiseLoss):
         return _PairLossFn.apply(pos_score, neg_score, log_pos_prob, log_neg_prob, LOSS_SSM)
 
 
+class FusedSoftmaxLoss(iface.FullScoreLoss):
+    """SoftmaxLoss (loss_func.py:39-42), 1-D positives.  Standalone: one pass over a materialised
+    ``all_score`` row block; inside FusedRetrieverMixin the [B, N-1] matrix is never built
+    (rsb200_fullsoftmax_fwd_bwd)."""
+    fused_kind = _lib.LOSS_FULL
+
+    def forward(self, label, pos_score, all_score):
+        if all_score.dim() != pos_score.dim() + 1:
+            raise _lib.Rsb200Error("FusedSoftmaxLoss handles 1-D positives (all_score [B, N-1]); "
+                                   "use the reference class for the padded 2-D branch")
+        return _PairLossFn.apply(pos_score, all_score, None, None, _lib.LOSS_FULL)
+
+
+class _FullSoftmaxFn(torch.autograd.Function):
+    """L3 + Q1-full: loss = mean_b(logsumexp_i q_b.w_i - q_b.w_pos_b) with dQ and dense dW computed in
+    the same call; the [B, N-1] score matrix never exists."""
+
+    @staticmethod
+    def forward(ctx, query: Tensor, w_item: Tensor, pos: Tensor):
+        _need_cuda(query, "query")
+        q = query.contiguous().float()
+        B, d = q.shape
+        N = w_item.shape[0]
+        dev = q.device
+        pos = pos.to(dev, torch.int64).contiguous()
+        nbytes = int(lib().rsb200_fullsoftmax_workspace_bytes(B, N, d))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        dq = torch.empty_like(q)
+        dw = torch.empty(N, d, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().rsb200_fullsoftmax_fwd_bwd(ptr(q), ptr(w_item.detach()), ptr(pos), N, B, d, ptr(loss), ptr(dq), ptr(dw),
+                                                   ptr(ws), nbytes, stream_ptr()), "fullsoftmax_fwd_bwd")
+        ctx.save_for_backward(dq, dw)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        dq, dw = ctx.saved_tensors
+        return g * dq, g * dw, None
+
+
 # ============================================================================ R1: the fused step
 class _FusedStepFn(torch.autograd.Function):
     """forward = PHASE_COUNT|SCAN|FWD (loss + gradient coefficients), backward = PHASE_SCATTER
@@ -372,7 +414,27 @@ class FusedRetrieverMixin:
                 g._indices().data_ptr() in self.__dict__.get("_fused_sparse_ptrs", ()):
             g._coalesced_(True)
 
+    def _fused_full_softmax(self, batch):
+        """config-4 path: full-catalog SoftmaxLoss with plain embedding towers and no sampler
+        (baseretriever.py:177-186 + loss_func.py:39-42)."""
+        if type(self.loss_fn) is not FusedSoftmaxLoss or self.sampler is not None:
+            return None
+        if type(self.score_func) is not FusedInnerProductScorer or not isinstance(self.item_encoder, torch.nn.Embedding):
+            return None
+        if batch[self.fiid].dim() != 1 or len(getattr(self, "item_fields", [self.fiid])) != 1:
+            return None
+        wi = self.item_encoder.weight
+        if not wi.is_cuda or wi.shape[1] > 128:
+            return None
+        query = self.query_encoder(self._get_query_feat(batch))         # any query encoder (keeps its own autograd)
+        if query.dim() != 2:
+            return None
+        return _FullSoftmaxFn.apply(query, wi, batch[self.fiid])
+
     def training_step(self, batch):
+        full = self._fused_full_softmax(batch)
+        if full is not None:
+            return full
         combo = self._fused_combo(batch)
         if combo is None:
             return super().training_step(batch)
