@@ -262,6 +262,22 @@ int32_t rsb200_fullsoftmax_fwd_bwd(const float* q /* [B,d] */, const float* w_it
                                    float* loss /* [1] */, float* dq /* [B,d] */, float* dw /* [num_items,d] dense, overwritten */,
                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* -------------------------------------------------------------------------
+ * A1  attention core of SASRecQueryEncoder / BERT4Rec on tcgen05 tensor cores (bf16 operands,
+ *     fp32 accumulation in TMEM).   recstudio/model/seq/sasrec.py:19-32,44-53
+ *     (nn.TransformerEncoderLayer self-attention: softmax(Q K^T / sqrt(dh) + masks) V per head;
+ *      mask = causal triu(1) (unless bidirectional) AND key padding hist == 0)
+ * q, k, v, out: fp32 [B, L, heads * head_dim] (head h occupies columns [h*dh, (h+1)*dh));
+ * hist: int64 [B, L] item ids (0 = padding key) or NULL; lse: [B, heads, L] or NULL.
+ * Limits: head_dim == 64, L <= 256.  err_flag[0] is set if a tensor-core barrier timed out.
+ * bf16 operands: results match an fp32 evaluation to ~1e-2 relative (not the 1e-5 of the fp32 paths).
+ */
+int32_t rsb200_attn_fwd(const float* q, const float* k, const float* v, const int64_t* hist, int64_t B, int64_t L,
+                        int64_t heads, int64_t head_dim, int32_t causal, float* out, float* lse, uint32_t* err_flag,
+                        void* stream);
+/* validation hook for the tcgen05 plumbing: D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T, fp32 accumulate */
+int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D, int64_t N, int64_t K, uint32_t* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

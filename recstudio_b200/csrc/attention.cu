@@ -1,0 +1,243 @@
+// attention.cu -- A1: the attention core of SASRecQueryEncoder / BERT4Rec on the 5th-gen tensor
+// cores (tcgen05.mma, accumulators in TMEM), the one place on this path that is a dense
+// bf16 contraction.
+//   reference: recstudio/model/seq/sasrec.py:19-32,44-53 (nn.TransformerEncoderLayer self-attention,
+//   causal mask triu(ones(L,L),1) AND key-padding mask hist == 0, softmax(QK^T/sqrt(dh)) V per head)
+//
+// One CTA (128 threads = 4 warps = 128 TMEM lanes) per (sequence, head); L <= 256, head_dim = 64.
+//   S  = Q_tile K^T    : tcgen05.mma M128 N256 K16 x4   -> TMEM columns [0, 256)
+//   P  = softmax(mask(S / 8)) : every thread owns one query row (tcgen05.ld 32x32b), no shuffles;
+//        P is written to shared memory as bf16 in the UMMA K-major operand layout
+//   O  = P V           : tcgen05.mma M128 N64 K16 x16   -> TMEM columns [256, 320)
+// Operands are staged with plain loads (fp32 -> bf16 conversion on the fly) into the
+// interleaved no-swizzle layout of tc05.cuh; V is transposed while staging so that both GEMMs
+// use K-major operands.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace rsb {
+using namespace tc;
+
+// ---------------------------------------------------------------------------------------------
+// Debug / validation entry: D[128, N] = A[128, K] * B[N, K]^T with bf16 operands, fp32 accumulate.
+__global__ void __launch_bounds__(128)
+tc_gemm_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
+                    uint32_t* __restrict__ err) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);                       // [128 x K]
+    __nv_bfloat16* sB = reinterpret_cast<__nv_bfloat16*>(smem_raw + (size_t)128 * K * 2); // [N x K]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int r = i / K, c = i % K;
+        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sA) + kmajor_off(r, c, 128)) = __float2bfloat16(A[i]);
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        const int r = i / K, c = i % K;
+        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(sB) + kmajor_off(r, c, N)) = __float2bfloat16(B[i]);
+    }
+    uint32_t ncols = 32;
+    while ((int)ncols < N) ncols <<= 1;
+    if (warp == 0) {
+        tmem_alloc(&tmem_slot, ncols);
+        if (lane == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t taddr = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            const uint64_t ad = make_desc(smem_addr(sA) + k16 * 2 * (128 * 16), 128 * 16, 128);
+            const uint64_t bd = make_desc(smem_addr(sB) + k16 * 2 * (N * 16), N * 16, 128);
+            mma_bf16(taddr, ad, bd, idesc, k16 > 0);
+        }
+        mma_commit(&bar);
+    }
+    const bool ok = mbar_wait(&bar, 0);
+    fence_after_sync();
+    if (!ok) {
+        if (tid == 0) *err = 1u;
+    } else {
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (c0 + i < N) D[(size_t)(warp * 32 + lane) * N + c0 + i] = v[i];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(taddr, ncols);
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kLP = 256;       // padded sequence length (keys)
+constexpr int kDH = 64;        // head dim
+constexpr uint32_t kTmemCols = 512;
+constexpr size_t kAttnSmem = (size_t)kLP * kDH * 2 * 3 + (size_t)128 * kLP * 2 + kLP;   // Q, K, Vt, P, key-valid bytes
+
+__global__ void __launch_bounds__(128, 1)
+attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                const int64_t* __restrict__ hist, int L, int heads, int causal, float scale,
+                float* __restrict__ out, float* __restrict__ lse_out, uint32_t* __restrict__ err) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sQ = smem_raw;                                  // 2 x [128 x 64] bf16 (one block per M tile)
+    unsigned char* sK = sQ + (size_t)kLP * kDH * 2;                // [256 x 64]
+    unsigned char* sVt = sK + (size_t)kLP * kDH * 2;               // [64 x 256]  (rows = head dim, K = keys)
+    unsigned char* sP = sVt + (size_t)kLP * kDH * 2;               // [128 x 256]
+    unsigned char* keyok = sP + (size_t)128 * kLP * 2;             // [256]
+    __shared__ __align__(8) uint64_t bar_s, bar_o;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int d = heads * kDH;
+    const float* qb = q + (size_t)b * L * d + h * kDH;
+    const float* kb = k + (size_t)b * L * d + h * kDH;
+    const float* vb = v + (size_t)b * L * d + h * kDH;
+
+    // ---- stage operands (fp32 -> bf16), zero beyond L ---------------------------------------
+    for (int i = tid; i < kLP * (kDH / 4); i += 128) {
+        const int r = i / (kDH / 4), c = (i % (kDH / 4)) * 4;
+        float4 fq = make_float4(0, 0, 0, 0), fk = fq, fv = fq;
+        if (r < L) {
+            fq = ldg128(qb + (size_t)r * d + c); fk = ldg128(kb + (size_t)r * d + c); fv = ldg128(vb + (size_t)r * d + c);
+        }
+        const float aq[4] = {fq.x, fq.y, fq.z, fq.w}, ak[4] = {fk.x, fk.y, fk.z, fk.w}, av[4] = {fv.x, fv.y, fv.z, fv.w};
+        unsigned char* qt = sQ + (size_t)(r >> 7) * (128 * kDH * 2);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            *reinterpret_cast<__nv_bfloat16*>(qt + kmajor_off(r & 127, c + x, 128)) = __float2bfloat16(aq[x]);
+            *reinterpret_cast<__nv_bfloat16*>(sK + kmajor_off(r, c + x, kLP)) = __float2bfloat16(ak[x]);
+            *reinterpret_cast<__nv_bfloat16*>(sVt + kmajor_off(c + x, r, kDH)) = __float2bfloat16(av[x]);
+        }
+    }
+    for (int j = tid; j < kLP; j += 128) keyok[j] = (j < L && (hist == nullptr || hist[(size_t)b * L + j] != 0)) ? 1 : 0;
+    if (warp == 0) {
+        tmem_alloc(&tmem_slot, kTmemCols);
+        if (lane == 0) { mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); fence_mbar_init(); }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tS = tmem_slot, tO = tmem_slot + 256;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    bool failed = false;
+
+    const int mtiles = (L + 127) / 128;
+    for (int mt = 0; mt < mtiles; ++mt) {
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, kLP);
+            const uint32_t qa = smem_addr(sQ) + mt * (128 * kDH * 2), ka = smem_addr(sK);
+#pragma unroll
+            for (int k16 = 0; k16 < kDH / 16; ++k16)
+                mma_bf16(tS, make_desc(qa + k16 * 2 * (128 * 16), 128 * 16, 128),
+                         make_desc(ka + k16 * 2 * (kLP * 16), kLP * 16, 128), idesc, k16 > 0);
+            mma_commit(&bar_s);
+        }
+        if (!mbar_wait(&bar_s, mt & 1)) failed = true;
+        fence_after_sync();
+        const int row = warp * 32 + lane, gi = mt * 128 + row;       // this thread's query row
+        // pass 1: row max of the masked, scaled scores
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < kLP; c0 += 32) {
+            float s[32];
+            tmem_ld32(tS + lane_base + c0, s);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int j = c0 + i;
+                const bool ok = keyok[j] && !(causal && j > gi);
+                if (ok) mx = fmaxf(mx, s[i] * scale);
+            }
+        }
+        // pass 2: P = exp(s - max) (bf16, UMMA K-major layout), row sum
+        float l = 0.f;
+        for (int c0 = 0; c0 < kLP; c0 += 32) {
+            float s[32];
+            tmem_ld32(tS + lane_base + c0, s);
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+                __align__(16) __nv_bfloat16 pk[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    const int j = c0 + g8 * 8 + x;
+                    const bool ok = keyok[j] && !(causal && j > gi);
+                    const float p = (ok && mx != -INFINITY) ? __expf(s[g8 * 8 + x] * scale - mx) : 0.f;
+                    pk[x] = __float2bfloat16(p);
+                    l += __bfloat162float(pk[x]);            // normalise by what the tensor core will actually sum
+                }
+                *reinterpret_cast<uint4*>(sP + kmajor_off(row, c0 + g8 * 8, 128)) = *reinterpret_cast<const uint4*>(pk);
+            }
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, kDH);
+            const uint32_t pa = smem_addr(sP), va = smem_addr(sVt);
+#pragma unroll
+            for (int k16 = 0; k16 < kLP / 16; ++k16)
+                mma_bf16(tO, make_desc(pa + k16 * 2 * (128 * 16), 128 * 16, 128),
+                         make_desc(va + k16 * 2 * (kDH * 16), kDH * 16, 128), idesc, k16 > 0);
+            mma_commit(&bar_o);
+        }
+        if (!mbar_wait(&bar_o, mt & 1)) failed = true;
+        fence_after_sync();
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        for (int c0 = 0; c0 < kDH; c0 += 32) {
+            float o[32];
+            tmem_ld32(tO + lane_base + c0, o);
+            if (gi < L) {
+                float* dst = out + ((size_t)b * L + gi) * d + h * kDH + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+            }
+        }
+        if (gi < L && lse_out) lse_out[((size_t)b * heads + h) * L + gi] = (l > 0.f) ? mx + logf(l) : -INFINITY;
+        fence_before_sync();
+        __syncthreads();                 // sP / TMEM are reused by the next M tile
+        fence_after_sync();
+    }
+    if (failed && tid == 0) *err = 1u;
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, kTmemCols);
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D, int64_t N, int64_t K, uint32_t* err_flag,
+                                       void* stream) {
+    RSB_REQUIRE(A && B && D && err_flag, RSB200_EINVAL, "null pointer");
+    RSB_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K <= 256 && K % 16 == 0, RSB200_EINVAL, "N, K must be multiples of 16 in [16, 256]");
+    const size_t smem = (size_t)(128 + N) * K * 2;
+    RSB_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_gemm_test_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, (int)N, (int)K, err_flag);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t rsb200_attn_fwd(const float* q, const float* k, const float* v, const int64_t* hist, int64_t B, int64_t L,
+                                   int64_t heads, int64_t head_dim, int32_t causal, float* out, float* lse,
+                                   uint32_t* err_flag, void* stream) {
+    RSB_REQUIRE(q && k && v && out && err_flag, RSB200_EINVAL, "null pointer");
+    RSB_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), RSB200_EINVAL, "pointers must be 16-byte aligned");
+    RSB_REQUIRE(head_dim == kDH, RSB200_EUNSUPPORTED, "attention kernel is built for head_dim = 64 (got %lld)", (long long)head_dim);
+    RSB_REQUIRE(L >= 1 && L <= kLP, RSB200_EUNSUPPORTED, "sequence length must be in [1, 256] (got %lld)", (long long)L);
+    RSB_REQUIRE(B >= 1 && heads >= 1 && B * heads < ((int64_t)1 << 31), RSB200_EINVAL, "bad shape");
+    RSB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    attn_fwd_kernel<<<(unsigned)(B * heads), 128, kAttnSmem, (cudaStream_t)stream>>>(
+        q, k, v, hist, (int)L, (int)heads, causal, 1.0f / sqrtf((float)head_dim), out, lse, err_flag);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
