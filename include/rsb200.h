@@ -213,6 +213,14 @@ int32_t rsb200_rows_coalesce(const int64_t* ids, const float* vals, int64_t M, i
                              uint64_t* ent, uint32_t* urow, int64_t cap, uint64_t* scan_tmp, int64_t scan_tmp_elems,
                              uint32_t* err_flag, void* stream);
 
+/* Optimizer step on the touched rows only (next-row 8(f)-1; the reference: dense optimizer over the whole
+ * table, recommender.py:445-474,646).  rows[R] / vals[R,d] as produced by rsb200_pair_step (SINK_COMPACT);
+ * R is read from DEVICE memory (*count_dev, e.g. &totals[1]) -- no host sync.  kind: 0 SGD, 1 Adagrad
+ * (state1 = sum of squares), 2 SparseAdam (state1 = exp_avg, state2 = exp_avg_sq, step >= 1). */
+int32_t rsb200_rows_update(int32_t kind, float* w, float* state1, float* state2, int64_t num_rows, int64_t d,
+                           const int64_t* rows, const float* vals, const uint32_t* count_dev, int64_t cap,
+                           int64_t step, float lr, float beta1, float beta2, float eps, void* stream);
+
 /* -------------------------------------------------------------------------
  * Q1 / Q2 standalone on ids (no [B,n,d] materialisation):
  *   score[b, j] = score_func(q[b], W[ids[b, j]])       scorer.py:10-14 / 28-34
@@ -275,6 +283,12 @@ int32_t rsb200_fullsoftmax_fwd_bwd(const float* q /* [B,d] */, const float* w_it
 int32_t rsb200_attn_fwd(const float* q, const float* k, const float* v, const int64_t* hist, int64_t B, int64_t L,
                         int64_t heads, int64_t head_dim, int32_t causal, float* out, float* lse, uint32_t* err_flag,
                         void* stream);
+/* backward of rsb200_attn_fwd: o / lse are its outputs, d_o the upstream gradient [B, L, heads*head_dim];
+ * writes dq, dk, dv (same layout, overwritten).  dV = P^T dO, dS = P o (dO V^T - rowsum(dO o O)) / sqrt(dh),
+ * dQ = dS K, dK = dS^T Q, all five contractions on tcgen05. */
+int32_t rsb200_attn_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
+                        const int64_t* hist, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t causal,
+                        float* dq, float* dk, float* dv, uint32_t* err_flag, void* stream);
 /* validation hook for the tcgen05 plumbing: D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T, fp32 accumulate */
 int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D, int64_t N, int64_t K, uint32_t* err_flag, void* stream);
 

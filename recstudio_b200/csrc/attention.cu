@@ -212,9 +212,216 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     if (warp == 0) tmem_dealloc(tmem_slot, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward.  With P = softmax(mask(S / 8)), D_i = sum_c dO_ic O_ic:
+//     dV = P^T dO,   dP = dO V^T,   dS = P o (dP - D) / 8,   dQ = dS K,   dK = dS^T Q.
+// One kernel, two roles (template KEYSIDE), so that every tensor-core A operand is written by the
+// thread that OWNS its row (no transposed scatter through shared memory):
+//   query side (KEYSIDE = 0): rows = queries, columns = keys  ->  dQ = dS  K
+//   key   side (KEYSIDE = 1): rows = keys,    columns = queries -> dV = P^T dO,  dK = dS^T Q
+// (the key side recomputes S^T = K Q^T and dP^T = V dO^T directly).  Columns are processed in
+// halves of 128 so that S, dP (2 x 128 TMEM columns) and the output accumulators (2 x 64) coexist.
+constexpr size_t kBwdSmem = (size_t)128 * kDH * 2 * 4      // X tile, U tile, Y half, W half
+                          + (size_t)128 * 128 * 2 * 2      // E_P, E_dS
+                          + (size_t)kDH * kLP * 2 * 2      // Yt, Wt
+                          + (size_t)kLP * 4 * 2 + kLP;     // lse, D, key-valid
+
+template <bool KEYSIDE>
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                const float* __restrict__ o, const float* __restrict__ d_o, const float* __restrict__ lse,
+                const int64_t* __restrict__ hist, int L, int heads, int causal, float scale,
+                float* __restrict__ out_ds /* dQ | dK */, float* __restrict__ out_p /* - | dV */, uint32_t* __restrict__ err) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* sX = smem_raw;                                  // [128 x 64] rows operand of S
+    unsigned char* sU = sX + 128 * kDH * 2;                        // [128 x 64] rows operand of dP
+    unsigned char* sYh = sU + 128 * kDH * 2;                       // [128 x 64] column-half operand of S
+    unsigned char* sWh = sYh + 128 * kDH * 2;                      // [128 x 64] column-half operand of dP
+    unsigned char* sEP = sWh + 128 * kDH * 2;                      // [128 x 128] P   (rows x column half)
+    unsigned char* sEdS = sEP + 128 * 128 * 2;                     // [128 x 128] dS
+    unsigned char* sYt = sEdS + 128 * 128 * 2;                     // [64 x 256]  Y^T (B operand of dS * Y)
+    unsigned char* sWt = sYt + kDH * kLP * 2;                      // [64 x 256]  W^T (B operand of P * W), key side only
+    float* s_lse = reinterpret_cast<float*>(sWt + kDH * kLP * 2);  // [256] per query
+    float* s_D = s_lse + kLP;                                      // [256] per query
+    unsigned char* keyok = reinterpret_cast<unsigned char*>(s_D + kLP);
+    __shared__ __align__(8) uint64_t bar1, bar2;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int d = heads * kDH;
+    const size_t base = (size_t)b * L * d + h * kDH;
+    const float* X = (KEYSIDE ? k : q) + base;        // rows operand of S
+    const float* Y = (KEYSIDE ? q : k) + base;        // cols operand of S
+    const float* U = (KEYSIDE ? v : d_o) + base;      // rows operand of dP
+    const float* W = (KEYSIDE ? d_o : v) + base;      // cols operand of dP
+
+    auto put = [](unsigned char* dst, uint32_t off, float x) { *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16(x); };
+    // natural [128 x 64] tile of rows row0.. of src
+    auto stage_rows = [&](unsigned char* dst, const float* src, int row0) {
+        for (int i = tid; i < 128 * (kDH / 4); i += 128) {
+            const int r = i / (kDH / 4), c = (i % (kDH / 4)) * 4;
+            float4 f = make_float4(0, 0, 0, 0);
+            if (row0 + r < L) f = ldg128(src + (size_t)(row0 + r) * d + c);
+            put(dst, kmajor_off(r, c, 128), f.x); put(dst, kmajor_off(r, c + 1, 128), f.y);
+            put(dst, kmajor_off(r, c + 2, 128), f.z); put(dst, kmajor_off(r, c + 3, 128), f.w);
+        }
+    };
+    // transposed [64 x 256]: element (c, j) = src[j][c]
+    auto stage_t = [&](unsigned char* dst, const float* src) {
+        for (int i = tid; i < kLP * (kDH / 4); i += 128) {
+            const int j = i / (kDH / 4), c = (i % (kDH / 4)) * 4;
+            float4 f = make_float4(0, 0, 0, 0);
+            if (j < L) f = ldg128(src + (size_t)j * d + c);
+            put(dst, kmajor_off(c, j, kDH), f.x); put(dst, kmajor_off(c + 1, j, kDH), f.y);
+            put(dst, kmajor_off(c + 2, j, kDH), f.z); put(dst, kmajor_off(c + 3, j, kDH), f.w);
+        }
+    };
+    stage_t(sYt, Y);
+    if (KEYSIDE) stage_t(sWt, W);
+    for (int i = tid; i < kLP; i += 128) {
+        float dsum = 0.f, ls = 0.f;
+        if (i < L) {
+            const float* orow = o + base + (size_t)i * d;
+            const float* grow = d_o + base + (size_t)i * d;
+            for (int c = 0; c < kDH; c += 4) dsum += dot4(ldg128(orow + c), ldg128(grow + c));
+            ls = lse[((size_t)b * heads + h) * L + i];
+        }
+        s_D[i] = dsum; s_lse[i] = ls;
+        keyok[i] = (i < L && (hist == nullptr || hist[(size_t)b * L + i] != 0)) ? 1 : 0;
+    }
+    if (warp == 0) {
+        tmem_alloc(&tmem_slot, kTmemCols);
+        if (lane == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); fence_mbar_init(); }
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tS = tmem_slot, tdP = tmem_slot + 128, tOdS = tmem_slot + 256, tOP = tmem_slot + 320;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    bool failed = false;
+    uint32_t ph1 = 0, ph2 = 0;
+    const int tiles = (L + 127) / 128;
+    const int row = warp * 32 + lane;
+
+    for (int rt = 0; rt < tiles; ++rt) {
+        stage_rows(sX, X, rt * 128);
+        stage_rows(sU, U, rt * 128);
+        const int gr = rt * 128 + row;                        // global row index of this thread
+        for (int ch = 0; ch < tiles; ++ch) {
+            stage_rows(sYh, Y, ch * 128);
+            stage_rows(sWh, W, ch * 128);
+            fence_async_smem();
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, 128);
+#pragma unroll
+                for (int k16 = 0; k16 < kDH / 16; ++k16) {
+                    const uint32_t koff = k16 * 2 * (128 * 16);
+                    mma_bf16(tS, make_desc(smem_addr(sX) + koff, 128 * 16, 128), make_desc(smem_addr(sYh) + koff, 128 * 16, 128), idesc, k16 > 0);
+                    mma_bf16(tdP, make_desc(smem_addr(sU) + koff, 128 * 16, 128), make_desc(smem_addr(sWh) + koff, 128 * 16, 128), idesc, k16 > 0);
+                }
+                mma_commit(&bar1);
+            }
+            if (!mbar_wait(&bar1, ph1)) failed = true;
+            ph1 ^= 1;
+            fence_after_sync();
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                float s[32], dp[32];
+                tmem_ld32(tS + lane_base + c0, s);
+                tmem_ld32(tdP + lane_base + c0, dp);
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    __align__(16) __nv_bfloat16 pk[8], dk[8];
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) {
+                        const int gc = ch * 128 + c0 + g8 * 8 + x;         // global column index
+                        const int qi = KEYSIDE ? gc : gr, kj = KEYSIDE ? gr : gc;
+                        const bool ok = qi < L && kj < kLP && keyok[kj] && !(causal && kj > qi);
+                        float pv = 0.f, dsv = 0.f;
+                        if (ok) {
+                            pv = __expf(s[g8 * 8 + x] * scale - s_lse[qi]);
+                            dsv = pv * (dp[g8 * 8 + x] - s_D[qi]) * scale;
+                        }
+                        pk[x] = __float2bfloat16(pv); dk[x] = __float2bfloat16(dsv);
+                    }
+                    *reinterpret_cast<uint4*>(sEP + kmajor_off(row, c0 + g8 * 8, 128)) = *reinterpret_cast<const uint4*>(pk);
+                    *reinterpret_cast<uint4*>(sEdS + kmajor_off(row, c0 + g8 * 8, 128)) = *reinterpret_cast<const uint4*>(dk);
+                }
+            }
+            fence_async_smem();
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_bf16(128, kDH);
+#pragma unroll
+                for (int k16 = 0; k16 < 128 / 16; ++k16) {
+                    const uint32_t aoff = k16 * 2 * (128 * 16);
+                    const uint32_t boff = (ch * 16 + k16 * 2) * (kDH * 16);       // column half ch, k-group pair k16
+                    const uint32_t acc = (ch > 0 || k16 > 0) ? 1u : 0u;
+                    mma_bf16(tOdS, make_desc(smem_addr(sEdS) + aoff, 128 * 16, 128), make_desc(smem_addr(sYt) + boff, kDH * 16, 128), idesc, acc);
+                    if (KEYSIDE)
+                        mma_bf16(tOP, make_desc(smem_addr(sEP) + aoff, 128 * 16, 128), make_desc(smem_addr(sWt) + boff, kDH * 16, 128), idesc, acc);
+                }
+                mma_commit(&bar2);
+            }
+            if (!mbar_wait(&bar2, ph2)) failed = true;     // E / Yh / Wh buffers are free again
+            ph2 ^= 1;
+            fence_after_sync();
+        }
+        for (int c0 = 0; c0 < kDH; c0 += 32) {
+            float a[32];
+            tmem_ld32(tOdS + lane_base + c0, a);
+            if (gr < L) {
+                float* dst = out_ds + base + (size_t)gr * d + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+            }
+            if (KEYSIDE) {
+                tmem_ld32(tOP + lane_base + c0, a);
+                if (gr < L) {
+                    float* dst = out_p + base + (size_t)gr * d + c0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+                }
+            }
+        }
+        fence_before_sync();
+        __syncthreads();              // TMEM accumulators and the X / U tiles are reused by the next row tile
+        fence_after_sync();
+    }
+    if (failed && tid == 0) *err = 1u;
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, kTmemCols);
+}
+
 }  // namespace rsb
 
 using namespace rsb;
+
+extern "C" int32_t rsb200_attn_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
+                                   const float* lse, const int64_t* hist, int64_t B, int64_t L, int64_t heads,
+                                   int64_t head_dim, int32_t causal, float* dq, float* dk, float* dv, uint32_t* err_flag,
+                                   void* stream) {
+    RSB_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv && err_flag, RSB200_EINVAL, "null pointer");
+    RSB_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
+                aligned16(dk) && aligned16(dv), RSB200_EINVAL, "pointers must be 16-byte aligned");
+    RSB_REQUIRE(head_dim == kDH, RSB200_EUNSUPPORTED, "attention kernel is built for head_dim = 64 (got %lld)", (long long)head_dim);
+    RSB_REQUIRE(L >= 1 && L <= kLP, RSB200_EUNSUPPORTED, "sequence length must be in [1, 256] (got %lld)", (long long)L);
+    RSB_REQUIRE(B >= 1 && heads >= 1 && B * heads < ((int64_t)1 << 31), RSB200_EINVAL, "bad shape");
+    const float scale = 1.0f / sqrtf((float)head_dim);
+    cudaStream_t st = (cudaStream_t)stream;
+    RSB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    RSB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+    attn_bwd_kernel<false><<<(unsigned)(B * heads), 128, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dq, nullptr, err_flag);
+    RSB_LAUNCH_CHECK();
+    attn_bwd_kernel<true><<<(unsigned)(B * heads), 128, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dk, dv, err_flag);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D, int64_t N, int64_t K, uint32_t* err_flag,
                                        void* stream) {

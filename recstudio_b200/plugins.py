@@ -361,6 +361,51 @@ class _FusedStepFn(torch.autograd.Function):
         return gi, gu, None, None, None, None, None, None, None, None, None
 
 
+class _FusedHeadFn(torch.autograd.Function):
+    """The fused step for an arbitrary query encoder (SASRec, DSSM ...): the [B, d] encoder output is
+    the query 'table' (row 0 = padding, query b at row b + 1), so the same kernels produce the loss,
+    the item-row gradients and d loss / d query, which flows back into the encoder through autograd."""
+
+    @staticmethod
+    def forward(ctx, w_item: Tensor, query: Tensor, host, ws, pos, neg32, lqp, lqn, loss_kind, score_kind):
+        B, d = query.shape
+        wq = torch.cat([query.new_zeros(1, d), query.detach().float()], dim=0).contiguous()
+        uid = torch.arange(1, B + 1, device=query.device, dtype=torch.int64)
+        loss = fused.pair_step(ws, w_item, wq, uid, pos, neg32, loss_kind, score_kind, logq_pos=lqp, logq_neg=lqn,
+                               phases=_lib.PHASE_COUNT | _lib.PHASE_SCAN | _lib.PHASE_FWD,
+                               dense_item_grad=w_item, dense_user_grad=wq)
+        ctx.host, ctx.ws = host, ws
+        ctx.args = (wq, uid, pos, neg32, lqp, lqn, loss_kind, score_kind)
+        ctx.save_for_backward(w_item)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (w_item,) = ctx.saved_tensors
+        ws, host = ctx.ws, ctx.host
+        wq, uid, pos, neg32, lqp, lqn, loss_kind, score_kind = ctx.args
+        B, d = wq.shape[0] - 1, wq.shape[1]
+        g = g.reshape(1).to(torch.float32).contiguous()
+        common = dict(logq_pos=lqp, logq_neg=lqn, phases=_lib.PHASE_SCATTER, grad_scale_dev=g)
+        nones = (None,) * 8
+        if host.fused_grad == "dense":
+            gi, gq = torch.zeros_like(w_item), torch.zeros_like(wq)
+            fused.pair_step(ws, w_item, wq, uid, pos, neg32, loss_kind, score_kind, dense_item_grad=gi, dense_user_grad=gq, **common)
+            return (gi, gq[1:]) + nones
+        iv = torch.empty(ws.cap_item, d, dtype=torch.float32, device=w_item.device)
+        uv = torch.empty(ws.cap_user, d, dtype=torch.float32, device=w_item.device)
+        fused.pair_step(ws, w_item, wq, uid, pos, neg32, loss_kind, score_kind, item_vals=iv, user_vals=uv, **common)
+        dquery = uv[:B]                      # every query row 1..B is touched exactly once, rows come out ascending
+        if host.fused_grad == "rows":
+            ws.row_grads = (ws.item_rows, iv, None, None, ws.totals)
+            return (None, dquery) + nones
+        ri = int(ws.totals[1].item())
+        ii = ws.item_rows[:ri].unsqueeze(0).clone()
+        gi = torch.sparse_coo_tensor(ii, iv[:ri], size=w_item.shape, is_coalesced=True, check_invariants=False)
+        host._fused_sparse_ptrs = {ii.data_ptr()}
+        return (gi, dquery) + nones
+
+
 _FUSABLE_SAMPLERS = (FusedUniformSampler, FusedPopularSampler)
 _LOSS_KIND = {FusedBPRLoss: LOSS_BPR, FusedSampledSoftmaxLoss: LOSS_SSM}
 _SCORE_KIND = {FusedInnerProductScorer: SCORE_IP, FusedEuclideanScorer: SCORE_EUCLID}
@@ -380,6 +425,9 @@ class FusedRetrieverMixin:
     fused_grad = "dense"
 
     def _fused_combo(self, batch):
+        """(loss_kind, score_kind, two_tables) when the kernels implement this plugin combination, else None.
+        two_tables: both towers are plain embedding tables (BPR-style); otherwise the query encoder is an
+        arbitrary module (SASRec ...) and only the head is fused."""
         cfg = self.config["train"] if hasattr(self, "config") else {}
         if cfg.get("sampling_method", "none") != "none" or cfg.get("excluding_hist", False):
             return None
@@ -388,23 +436,22 @@ class FusedRetrieverMixin:
         lk, sk = _LOSS_KIND.get(type(self.loss_fn)), _SCORE_KIND.get(type(self.score_func))
         if lk is None or sk is None:
             return None
-        if not isinstance(self.item_encoder, torch.nn.Embedding) or not isinstance(self.query_encoder, torch.nn.Embedding):
+        if not isinstance(self.item_encoder, torch.nn.Embedding):
             return None
-        if len(getattr(self, "item_fields", [self.fiid])) != 1:
-            return None
-        if self.fuid not in batch or batch[self.fiid].dim() != 1:
+        if len(getattr(self, "item_fields", [self.fiid])) != 1 or batch[self.fiid].dim() != 1:
             return None
         if not self.item_encoder.weight.is_cuda:
             raise _lib.Rsb200Error("the fused retriever needs its tables on a CUDA device (no CPU fallback)")
-        return lk, sk
+        two_tables = isinstance(self.query_encoder, torch.nn.Embedding) and self.fuid in batch
+        return lk, sk, two_tables
 
-    def _fused_ws(self, B: int, n: int):
+    def _fused_ws(self, B: int, n: int, num_query_rows: int):
         cache = self.__dict__.setdefault("_fused_ws_cache", {})
-        wi, wu = self.item_encoder.weight, self.query_encoder.weight
-        key = (B, n, wi.shape, wu.shape, wi.device, self.fused_grad)
+        wi = self.item_encoder.weight
+        key = (B, n, wi.shape, num_query_rows, wi.device, self.fused_grad)
         if key not in cache:
             cache.clear()       # one live workspace per model: batch shape is stable within an epoch
-            cache[key] = fused.PairWorkspace(wi.shape[0], wu.shape[0], B, n, wi.shape[1], wi.device,
+            cache[key] = fused.PairWorkspace(wi.shape[0], num_query_rows, B, n, wi.shape[1], wi.device,
                                              sink="dense" if self.fused_grad == "dense" else "compact", alloc_vals=False)
         return cache[key]
 
@@ -438,21 +485,31 @@ class FusedRetrieverMixin:
         combo = self._fused_combo(batch)
         if combo is None:
             return super().training_step(batch)
-        loss_kind, score_kind = combo
-        wi, wu = self.item_encoder.weight, self.query_encoder.weight
+        loss_kind, score_kind, two_tables = combo
+        wi = self.item_encoder.weight
         if self.fused_grad == "sparse" and not self.__dict__.get("_fused_hooks", False):
             wi.register_post_accumulate_grad_hook(self._restore_coalesced)
-            wu.register_post_accumulate_grad_hook(self._restore_coalesced)
+            if two_tables:
+                self.query_encoder.weight.register_post_accumulate_grad_hook(self._restore_coalesced)
             self.__dict__["_fused_hooks"] = True
-        user = batch[self.fuid].to(wi.device, non_blocking=True).contiguous()
         pos = batch[self.fiid].to(wi.device, non_blocking=True).contiguous()
         B, n = pos.numel(), int(self.neg_count)
-        ws = self._fused_ws(B, n)
+        if two_tables:
+            wu = self.query_encoder.weight
+            user = batch[self.fuid].to(wi.device, non_blocking=True).contiguous()
+            ws = self._fused_ws(B, n, wu.shape[0])
+        else:
+            query = self.query_encoder(self._get_query_feat(batch))      # [B, d], keeps its own autograd graph
+            if query.dim() != 2 or query.shape[0] != B:
+                return super().training_step(batch)
+            ws = self._fused_ws(B, n, B + 1)
         neg32, lqn = self.sampler.fused_draw(B, n, wi.device)
         lqp = self.sampler.compute_item_p(None, pos) if (lqn is not None and loss_kind == LOSS_SSM) else None
         if loss_kind != LOSS_SSM:
             lqn = None
-        return _FusedStepFn.apply(wi, wu, self, ws, user, pos, neg32, lqp, lqn, loss_kind, score_kind)
+        if two_tables:
+            return _FusedStepFn.apply(wi, wu, self, ws, user, pos, neg32, lqp, lqn, loss_kind, score_kind)
+        return _FusedHeadFn.apply(wi, query, self, ws, pos, neg32, lqp, lqn, loss_kind, score_kind)
 
     def topk(self, batch, k, user_h=None, return_query=False):
         """BaseRetriever.topk (baseretriever.py:374-397) on rsb200_topk_full when the scorer is

@@ -91,8 +91,12 @@ class MiniRetriever(torch.nn.Module):
     def _get_item_feat(self, data):
         return data[self.fiid] if isinstance(data, dict) else data
 
-    def _get_query_feat(self, data):
-        return data[self.fuid] if isinstance(data, dict) else data
+    def _get_query_feat(self, data):                                            # baseretriever.py:86-97
+        if not isinstance(data, dict):
+            return data
+        if len(self.query_fields) == 1:
+            return data[list(self.query_fields)[0]]
+        return dict((field, value) for field, value in data.items() if field in self.query_fields)
 
     def _get_item_vector(self):
         return self.item_encoder.weight[1:]                                    # baseretriever.py:122-123
@@ -277,4 +281,39 @@ def build_synthetic(num_users: int, num_items: int, d: int, n: int, loss: str = 
         m.query_encoder.weight.normal_(0, std if init_std is None else init_std, generator=g)
         m.item_encoder.weight[0] = 0
         m.query_encoder.weight[0] = 0
+    return m
+
+
+def build_sasrec_synthetic(num_items: int, d: int, n: int, max_seq_len: int = 200, n_head: int = 2, hidden_size: int = 128,
+                           n_layer: int = 2, dropout: float = 0.0, loss: str = "ssm", fused_grad: str = "dense",
+                           device="cuda:0", init_std: float = 0.02, seed: int = 2022) -> FusedRetriever:
+    """SASRec (recstudio/model/seq/sasrec.py:70-123) on the fused path without a dataset object: the item
+    tower is a FusedEmbedding shared with the FusedSASRecQueryEncoder (sasrec.py:107), the head is the fused
+    sampled-softmax / BPR step (BASELINE config 3).  Batches: {'in_item_id' [B, L], 'seqlen' [B], 'item_id' [B]}."""
+    from . import attention
+    loss_m = plugins.FusedBPRLoss() if loss == "bpr" else plugins.FusedSampledSoftmaxLoss()
+    item = plugins.FusedEmbedding(num_items, d, padding_idx=0)
+    enc = attention.FusedSASRecQueryEncoder(fiid="item_id", embed_dim=d, max_seq_len=max_seq_len, n_head=n_head,
+                                            hidden_size=hidden_size, dropout=dropout, activation="gelu", layer_norm_eps=1e-12,
+                                            n_layer=n_layer, item_encoder=item)
+    kwargs = dict(item_encoder=item, query_encoder=enc, scorer=plugins.FusedInnerProductScorer(),
+                  sampler=plugins.FusedUniformSampler(num_items), loss=loss_m)
+    if iface.HAVE_RECSTUDIO:
+        from recstudio.utils import get_model
+        conf = get_model("SASRec")[1]
+        conf["train"].update({"negative_count": n, "gpu": None, "seed": seed})
+        conf["model"]["embed_dim"] = d
+        m = FusedRetriever(conf, fused_grad=fused_grad, **kwargs)
+        m.fuid, m.fiid, m.frating = "user_id", "item_id", "rating"
+        m.item_fields, m.neg_count = {"item_id"}, n
+    else:
+        m = FusedRetriever({"model": {"embed_dim": d}, "train": {"negative_count": n, "seed": seed}}, fused_grad=fused_grad, **kwargs)
+    m.query_fields = {"in_item_id", "seqlen"}
+    m = m.to(device)
+    with torch.no_grad():      # init_method: normal (seq/config/sasrec.yaml:11, init.py:18-27), padding row re-zeroed
+        g = torch.Generator(device=device).manual_seed(seed)
+        for p in m.parameters():
+            if p.dim() > 1:
+                p.normal_(0, init_std, generator=g)
+        m.item_encoder.weight[0] = 0
     return m

@@ -1,0 +1,42 @@
+"""Row optimizer (8(f)-1): FusedRowOptimizer on the rows left by the fused step equals the torch
+optimizer of the same name fed with the same sparse gradient."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("learner,torch_cls,kw", [("sgd", torch.optim.SGD, {}), ("adagrad", torch.optim.Adagrad, {}),
+                                                    ("sparse_adam", torch.optim.SparseAdam, {})])
+def test_row_optimizer_matches_torch(learner, torch_cls, kw):
+    from recstudio_b200 import retriever, rowopt
+    U, N, d, B, n = 200, 3000, 64, 64, 50
+    a = retriever.build_synthetic(U, N, d, n, fused_grad="rows", device=DEV, init_std=0.2, seed=1)
+    b = retriever.build_synthetic(U, N, d, n, fused_grad="sparse", device=DEV, init_std=0.2, seed=1)
+    assert torch.equal(a.item_encoder.weight, b.item_encoder.weight)
+    opt_a = rowopt.FusedRowOptimizer(a, learner, lr=0.05)
+    opt_b = torch_cls(b.parameters(), lr=0.05, **kw)
+    gen = torch.Generator().manual_seed(0)
+    for it in range(4):
+        batch = {"user_id": torch.randint(1, U, (B,), generator=gen).to(DEV), "item_id": torch.randint(1, N, (B,), generator=gen).to(DEV),
+                 "rating": torch.ones(B, device=DEV)}
+        for m, opt in ((a, opt_a), (b, opt_b)):
+            torch.manual_seed(100 + it)                       # identical negatives for both models
+            opt.zero_grad()
+            loss = m.training_step(dict(batch))
+            loss.backward()
+            opt.step()
+        for wa, wb in ((a.item_encoder.weight, b.item_encoder.weight), (a.query_encoder.weight, b.query_encoder.weight)):
+            scale = wb.abs().max().item()
+            assert (wa - wb).abs().max().item() <= 2e-6 * scale, (learner, it)
+    assert float(a.item_encoder.weight[0].abs().sum()) == 0.0     # padding row untouched
+
+
+def test_row_optimizer_needs_rows():
+    from recstudio_b200 import _lib, retriever, rowopt
+    m = retriever.build_synthetic(20, 100, 32, 5, fused_grad="rows", device=DEV)
+    with pytest.raises(_lib.Rsb200Error):
+        rowopt.FusedRowOptimizer(m, "sgd").step()
+    with pytest.raises(ValueError):
+        rowopt.FusedRowOptimizer(m, "adam")
