@@ -245,6 +245,26 @@ class FusedRetriever(plugins.FusedRetrieverMixin, _Base):
     def _get_loss_func(self):
         return plugins.FusedBPRLoss()
 
+    def _get_optimizers(self):
+        """The reference's documented multi-learner hook (recommender.py:403-406).  With
+        ``fused_grad='rows'`` the two embedding tables are stepped by ``FusedRowOptimizer`` straight from
+        the fused step's workspace; every other parameter keeps the reference's optimizer."""
+        if self.fused_grad != "rows":
+            return super()._get_optimizers()
+        from .rowopt import FusedRowOptimizer
+        tr = self.config["train"]
+        name = str(tr.get("learner", "adam")).lower()
+        learner = {"sgd": "sgd", "adagrad": "adagrad"}.get(name, "sparse_adam")      # adam / sparse_adam -> SparseAdam semantics
+        lr = tr.get("learning_rate", 0.001)
+        opts = [{"optimizer": FusedRowOptimizer(self, learner, lr=lr)}]
+        tables = {id(self.item_encoder.weight)}
+        if isinstance(self.query_encoder, torch.nn.Embedding):
+            tables.add(id(self.query_encoder.weight))
+        rest = [p for p in self.parameters() if id(p) not in tables]
+        if rest:
+            opts.append({"optimizer": self._get_optimizer(name, rest, lr, tr.get("weight_decay", 0))})
+        return opts
+
 
 class FusedBPR(FusedRetriever):
     """The reference's BPR (recstudio/model/mf/bpr.py:7-25) on the fused path."""
