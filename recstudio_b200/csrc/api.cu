@@ -147,6 +147,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         p.num_items = (int)a->num_items; p.num_users = (int)a->num_users; p.B = (int)B; p.n = (int)n; p.D = (int)a->d;
         const double denom = (a->loss_kind == RSB200_LOSS_BPR) ? (double)B * (double)(n > 0 ? n : 1) : (double)B;
         p.loss_scale = (float)(1.0 / (denom > 0 ? denom : 1.0));
+        p.prefetch = (a->variant == 3) ? 1 : 0;
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
         if (rc) return rc;

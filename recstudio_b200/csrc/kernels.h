@@ -16,6 +16,7 @@ struct FwdParams {
     int num_items, num_users, B, n, D;
     float coef_scale;   // grad_scale / (B n) for BPR, grad_scale / B for SSM
     float loss_scale;   // 1 / (B n)              for BPR, 1 / B              for SSM
+    int prefetch;       // variant 3: L2-prefetch the next batch's rows
 };
 
 struct ScatterParams {

@@ -378,6 +378,15 @@ pair_fwd_kernel(const FwdParams p) {
             }
             cur = nxt; nxt = nn;
         } else {
+            // variant 3: fetch the ids of the NEXT batch now and ask L2 for its rows (one prefetch per
+            // 128-byte line, issued by the lane that holds the id), so that next batch's loads are L2 hits
+            if (p.prefetch && jb + 32 < j1) {
+                nxt = load_meta<LOSS>(p, rowbase, jb + 32, j1, lane);
+                if (jb + 32 + lane < j1) {
+                    const char* rp = reinterpret_cast<const char*>(p.w_item + (size_t)nxt.id * D);
+                    for (int o = 0; o < D * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(rp + o));
+                }
+            }
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 if (jb + g * LOADS < j1) {            // warp-uniform
@@ -390,7 +399,8 @@ pair_fwd_kernel(const FwdParams p) {
                 if (cur.slot != kNoSlot)
                     p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
             }
-            if (jb + 32 < j1) cur = load_meta<LOSS>(p, rowbase, jb + 32, j1, lane);
+            if (p.prefetch) cur = nxt;
+            else if (jb + 32 < j1) cur = load_meta<LOSS>(p, rowbase, jb + 32, j1, lane);
         }
     }
 

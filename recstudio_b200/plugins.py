@@ -519,6 +519,9 @@ class FusedRetrieverMixin:
         item_w = getattr(self.item_encoder, "weight", None)
         fusable = (sk is not None and not getattr(self, "use_index", False) and isinstance(self.item_encoder, torch.nn.Embedding)
                    and len(getattr(self, "item_fields", [self.fiid])) == 1 and item_w is not None and item_w.is_cuda)
+        more = user_h.size(1) if user_h is not None else 0
+        if fusable and (k + more + 8 > 1024 or k > item_w.shape[0] - 1):
+            fusable = False                      # candidate set too large for the in-smem final sort: reference path
         if not fusable:
             return super().topk(batch, k, user_h, return_query)
         from . import topk as _topk
