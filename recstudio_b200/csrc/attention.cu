@@ -82,6 +82,47 @@ constexpr int kDH = 64;        // head dim
 constexpr uint32_t kTmemCols = 512;
 constexpr size_t kAttnSmem = (size_t)kLP * kDH * 2 * 3 + (size_t)128 * kLP * 2 + kLP;   // Q, K, Vt, P, key-valid bytes
 
+// ---------------------------------------------------------------------------------------------
+// Operand staging: fp32 global -> bf16 shared memory in the interleaved K-major layout, one 16-byte
+// shared-memory store per 8 elements (a whole 16-byte chunk of the layout), conflict-free.
+__device__ __forceinline__ uint4 pack8(const float4 a, const float4 b) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    return u;
+}
+// natural tile: dst[r][c] = src[(row0 + r) * ld + c], r < R (rows >= L are zero), c < 64
+__device__ __forceinline__ void stage_natural(unsigned char* dst, const float* __restrict__ src, int row0, int L, int ld, int R, int tid) {
+    for (int i = tid; i < R * (kDH / 8); i += 128) {
+        const int r = i % R, cg = i / R;                     // consecutive threads -> consecutive rows: contiguous 16-B stores
+        float4 a = make_float4(0, 0, 0, 0), b = a;
+        if (row0 + r < L) {
+            const float* p = src + (size_t)(row0 + r) * ld + cg * 8;
+            a = ldg128(p); b = ldg128(p + 4);
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)cg * (R * 16) + r * 16) = pack8(a, b);
+    }
+}
+// transposed tile [64 x 256]: dst[c][j] = src[j * ld + c]  (rows = head dim, K = sequence positions)
+__device__ __forceinline__ void stage_transposed(unsigned char* dst, const float* __restrict__ src, int L, int ld, int tid) {
+    for (int i = tid; i < (kLP / 8) * (kDH / 4); i += 128) {
+        const int c4 = i % (kDH / 4), jg = i / (kDH / 4);    // 16 consecutive threads read 256 contiguous bytes of one row
+        float4 f[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int j = jg * 8 + x;
+            f[x] = (j < L) ? ldg128(src + (size_t)j * ld + c4 * 4) : make_float4(0, 0, 0, 0);
+        }
+        unsigned char* base = dst + (size_t)jg * (kDH * 16) + (c4 * 4) * 16;
+        *reinterpret_cast<uint4*>(base) = pack8(make_float4(f[0].x, f[1].x, f[2].x, f[3].x), make_float4(f[4].x, f[5].x, f[6].x, f[7].x));
+        *reinterpret_cast<uint4*>(base + 16) = pack8(make_float4(f[0].y, f[1].y, f[2].y, f[3].y), make_float4(f[4].y, f[5].y, f[6].y, f[7].y));
+        *reinterpret_cast<uint4*>(base + 32) = pack8(make_float4(f[0].z, f[1].z, f[2].z, f[3].z), make_float4(f[4].z, f[5].z, f[6].z, f[7].z));
+        *reinterpret_cast<uint4*>(base + 48) = pack8(make_float4(f[0].w, f[1].w, f[2].w, f[3].w), make_float4(f[4].w, f[5].w, f[6].w, f[7].w));
+    }
+}
+
 __global__ void __launch_bounds__(128, 1)
 attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 const int64_t* __restrict__ hist, int L, int heads, int causal, float scale,
@@ -102,21 +143,10 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     const float* vb = v + (size_t)b * L * d + h * kDH;
 
     // ---- stage operands (fp32 -> bf16), zero beyond L ---------------------------------------
-    for (int i = tid; i < kLP * (kDH / 4); i += 128) {
-        const int r = i / (kDH / 4), c = (i % (kDH / 4)) * 4;
-        float4 fq = make_float4(0, 0, 0, 0), fk = fq, fv = fq;
-        if (r < L) {
-            fq = ldg128(qb + (size_t)r * d + c); fk = ldg128(kb + (size_t)r * d + c); fv = ldg128(vb + (size_t)r * d + c);
-        }
-        const float aq[4] = {fq.x, fq.y, fq.z, fq.w}, ak[4] = {fk.x, fk.y, fk.z, fk.w}, av[4] = {fv.x, fv.y, fv.z, fv.w};
-        unsigned char* qt = sQ + (size_t)(r >> 7) * (128 * kDH * 2);
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            *reinterpret_cast<__nv_bfloat16*>(qt + kmajor_off(r & 127, c + x, 128)) = __float2bfloat16(aq[x]);
-            *reinterpret_cast<__nv_bfloat16*>(sK + kmajor_off(r, c + x, kLP)) = __float2bfloat16(ak[x]);
-            *reinterpret_cast<__nv_bfloat16*>(sVt + kmajor_off(c + x, r, kDH)) = __float2bfloat16(av[x]);
-        }
-    }
+    stage_natural(sQ, qb, 0, L, d, 128, tid);
+    stage_natural(sQ + 128 * kDH * 2, qb, 128, L, d, 128, tid);
+    stage_natural(sK, kb, 0, L, d, kLP, tid);
+    stage_transposed(sVt, vb, L, d, tid);
     for (int j = tid; j < kLP; j += 128) keyok[j] = (j < L && (hist == nullptr || hist[(size_t)b * L + j] != 0)) ? 1 : 0;
     if (warp == 0) {
         tmem_alloc(&tmem_slot, kTmemCols);
@@ -255,27 +285,8 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     const float* U = (KEYSIDE ? v : d_o) + base;      // rows operand of dP
     const float* W = (KEYSIDE ? d_o : v) + base;      // cols operand of dP
 
-    auto put = [](unsigned char* dst, uint32_t off, float x) { *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16(x); };
-    // natural [128 x 64] tile of rows row0.. of src
-    auto stage_rows = [&](unsigned char* dst, const float* src, int row0) {
-        for (int i = tid; i < 128 * (kDH / 4); i += 128) {
-            const int r = i / (kDH / 4), c = (i % (kDH / 4)) * 4;
-            float4 f = make_float4(0, 0, 0, 0);
-            if (row0 + r < L) f = ldg128(src + (size_t)(row0 + r) * d + c);
-            put(dst, kmajor_off(r, c, 128), f.x); put(dst, kmajor_off(r, c + 1, 128), f.y);
-            put(dst, kmajor_off(r, c + 2, 128), f.z); put(dst, kmajor_off(r, c + 3, 128), f.w);
-        }
-    };
-    // transposed [64 x 256]: element (c, j) = src[j][c]
-    auto stage_t = [&](unsigned char* dst, const float* src) {
-        for (int i = tid; i < kLP * (kDH / 4); i += 128) {
-            const int j = i / (kDH / 4), c = (i % (kDH / 4)) * 4;
-            float4 f = make_float4(0, 0, 0, 0);
-            if (j < L) f = ldg128(src + (size_t)j * d + c);
-            put(dst, kmajor_off(c, j, kDH), f.x); put(dst, kmajor_off(c + 1, j, kDH), f.y);
-            put(dst, kmajor_off(c + 2, j, kDH), f.z); put(dst, kmajor_off(c + 3, j, kDH), f.w);
-        }
-    };
+    auto stage_rows = [&](unsigned char* dst, const float* src, int row0) { stage_natural(dst, src, row0, L, d, 128, tid); };
+    auto stage_t = [&](unsigned char* dst, const float* src) { stage_transposed(dst, src, L, d, tid); };
     stage_t(sYt, Y);
     if (KEYSIDE) stage_t(sWt, W);
     for (int i = tid; i < kLP; i += 128) {

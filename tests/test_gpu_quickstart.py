@@ -23,6 +23,11 @@ def test_bpr_ml100k_reference_trainer_drop_in():
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
     assert r.returncode == 0 and line, (r.stdout[-1500:], r.stderr[-3000:])
     res = json.loads(line[-1][7:])
+    try:                                           # keep the numbers as evidence (gpurun merges this directory back)
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        json.dump(res, open(os.path.join(REPO, "gpurun_out", "ml100k_dropin.json"), "w"), indent=1)
+    except OSError:
+        pass
     ref, fd, fs = res["reference"], res["fused_dense"], res["fused_sparse"]
     assert fd["encoder"] == "FusedEmbedding" and fd["sampler"] == "FusedUniformSampler" and fd["fused_ws"], fd
     assert ref["encoder"] == "Embedding" and not ref["fused_ws"]

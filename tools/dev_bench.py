@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--score", type=int, default=0)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--sampler", default="uniform", choices=["uniform", "popular"])
+    ap.add_argument("--mode", type=int, default=0, help="PopularSamplerModel mode (0 log, 2 count^0.75)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(2022)
@@ -30,12 +32,23 @@ def main():
     user = torch.randint(1, a.U, (a.B,), device=dev)
     pos = torch.randint(1, a.N, (a.B,), device=dev)
     ws = fused.PairWorkspace(a.N, a.U, a.B, a.n, a.d, dev)
+    pop = None
+    if a.sampler == "popular":
+        import numpy as np
+        from recstudio_b200 import plugins
+        rng = np.random.RandomState(0)
+        counts = np.floor(rng.zipf(1.05, size=a.N)).clip(max=1e9)            # Zipf(1.05) interaction counts
+        counts[0] = 0
+        pop = plugins.FusedPopularSampler(counts, mode=a.mode).to(dev)
     names = ["sample", "count", "scan", "fwd", "scatter"]
     tot = {k: 0.0 for k in names}
     for it in range(a.steps + 3):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record()
-        _, neg32 = sampling.uniform_draw(a.N, a.B, a.n, dev, want_i64=False, want_i32=True)
+        if pop is None:
+            _, neg32 = sampling.uniform_draw(a.N, a.B, a.n, dev, want_i64=False, want_i32=True)
+        else:
+            neg32, _lq = pop.fused_draw(a.B, a.n, dev)
         ev[1].record()
         for i, ph in enumerate((_lib.PHASE_COUNT, _lib.PHASE_SCAN, _lib.PHASE_FWD, _lib.PHASE_SCATTER)):
             loss = fused.pair_step(ws, wi, wu, user, pos, neg32, a.loss, a.score, phases=ph, variant=a.variant)

@@ -2,10 +2,11 @@
 mkdir -p gpurun_out
 timeout 2700 python -m pytest tests -q -m gpu --timeout 1500 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-grep -E "passed|failed|FAILED|ERROR|Error|assert|^E " gpurun_out/pytest_gpu.log | head -60
+grep -E "passed|failed|FAILED|ERROR|Error|assert|^E " gpurun_out/pytest_gpu.log | head -40
 rm -f gpurun_out/dev_bench.log
-for cfg in "--loss 0 --score 0 --variant 0" "--loss 0 --score 0 --variant 3" "--loss 1 --score 0 --variant 3"; do
+for cfg in "--loss 1 --sampler popular --mode 0" "--loss 1 --sampler popular --mode 2" "--N 100000001 --steps 5"; do
   echo "# $cfg" >> gpurun_out/dev_bench.log
-  timeout 300 python tools/dev_bench.py $cfg >> gpurun_out/dev_bench.log 2>&1
+  timeout 600 python tools/dev_bench.py $cfg >> gpurun_out/dev_bench.log 2>&1
 done
-cut -c1-330 gpurun_out/dev_bench.log
+cut -c1-420 gpurun_out/dev_bench.log
+timeout 600 python tools/dev_bench_c3.py > gpurun_out/dev_c3.json 2> gpurun_out/dev_c3.err; cat gpurun_out/dev_c3.json; tail -3 gpurun_out/dev_c3.err
