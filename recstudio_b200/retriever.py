@@ -223,11 +223,21 @@ class FusedRetriever(plugins.FusedRetrieverMixin, _Base):
     sampler=, loss=`` -- any of them may be a reference plugin, the fused path engages when the
     combination is recognised."""
 
-    def __init__(self, config: Dict = None, fused_grad: str = "dense", **kwargs):
+    def __init__(self, config: Dict = None, fused_grad: str = "dense", device_loader: bool = False, **kwargs):
         super().__init__(config, **kwargs)
         if fused_grad not in ("dense", "sparse", "rows"):
             raise ValueError("fused_grad must be 'dense', 'sparse' or 'rows'")
         self.fused_grad = fused_grad
+        self.device_loader = device_loader
+
+    def _get_train_loaders(self, train_data, ddp=False):
+        """recommender.py:384-388.  With ``device_loader=True`` the interaction columns live on the GPU and
+        batches are sliced there (same epoch permutation as the reference's DataSampler)."""
+        if not self.device_loader:
+            return super()._get_train_loaders(train_data, ddp)
+        from .loader import DeviceBatchLoader
+        dev = next(self.parameters()).device
+        return [DeviceBatchLoader.from_dataset(train_data, self.config["train"]["batch_size"], dev, shuffle=True, drop_last=False)]
 
     # subclass hooks of BaseRetriever (baseretriever.py:83-115, recommender.py:369-370)
     def _get_item_encoder(self, train_data):

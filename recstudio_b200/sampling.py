@@ -54,7 +54,9 @@ def build_guide(table: torch.Tensor, guide_bits: Optional[int] = None):
     """guide[k] = searchsorted(table, k / 2^bits): O(1)-expected replacement of the bisection."""
     n = table.numel()
     if guide_bits is None:
-        guide_bits = max(1, min(24, (max(n, 2) - 1).bit_length()))
+        # ~N/4 guide entries, at most 2^22 (16 MB): guide + table + pop_prob (4 B/item each) then stay inside the
+        # 126 MB L2 at N = 10 M (a 2^24-entry guide pushed the random reads of the draw out to DRAM: 0.24 ms/step)
+        guide_bits = max(1, min(22, (max(n, 2) - 1).bit_length() - 2))
     guide = torch.empty((1 << guide_bits) + 1, dtype=torch.int32, device=table.device)
     with torch.cuda.device(table.device):
         check(lib().rsb200_popular_build_guide(ptr(table), n, guide_bits, ptr(guide), stream_ptr()), "build_guide")

@@ -30,12 +30,13 @@ from recstudio_b200.retriever import FusedBPR  # noqa: E402
 EPOCHS = int(os.environ.get("RSB_EPOCHS", "8"))
 
 
-def run(kind, grad_mode="dense", learner="adam"):
+def run(kind, grad_mode="dense", learner="adam", sampling_method="none", negative_count=1, device_loader=False):
     conf = get_model("BPR")[1]
-    conf["train"].update({"gpu": [0], "epochs": EPOCHS, "seed": 2022, "learner": learner, "early_stop_patience": 100})
+    conf["train"].update({"gpu": [0], "epochs": EPOCHS, "seed": 2022, "learner": learner, "early_stop_patience": 100,
+                          "sampling_method": sampling_method, "negative_count": negative_count})
     data_conf = {"user_feat_name": None}                 # pandas-3 CoW workaround; BPR uses ids only
     data_conf.update(conf["data"])
-    model = BPR(conf) if kind == "reference" else FusedBPR(conf, fused_grad=grad_mode)
+    model = BPR(conf) if kind == "reference" else FusedBPR(conf, fused_grad=grad_mode, device_loader=device_loader)
     datasets = TripletDataset(name="ml-100k", config=data_conf).build(**conf["data"])
     logging.getLogger("recstudio").setLevel(logging.ERROR)
     val = model.fit(*datasets[:2], run_mode="light")
@@ -50,5 +51,11 @@ def run(kind, grad_mode="dense", learner="adam"):
 
 if __name__ == "__main__":
     res = {"reference": run("reference"), "fused_dense": run("fused", "dense"),
-           "fused_sparse": run("fused", "sparse", learner="sparse_adam"), "epochs": EPOCHS, "torch": torch.__version__}
+           "fused_sparse": run("fused", "sparse", learner="sparse_adam"),
+           "fused_device_loader": run("fused", "dense", device_loader=True),      # 8(f)-3: batches sliced on the GPU
+           # sampling_method 'dns' (baseretriever.py:313-343) is outside the fused combination: the reference's own
+           # forward / sampling code runs on top of the standalone CUDA plugins (gather, scorer, loss)
+           "reference_dns": run("reference", sampling_method="dns", negative_count=[8, 2]),
+           "fused_dns": run("fused", "dense", sampling_method="dns", negative_count=[8, 2]),
+           "epochs": EPOCHS, "torch": torch.__version__}
     print("RESULT " + json.dumps(res))

@@ -138,6 +138,55 @@ def test_random_vs_oracle(case, loss, scorer):
     assert tot[0] == int((neg > 0).sum() + (pos > 0).sum()) and tot[2] == int((user > 0).sum())
 
 
+EDGE = [
+    # U, N, d, B, n   -- edge shapes: single query, single negative, tiny / maximum row width, one real item,
+    (5, 50, 128, 1, 1),         # B = 1, n = 1
+    (5, 2, 4, 3, 6),            # a catalog of ONE item (ids in {0, 1}), d = 4 (one active lane)
+    (30, 400, 512, 9, 40),      # d = 512: four float4 per lane
+    (30, 400, 8, 300, 3),       # many queries per CTA in the warp-per-query path, d = 8
+    (16, 3000, 128, 2, 5000),   # n far above 1024 (156 batches per warp), non multiple of 32
+    (16, 300, 64, 17, 255),     # n = 255: last warp-per-query size before the CTA-per-query switch
+    (16, 300, 64, 17, 256),     # n = 256: first CTA-per-query size
+]
+
+
+@pytest.mark.parametrize("case", EDGE)
+@pytest.mark.parametrize("loss", [R.BPR, R.SSM])
+def test_edge_shapes_vs_oracle(case, loss):
+    U, N, d, B, n = case
+    g = torch.Generator().manual_seed(B * 7 + n)
+    wi = torch.randn(N, d, generator=g) * 0.5; wi[0] = 0
+    wu = torch.randn(U, d, generator=g) * 0.5; wu[0] = 0
+    user = torch.randint(1, U, (B,), generator=g)
+    pos = torch.randint(1, N, (B,), generator=g)
+    neg = torch.randint(0 if N == 2 else 1, N, (B, n), generator=g)
+    ref = R.training_step_aten(wi, wu, user, pos, neg, loss=loss, scorer=R.IP)
+    out = _run(wi, wu, user, pos, neg, loss, R.IP)
+    assert abs(out["loss"] - ref["loss"].item()) <= RTOL * abs(ref["loss"].item())
+    _check_grads(out, ref["d_item"].numpy(), ref["d_user"].numpy())
+
+
+def test_all_padding_and_all_duplicate_batches():
+    """(a) every id of the batch is the padding id: loss is defined, no gradient row is produced;
+    (b) every negative of every query is the same item: one gradient row with B*n contributions."""
+    g = torch.Generator().manual_seed(3)
+    N, U, d, B, n = 64, 9, 32, 6, 40
+    wi = torch.randn(N, d, generator=g); wi[0] = 0
+    wu = torch.randn(U, d, generator=g); wu[0] = 0
+    z = torch.zeros(B, dtype=torch.int64)
+    out = _run(wi, wu, z, z, torch.zeros(B, n, dtype=torch.int64), R.BPR, R.IP)
+    assert abs(out["loss"] - np.log(2.0)) < 1e-6 and out["item_rows"].size == 0 and out["user_rows"].size == 0
+    assert out["ws"].totals.tolist() == [0, 0, 0, 0]
+    user = torch.randint(1, U, (B,), generator=g); pos = torch.randint(1, N, (B,), generator=g)
+    neg = torch.full((B, n), 7, dtype=torch.int64)
+    for loss in (R.BPR, R.SSM):
+        ref = R.training_step_aten(wi, wu, user, pos, neg, loss=loss, scorer=R.IP)
+        out = _run(wi, wu, user, pos, neg, loss, R.IP)
+        assert abs(out["loss"] - ref["loss"].item()) <= RTOL * abs(ref["loss"].item())
+        _check_grads(out, ref["d_item"].numpy(), ref["d_user"].numpy())
+        assert 7 in out["item_rows"]
+
+
 def test_accumulate_and_grad_scale():
     g = load_golden("step_small_ssm_ip")
     from recstudio_b200 import fused

@@ -35,6 +35,17 @@ def test_bpr_ml100k_reference_trainer_drop_in():
     assert abs(fd["item_norm"] - ref["item_norm"]) <= 2e-3 * ref["item_norm"], (fd, ref)
     for k, v in ref["test"].items():
         assert abs(fd["test"][k] - v) <= 0.01, (k, fd["test"][k], v)
+    # device-resident batch producer: same epoch permutations => same model
+    fl = res["fused_device_loader"]
+    assert abs(fl["item_norm"] - ref["item_norm"]) <= 2e-3 * ref["item_norm"], (fl, ref)
+    for k, v in ref["test"].items():
+        assert abs(fl["test"][k] - v) <= 0.01, (k, fl["test"][k], v)
+    # a sampling method the kernels do not fuse: reference code path over the standalone plugins, same stream of
+    # negatives => same model up to the summation-order noise of the standalone scorer kernels
+    rd, fdn = res["reference_dns"], res["fused_dns"]
+    assert abs(fdn["item_norm"] - rd["item_norm"]) <= 5e-3 * rd["item_norm"], (fdn, rd)
+    for k, v in rd["test"].items():
+        assert abs(fdn["test"][k] - v) <= 0.02, (k, fdn["test"][k], v)
     # sparse gradients + SparseAdam is a different optimizer (moments of untouched rows do not decay):
     # it must train to a comparable quality, not to identical numbers
     assert fs["test"]["ndcg@10"] > 0.3 * ref["test"]["ndcg@10"], (fs["test"], ref["test"])

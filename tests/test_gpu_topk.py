@@ -90,6 +90,26 @@ def test_random_vs_float64_oracle(shape):
     assert_topk_equiv(s.cpu(), i.cpu(), want_s, want_i)
 
 
+def test_topk_edges():
+    """k = every item, a single query, history that masks the whole top, and the error for k > items."""
+    from recstudio_b200 import _lib, topk
+    g = torch.Generator().manual_seed(8)
+    N, d = 20, 8
+    w = torch.randint(-3, 4, (N, d), generator=g).float(); w[0] = 0
+    q = torch.randint(-3, 4, (3, d), generator=g).float()
+    want_s, want_i = T.topk_exact(q.numpy(), w[1:].numpy(), N - 1, None)
+    s, i = topk.topk_full(q.to(DEV), w.to(DEV), N - 1, None)
+    assert np.array_equal(i.cpu().numpy(), want_i) and np.array_equal(s.cpu().numpy().astype(np.float64), want_s)
+    hist = torch.from_numpy(want_i[:, :5].copy())                      # mask exactly the five best of every query
+    want_s2, want_i2 = T.topk_exact(q.numpy(), w[1:].numpy(), 4, hist.numpy())
+    s2, i2 = topk.topk_full(q[:1].to(DEV), w.to(DEV), 4, hist[:1].to(DEV))      # Be = 1
+    assert np.array_equal(i2.cpu().numpy(), want_i2[:1]) and np.array_equal(i2.cpu().numpy(), want_i[:1, 5:9])
+    with pytest.raises(_lib.Rsb200Error):
+        topk.topk_full(q.to(DEV), w.to(DEV), N, None)                  # only N - 1 items exist
+    with pytest.raises(_lib.Rsb200Error):
+        topk.topk_full(q.to(DEV), w.to(DEV), 4, torch.ones(3, 2000, dtype=torch.int64, device=DEV))   # k + H too large
+
+
 @pytest.mark.parametrize("k", [10, 100])
 def test_config4_shape_vs_reference_algorithm(k):
     """1M items x 128, Be = 128, H = 64: the reference's topk (matmul -> topk(k+H) -> mask ->

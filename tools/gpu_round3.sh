@@ -4,9 +4,8 @@ timeout 2700 python -m pytest tests -q -m gpu --timeout 1500 > gpurun_out/pytest
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 grep -E "passed|failed|FAILED|ERROR|Error|assert|^E " gpurun_out/pytest_gpu.log | head -40
 rm -f gpurun_out/dev_bench.log
-for cfg in "--loss 1 --sampler popular --mode 0" "--loss 1 --sampler popular --mode 2" "--N 100000001 --steps 5"; do
+for cfg in "--loss 1 --sampler popular --mode 0"; do
   echo "# $cfg" >> gpurun_out/dev_bench.log
   timeout 600 python tools/dev_bench.py $cfg >> gpurun_out/dev_bench.log 2>&1
 done
 cut -c1-420 gpurun_out/dev_bench.log
-timeout 600 python tools/dev_bench_c3.py > gpurun_out/dev_c3.json 2> gpurun_out/dev_c3.err; cat gpurun_out/dev_c3.json; tail -3 gpurun_out/dev_c3.err
