@@ -134,14 +134,28 @@ select_groups_kernel(const float* __restrict__ gmax, int ngroups, int K, int32_t
             if ((key & pmask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
         }
         __syncthreads();
-        if (tid == 0) {                                    // walk bins from the top (2048 steps at most)
-            uint32_t acc = 0; int bsel = 0;
-            for (int bn = nb - 1; bn >= 0; --bn) {
-                if (acc + hist[bn] >= need) { bsel = bn; break; }
-                acc += hist[bn];
+        if (tid < 32) {
+            // find the bin (from the top) where the running count reaches `need`: lane L owns the L-th highest
+            // block of nb/32 bins; one warp scan over the block sums, then one lane walks its <= 64 bins
+            const int per = nb >> 5, hi = nb - tid * per, lo = hi - per;
+            uint32_t local = 0;
+            for (int bn = lo; bn < hi; ++bn) local += hist[bn];
+            uint32_t pre = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, pre, o);
+                if (tid >= o) pre += t;
             }
-            s_prefix = prefix | ((uint32_t)bsel << sh);
-            s_need = need - acc;
+            const unsigned m = __ballot_sync(kFull, pre >= need);      // non-empty: the total count is >= need
+            if (tid == __ffs(m) - 1) {
+                uint32_t acc = pre - local; int bsel = lo;
+                for (int bn = hi - 1; bn >= lo; --bn) {
+                    if (acc + hist[bn] >= need) { bsel = bn; break; }
+                    acc += hist[bn];
+                }
+                s_prefix = prefix | ((uint32_t)bsel << sh);
+                s_need = need - acc;
+            }
         }
         __syncthreads();
         prefix = s_prefix; need = s_need;

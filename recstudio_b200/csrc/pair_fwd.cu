@@ -590,6 +590,8 @@ static int32_t launch_fwd_vlsp(const FwdParams& p, cudaStream_t st) {
         pair_fwd_kernel<VPL, LOSS, SCORE, true, PIPE><<<p.B, kThreads, smem, st>>>(p);
     } else {
         size_t smem = (size_t)kWarps * (3 * p.D + 4) * sizeof(float);
+        if (smem > 48 * 1024)            // d = 512: 49 KB, above the default dynamic shared-memory limit
+            RSB_CUDA(cudaFuncSetAttribute(pair_fwd_kernel<VPL, LOSS, SCORE, false, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pair_fwd_kernel<VPL, LOSS, SCORE, false, PIPE><<<(unsigned)cdiv(p.B, kWarps), kThreads, smem, st>>>(p);
     }
     RSB_LAUNCH_CHECK();

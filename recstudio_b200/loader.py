@@ -44,6 +44,9 @@ class DeviceBatchLoader:
         return self.n // self.batch_size if self.drop_last else (self.n + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
+        # torch's DataLoader iterator draws its `_base_seed` from the global CPU generator BEFORE the (lazy)
+        # DataSampler body runs (torch/utils/data/dataloader.py:705-710): consume the same number first
+        torch.empty((), dtype=torch.int64).random_()
         if self.shuffle:                                         # dataset.py:1710-1722, same RNG consumption
             generator = torch.Generator()
             generator.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))

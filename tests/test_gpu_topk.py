@@ -106,8 +106,13 @@ def test_topk_edges():
     assert np.array_equal(i2.cpu().numpy(), want_i2[:1]) and np.array_equal(i2.cpu().numpy(), want_i[:1, 5:9])
     with pytest.raises(_lib.Rsb200Error):
         topk.topk_full(q.to(DEV), w.to(DEV), N, None)                  # only N - 1 items exist
+    # a tiny catalog caps the candidate set at its number of groups: a very wide history is fine here ...
+    s3, i3 = topk.topk_full(q.to(DEV), w.to(DEV), 4, torch.zeros(3, 2000, dtype=torch.int64, device=DEV))
+    assert np.array_equal(i3.cpu().numpy(), want_i[:, :4])
+    # ... but on a large catalog k + H + 8 > 1024 exceeds the in-shared-memory final sort and must fail loudly
+    wbig = torch.randn(30_000, d, generator=g)
     with pytest.raises(_lib.Rsb200Error):
-        topk.topk_full(q.to(DEV), w.to(DEV), 4, torch.ones(3, 2000, dtype=torch.int64, device=DEV))   # k + H too large
+        topk.topk_full(q.to(DEV), wbig.to(DEV), 4, torch.ones(3, 2000, dtype=torch.int64, device=DEV))
 
 
 @pytest.mark.parametrize("k", [10, 100])
