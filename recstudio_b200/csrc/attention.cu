@@ -95,6 +95,7 @@ __device__ __forceinline__ uint4 pack8(const float4 a, const float4 b) {
 }
 // natural tile: dst[r][c] = src[(row0 + r) * ld + c], r < R (rows >= L are zero), c < 64
 __device__ __forceinline__ void stage_natural(unsigned char* dst, const float* __restrict__ src, int row0, int L, int ld, int R, int tid) {
+#pragma unroll 4                                               // 8 independent 16-byte loads in flight per thread
     for (int i = tid; i < R * (kDH / 8); i += 128) {
         const int r = i % R, cg = i / R;                     // consecutive threads -> consecutive rows: contiguous 16-B stores
         float4 a = make_float4(0, 0, 0, 0), b = a;
@@ -107,6 +108,7 @@ __device__ __forceinline__ void stage_natural(unsigned char* dst, const float* _
 }
 // transposed tile [64 x 256]: dst[c][j] = src[j * ld + c]  (rows = head dim, K = sequence positions)
 __device__ __forceinline__ void stage_transposed(unsigned char* dst, const float* __restrict__ src, int L, int ld, int tid) {
+#pragma unroll 2
     for (int i = tid; i < (kLP / 8) * (kDH / 4); i += 128) {
         const int c4 = i % (kDH / 4), jg = i / (kDH / 4);    // 16 consecutive threads read 256 contiguous bytes of one row
         float4 f[8];
