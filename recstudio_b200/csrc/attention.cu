@@ -94,9 +94,9 @@ __device__ __forceinline__ uint4 pack8(const float4 a, const float4 b) {
     return u;
 }
 // natural tile: dst[r][c] = src[(row0 + r) * ld + c], r < R (rows >= L are zero), c < 64
-__device__ __forceinline__ void stage_natural(unsigned char* dst, const float* __restrict__ src, int row0, int L, int ld, int R, int tid) {
+__device__ __forceinline__ void stage_natural(unsigned char* dst, const float* __restrict__ src, int row0, int L, int ld, int R, int tid, int nt) {
 #pragma unroll 4                                               // 8 independent 16-byte loads in flight per thread
-    for (int i = tid; i < R * (kDH / 8); i += 128) {
+    for (int i = tid; i < R * (kDH / 8); i += nt) {
         const int r = i % R, cg = i / R;                     // consecutive threads -> consecutive rows: contiguous 16-B stores
         float4 a = make_float4(0, 0, 0, 0), b = a;
         if (row0 + r < L) {
@@ -107,9 +107,9 @@ __device__ __forceinline__ void stage_natural(unsigned char* dst, const float* _
     }
 }
 // transposed tile [64 x 256]: dst[c][j] = src[j * ld + c]  (rows = head dim, K = sequence positions)
-__device__ __forceinline__ void stage_transposed(unsigned char* dst, const float* __restrict__ src, int L, int ld, int tid) {
+__device__ __forceinline__ void stage_transposed(unsigned char* dst, const float* __restrict__ src, int L, int ld, int tid, int nt) {
 #pragma unroll 2
-    for (int i = tid; i < (kLP / 8) * (kDH / 4); i += 128) {
+    for (int i = tid; i < (kLP / 8) * (kDH / 4); i += nt) {
         const int c4 = i % (kDH / 4), jg = i / (kDH / 4);    // 16 consecutive threads read 256 contiguous bytes of one row
         float4 f[8];
 #pragma unroll
@@ -125,7 +125,14 @@ __device__ __forceinline__ void stage_transposed(unsigned char* dst, const float
     }
 }
 
-__global__ void __launch_bounds__(128, 1)
+// Thread layout of the attention kernels: kNW warps share every TMEM lane quarter (a warp can only touch
+// lanes 32*(warp % 4) .. +31) and split the COLUMNS, so a CTA has 4*kNW warps working on the softmax /
+// elementwise phases instead of 4 (ncu of the 4-warp version: tensor pipe 3 % active, 6 % warp occupancy,
+// 57 % of the samples in the per-row softmax).
+constexpr int kNW = 4;
+constexpr int kNT = 128 * kNW;
+
+__global__ void __launch_bounds__(kNT, 1)
 attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 const int64_t* __restrict__ hist, int L, int heads, int causal, float scale,
                 float* __restrict__ out, float* __restrict__ lse_out, uint32_t* __restrict__ err) {
@@ -137,19 +144,24 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     unsigned char* keyok = sP + (size_t)128 * kLP * 2;             // [256]
     __shared__ __align__(8) uint64_t bar_s, bar_o;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_max[kNW][128], s_sum[kNW][128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cq = warp >> 2;                                      // column slice of this warp
+    const int row = (warp & 3) * 32 + lane;                        // TMEM lane = query row inside the M tile
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int d = heads * kDH;
     const float* qb = q + (size_t)b * L * d + h * kDH;
     const float* kb = k + (size_t)b * L * d + h * kDH;
     const float* vb = v + (size_t)b * L * d + h * kDH;
+    constexpr int CW = kLP / kNW;                                  // score columns per warp slice (64)
+    constexpr int OW = kDH / kNW;                                  // output columns per warp slice (16)
 
     // ---- stage operands (fp32 -> bf16), zero beyond L ---------------------------------------
-    stage_natural(sQ, qb, 0, L, d, 128, tid);
-    stage_natural(sQ + 128 * kDH * 2, qb, 128, L, d, 128, tid);
-    stage_natural(sK, kb, 0, L, d, kLP, tid);
-    stage_transposed(sVt, vb, L, d, tid);
-    for (int j = tid; j < kLP; j += 128) keyok[j] = (j < L && (hist == nullptr || hist[(size_t)b * L + j] != 0)) ? 1 : 0;
+    stage_natural(sQ, qb, 0, L, d, 128, tid, kNT);
+    stage_natural(sQ + 128 * kDH * 2, qb, 128, L, d, 128, tid, kNT);
+    stage_natural(sK, kb, 0, L, d, kLP, tid, kNT);
+    stage_transposed(sVt, vb, L, d, tid, kNT);
+    for (int j = tid; j < kLP; j += kNT) keyok[j] = (j < L && (hist == nullptr || hist[(size_t)b * L + j] != 0)) ? 1 : 0;
     if (warp == 0) {
         tmem_alloc(&tmem_slot, kTmemCols);
         if (lane == 0) { mbar_init(&bar_s, 1); mbar_init(&bar_o, 1); fence_mbar_init(); }
@@ -159,7 +171,7 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     __syncthreads();
     fence_after_sync();
     const uint32_t tS = tmem_slot, tO = tmem_slot + 256;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     bool failed = false;
 
     const int mtiles = (L + 127) / 128;
@@ -175,10 +187,10 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
         }
         if (!mbar_wait(&bar_s, mt & 1)) failed = true;
         fence_after_sync();
-        const int row = warp * 32 + lane, gi = mt * 128 + row;       // this thread's query row
-        // pass 1: row max of the masked, scaled scores
+        const int gi = mt * 128 + row;                               // this thread's query row
+        // pass 1: max of the masked, scaled scores over this warp's column slice, then across the slices
         float mx = -INFINITY;
-        for (int c0 = 0; c0 < kLP; c0 += 32) {
+        for (int c0 = cq * CW; c0 < (cq + 1) * CW; c0 += 32) {
             float s[32];
             tmem_ld32(tS + lane_base + c0, s);
 #pragma unroll
@@ -188,9 +200,13 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
                 if (ok) mx = fmaxf(mx, s[i] * scale);
             }
         }
-        // pass 2: P = exp(s - max) (bf16, UMMA K-major layout), row sum
+        s_max[cq][row] = mx;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kNW; ++w) mx = fmaxf(mx, s_max[w][row]);
+        // pass 2: P = exp(s - max) (bf16, UMMA K-major layout), partial row sum
         float l = 0.f;
-        for (int c0 = 0; c0 < kLP; c0 += 32) {
+        for (int c0 = cq * CW; c0 < (cq + 1) * CW; c0 += 32) {
             float s[32];
             tmem_ld32(tS + lane_base + c0, s);
 #pragma unroll
@@ -207,6 +223,7 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
                 *reinterpret_cast<uint4*>(sP + kmajor_off(row, c0 + g8 * 8, 128)) = *reinterpret_cast<const uint4*>(pk);
             }
         }
+        s_sum[cq][row] = l;
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -220,22 +237,25 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
                          make_desc(va + k16 * 2 * (kDH * 16), kDH * 16, 128), idesc, k16 > 0);
             mma_commit(&bar_o);
         }
+        l = 0.f;
+#pragma unroll
+        for (int w = 0; w < kNW; ++w) l += s_sum[w][row];
         if (!mbar_wait(&bar_o, mt & 1)) failed = true;
         fence_after_sync();
         const float inv = l > 0.f ? 1.0f / l : 0.f;
-        for (int c0 = 0; c0 < kDH; c0 += 32) {
-            float o[32];
-            tmem_ld32(tO + lane_base + c0, o);
+        {
+            float o[16];
+            tmem_ld16(tO + lane_base + cq * OW, o);
             if (gi < L) {
-                float* dst = out + ((size_t)b * L + gi) * d + h * kDH + c0;
+                float* dst = out + ((size_t)b * L + gi) * d + h * kDH + cq * OW;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
+                for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
             }
         }
-        if (gi < L && lse_out) lse_out[((size_t)b * heads + h) * L + gi] = (l > 0.f) ? mx + logf(l) : -INFINITY;
+        if (cq == 0 && gi < L && lse_out) lse_out[((size_t)b * heads + h) * L + gi] = (l > 0.f) ? mx + logf(l) : -INFINITY;
         fence_before_sync();
-        __syncthreads();                 // sP / TMEM are reused by the next M tile
+        __syncthreads();                 // sP / TMEM / s_max / s_sum are reused by the next M tile
         fence_after_sync();
     }
     if (failed && tid == 0) *err = 1u;
@@ -259,7 +279,7 @@ constexpr size_t kBwdSmem = (size_t)128 * kDH * 2 * 4      // X tile, U tile, Y 
                           + (size_t)kLP * 4 * 2 + kLP;     // lse, D, key-valid
 
 template <bool KEYSIDE>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(kNT, 1)
 attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 const float* __restrict__ o, const float* __restrict__ d_o, const float* __restrict__ lse,
                 const int64_t* __restrict__ hist, int L, int heads, int causal, float scale,
@@ -287,11 +307,11 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     const float* U = (KEYSIDE ? v : d_o) + base;      // rows operand of dP
     const float* W = (KEYSIDE ? d_o : v) + base;      // cols operand of dP
 
-    auto stage_rows = [&](unsigned char* dst, const float* src, int row0) { stage_natural(dst, src, row0, L, d, 128, tid); };
-    auto stage_t = [&](unsigned char* dst, const float* src) { stage_transposed(dst, src, L, d, tid); };
+    auto stage_rows = [&](unsigned char* dst, const float* src, int row0) { stage_natural(dst, src, row0, L, d, 128, tid, kNT); };
+    auto stage_t = [&](unsigned char* dst, const float* src) { stage_transposed(dst, src, L, d, tid, kNT); };
     stage_t(sYt, Y);
     if (KEYSIDE) stage_t(sWt, W);
-    for (int i = tid; i < kLP; i += 128) {
+    for (int i = tid; i < kLP; i += kNT) {
         float dsum = 0.f, ls = 0.f;
         if (i < L) {
             const float* orow = o + base + (size_t)i * d;
@@ -310,11 +330,14 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
     __syncthreads();
     fence_after_sync();
     const uint32_t tS = tmem_slot, tdP = tmem_slot + 128, tOdS = tmem_slot + 256, tOP = tmem_slot + 320;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     bool failed = false;
     uint32_t ph1 = 0, ph2 = 0;
     const int tiles = (L + 127) / 128;
-    const int row = warp * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;                    // TMEM lane of this thread
+    const int cq = warp >> 2;                                  // column slice of this warp (see kNW)
+    constexpr int CW = 128 / kNW, OW = kDH / kNW;
+    static_assert(CW == 32 && OW == 16, "column slices are one tmem_ld32 / tmem_ld16 wide");
 
     for (int rt = 0; rt < tiles; ++rt) {
         stage_rows(sX, X, rt * 128);
@@ -340,7 +363,8 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
             if (!mbar_wait(&bar1, ph1)) failed = true;
             ph1 ^= 1;
             fence_after_sync();
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            {
+                const int c0 = cq * CW;
                 float s[32], dp[32];
                 tmem_ld32(tS + lane_base + c0, s);
                 tmem_ld32(tdP + lane_base + c0, dp);
@@ -384,20 +408,21 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
             ph2 ^= 1;
             fence_after_sync();
         }
-        for (int c0 = 0; c0 < kDH; c0 += 32) {
-            float a[32];
-            tmem_ld32(tOdS + lane_base + c0, a);
+        {
+            const int c0 = cq * OW;
+            float a[16];
+            tmem_ld16(tOdS + lane_base + c0, a);
             if (gr < L) {
                 float* dst = out_ds + base + (size_t)gr * d + c0;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
             }
             if (KEYSIDE) {
-                tmem_ld32(tOP + lane_base + c0, a);
+                tmem_ld16(tOP + lane_base + c0, a);
                 if (gr < L) {
                     float* dst = out_p + base + (size_t)gr * d + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
                 }
             }
         }
@@ -429,9 +454,9 @@ extern "C" int32_t rsb200_attn_bwd(const float* q, const float* k, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     RSB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
     RSB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    attn_bwd_kernel<false><<<(unsigned)(B * heads), 128, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dq, nullptr, err_flag);
+    attn_bwd_kernel<false><<<(unsigned)(B * heads), kNT, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dq, nullptr, err_flag);
     RSB_LAUNCH_CHECK();
-    attn_bwd_kernel<true><<<(unsigned)(B * heads), 128, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dk, dv, err_flag);
+    attn_bwd_kernel<true><<<(unsigned)(B * heads), kNT, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dk, dv, err_flag);
     RSB_LAUNCH_CHECK();
     return 0;
 }
@@ -456,7 +481,7 @@ extern "C" int32_t rsb200_attn_fwd(const float* q, const float* k, const float* 
     RSB_REQUIRE(L >= 1 && L <= kLP, RSB200_EUNSUPPORTED, "sequence length must be in [1, 256] (got %lld)", (long long)L);
     RSB_REQUIRE(B >= 1 && heads >= 1 && B * heads < ((int64_t)1 << 31), RSB200_EINVAL, "bad shape");
     RSB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    attn_fwd_kernel<<<(unsigned)(B * heads), 128, kAttnSmem, (cudaStream_t)stream>>>(
+    attn_fwd_kernel<<<(unsigned)(B * heads), kNT, kAttnSmem, (cudaStream_t)stream>>>(
         q, k, v, hist, (int)L, (int)heads, causal, 1.0f / sqrtf((float)head_dim), out, lse, err_flag);
     RSB_LAUNCH_CHECK();
     return 0;
