@@ -292,6 +292,72 @@ int32_t rsb200_attn_bwd(const float* q, const float* k, const float* v, const fl
 /* validation hook for the tcgen05 plumbing: D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T, fp32 accumulate */
 int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D, int64_t N, int64_t K, uint32_t* err_flag, void* stream);
 
+/* -------------------------------------------------------------------------
+ * 8(e)  Row-sharded item table, owner-compute ("ship queries, not rows") training step.
+ *   The same step as rsb200_pair_step (baseretriever.py:142-176,399-404 + loss.backward(),
+ *   recommender.py:638) for a GLOBAL batch of G = world x B interactions, restricted to the rows ONE
+ *   owner holds (contiguous block [row0, row0 + local_rows) of the [num_items, d] table).  No torch /
+ *   NCCL types: the three small exchanges between the phases are the caller's (NCCL, gloo, or a loop
+ *   over owners on one device):
+ *
+ *     RSB200_SHARD_PREP    -> all-reduce SUM  sp[G]                 (4 B per query)
+ *     RSB200_SHARD_FWD     -> all-gather      stats_all[rank] slices (8 B per query)
+ *     RSB200_SHARD_FINISH  -> all-reduce SUM  dq[G, d]              (d loss / d query, 4d B per query)
+ *     RSB200_SHARD_SCATTER    gradient rows of the OWNED rows (never leave the owner)
+ *
+ *   loss is the mean over the global batch (identical on every owner); gradients are those of that
+ *   global mean.  Touches of global row 0 (padding) are scored but get no gradient row.
+ */
+#define RSB200_SHARD_PREP     1
+#define RSB200_SHARD_FWD      2
+#define RSB200_SHARD_FINISH   4
+#define RSB200_SHARD_SCATTER  8
+
+typedef struct rsb200_shard_args {
+    /* owner's table block and the global batch (device pointers) */
+    const float*   w_local;     /* [local_rows, d] rows row0 .. row0+local_rows-1 of the table */
+    const float*   q_all;       /* [G, d] query vectors of the global batch                    */
+    const int64_t* pos;         /* [G]    GLOBAL positive item ids                             */
+    const int32_t* neg;         /* [G, n] GLOBAL negative item ids                             */
+    const float*   logq_pos;    /* [G]    or NULL (SampledSoftmax)                             */
+    const float*   logq_neg;    /* [G, n] or NULL                                              */
+    const float*   grad_scale_dev; /* [1] or NULL, multiplied into the gradient rows by SCATTER */
+    /* exchanged between owners by the caller */
+    float*         sp;          /* [G]    PREP: positive score if owned, else 0                */
+    float*         stats_all;   /* [world, G, 2]  FWD writes slice [rank]                      */
+    float*         dq;          /* [G, d] FWD: raw partial; FINISH: this owner's share of d loss / d query */
+    /* outputs */
+    float*         loss;        /* [1]  global mean loss (after FINISH)                        */
+    int64_t*       item_rows;   /* [cap] LOCAL row ids, ascending unique (SCATTER)             */
+    float*         item_vals;   /* COMPACT: [cap, d]; DENSE: [local_rows, d]                   */
+    uint32_t*      totals;      /* [2] = {owned touches with a gradient, unique owned rows}    */
+    /* workspace */
+    int32_t*       neg_c;       /* [G * n] compacted LOCAL ids of the owned negatives (stride n) */
+    uint32_t*      slot_neg;    /* [G * n]                                                     */
+    float*         lq_c;        /* [G * n] or NULL when logq_neg is NULL                       */
+    int32_t*       ncount;      /* [G]   owned negatives per query                             */
+    int32_t*       pos_local;   /* [G]   local row of the positive or -1                       */
+    uint32_t*      slot_pos;    /* [G]                                                         */
+    uint32_t*      off;         /* [local_rows + 1] histogram -> CSR offsets                   */
+    uint32_t*      urow;        /* [cap]                                                       */
+    uint64_t*      ent;         /* [G * (n + 1)] worst case: every touch owned here            */
+    float*         loss_part;   /* [G]                                                         */
+    float*         lse;         /* [G]                                                         */
+    uint64_t*      scan_tmp;    /* [scan_tmp_elems >= rsb200_scan_tmp_elems(local_rows)]       */
+    uint32_t*      err_flag;    /* [1] set non-zero if an id was outside [0, num_items)        */
+    /* sizes */
+    int64_t G, n, d, num_items, row0, local_rows;
+    int64_t cap;                /* capacity of urow / item_rows: >= min(G*(n+1), local_rows)   */
+    int64_t scan_tmp_elems;
+    float   grad_scale;         /* upstream gradient (loss.backward() => 1.0)                  */
+    int32_t world, rank;        /* number of owners, index of this owner in stats_all          */
+    int32_t loss_kind, score_kind, sink, accumulate;
+} rsb200_shard_args;
+
+int32_t rsb200_shard_step(const rsb200_shard_args* args, int32_t phases, void* stream);
+size_t  rsb200_sizeof_shard_args(void);
+int64_t rsb200_scan_tmp_elems(int64_t num_rows);
+
 #ifdef __cplusplus
 }
 #endif

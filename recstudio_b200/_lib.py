@@ -21,6 +21,7 @@ LOSS_BPR, LOSS_SSM, LOSS_FULL = 0, 1, 2
 SCORE_IP, SCORE_EUCLID = 0, 1
 PHASE_COUNT, PHASE_SCAN, PHASE_FWD, PHASE_SCATTER, PHASE_ALL = 1, 2, 4, 8, 15
 SINK_COMPACT, SINK_DENSE = 0, 1
+SHARD_PREP, SHARD_FWD, SHARD_FINISH, SHARD_SCATTER = 1, 2, 4, 8
 
 
 class Rsb200Error(RuntimeError):
@@ -62,6 +63,10 @@ class PairSizes(C.Structure):
     _fields_ = _struct_fields("rsb200_pair_sizes")
 
 
+class ShardArgs(C.Structure):
+    _fields_ = _struct_fields("rsb200_shard_args")
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -90,6 +95,11 @@ def lib():
         L.rsb200_sizeof_pair_args.restype = C.c_size_t
         if L.rsb200_sizeof_pair_args() != C.sizeof(PairArgs):
             raise Rsb200Error('rsb200_pair_args layout mismatch between rsb200.h and librsb200.so: rebuild')
+        L.rsb200_sizeof_shard_args.restype = C.c_size_t
+        if L.rsb200_sizeof_shard_args() != C.sizeof(ShardArgs):
+            raise Rsb200Error('rsb200_shard_args layout mismatch between rsb200.h and librsb200.so: rebuild')
+        L.rsb200_scan_tmp_elems.restype = C.c_int64
+        L.rsb200_scan_tmp_elems.argtypes = [C.c_int64]
         L.rsb200_launch_count.restype = C.c_uint64
         L.rsb200_philox_counter_offset.restype = C.c_int64
         L.rsb200_philox_counter_offset.argtypes = [C.c_int64, C.c_int32, C.c_int32]
@@ -106,6 +116,7 @@ def lib():
             "rsb200_popular_logq": [v, i64, v, i64, v, v],
             "rsb200_pair_workspace_sizes": [i64, i64, i64, i64, i64, C.POINTER(PairSizes)],
             "rsb200_pair_step": [C.POINTER(PairArgs), i32, v],
+            "rsb200_shard_step": [C.POINTER(ShardArgs), i32, v],
             "rsb200_gather_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_scatter_add_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_rows_update": [i32, v, v, v, i64, i64, v, v, v, i64, i64, f32, f32, f32, f32, v],

@@ -148,6 +148,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         const double denom = (a->loss_kind == RSB200_LOSS_BPR) ? (double)B * (double)(n > 0 ? n : 1) : (double)B;
         p.loss_scale = (float)(1.0 / (denom > 0 ? denom : 1.0));
         p.prefetch = (a->variant == 3) ? 1 : 0;
+        p.ncount = nullptr; p.sp_in = nullptr; p.stats_part = nullptr;
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
         if (rc) return rc;

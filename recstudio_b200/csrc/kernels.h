@@ -17,6 +17,10 @@ struct FwdParams {
     float coef_scale;   // grad_scale / (B n) for BPR, grad_scale / B for SSM
     float loss_scale;   // 1 / (B n)              for BPR, 1 / B              for SSM
     int prefetch;       // variant 3: L2-prefetch the next batch's rows
+    // owner-compute (PARTIAL) mode of the row-sharded step, see shard.cu
+    const int32_t* ncount;   // [B] length of each query's compacted negative list (stride n)
+    const float* sp_in;      // [B] positive score (computed by the positive's owner)
+    float* stats_part;       // [B, 2] {csum, loss} (BPR) | {m, l} (SSM)
 };
 
 struct ScatterParams {
@@ -45,6 +49,7 @@ int32_t launch_scan(uint32_t* cnt_off, int64_t num_rows, uint32_t* urow, int64_t
                     uint64_t* tmp, int64_t tmp_elems, cudaStream_t st);
 // pair_fwd.cu
 int32_t launch_pair_fwd(const FwdParams& p, int loss, int score, int variant, cudaStream_t st);
+int32_t launch_pair_fwd_partial(const FwdParams& p, int loss, int score, cudaStream_t st);
 // scatter.cu
 int32_t launch_scatter(const ScatterParams& p, int64_t cap_rows, cudaStream_t st);
 int32_t launch_loss_sum(const float* part, int B, float* loss, cudaStream_t st);

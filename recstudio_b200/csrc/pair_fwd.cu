@@ -271,9 +271,15 @@ __device__ __forceinline__ void finish_query(const FwdParams& p, WarpState<VPL>&
 }
 
 // VPL = float4 per lane per row (D <= 128*VPL); lanes whose columns are >= D are idle.
-template <int VPL, int LOSS, int SCORE, bool MULTI, bool PIPE>
+//
+// PARTIAL = owner-compute step of the row-sharded table (shard.cu): the "user table" is the all-gathered
+// query matrix (query b = row b), the negatives are this owner's compacted sub-list of ncount[b] LOCAL row
+// ids, the positive score comes from its owner through sp_in, and instead of the final loss / dq the warp
+// leaves its partial state (raw accumulator + {csum, loss} | {m, l}) for shard_finish_kernel.
+template <int VPL, int LOSS, int SCORE, bool MULTI, bool PIPE, bool PARTIAL = false>
 __global__ void __launch_bounds__(kThreads, (VPL == 1 && !PIPE) ? 3 : 2)
 pair_fwd_kernel(const FwdParams p) {
+    static_assert(!PARTIAL || (!MULTI && !PIPE), "the owner-compute step runs one query per warp");
     constexpr int LOADS = Cfg<VPL>::LOADS, REP = Cfg<VPL>::REP, NG = Cfg<VPL>::NG;
     constexpr float kRepInv = 1.0f / REP;
     static_assert(NG % 2 == 0, "the pipelined loop alternates two row buffers");
@@ -293,9 +299,12 @@ pair_fwd_kernel(const FwdParams p) {
     float* s_acc = s_vp + D;                       // [nw][D]
     float* s_stat = s_acc + (size_t)nw * D;        // [nw][4] = {m, l, csum, loss}
 
-    int64_t uid = p.user[b], pid = p.pos[b];
-    if (uid < 0 || uid >= p.num_users) uid = 0;
-    if (pid < 0 || pid >= p.num_items) pid = 0;
+    int64_t uid = b, pid = 0;
+    if (!PARTIAL) {
+        uid = p.user[b]; pid = p.pos[b];
+        if (uid < 0 || uid >= p.num_users) uid = 0;
+        if (pid < 0 || pid >= p.num_items) pid = 0;
+    }
 
     float4 q[VPL], vp[VPL];
     bool act[VPL];
@@ -304,12 +313,13 @@ pair_fwd_kernel(const FwdParams p) {
         int col = lane * 4 + t * 128;
         act[t] = col < D;
         q[t] = act[t] ? ldg128(p.w_user + (size_t)uid * D + col) : make_float4(0, 0, 0, 0);
-        vp[t] = act[t] ? ldg128(p.w_item + (size_t)pid * D + col) : make_float4(0, 0, 0, 0);
+        vp[t] = (act[t] && !PARTIAL) ? ldg128(p.w_item + (size_t)pid * D + col) : make_float4(0, 0, 0, 0);
     }
 
     // this warp's slice of the negatives
     const int n = p.n;
     int j0 = 0, j1 = n;
+    if (PARTIAL) j1 = min(n, max(0, __ldg(p.ncount + b)));
     if (MULTI) {
         int per = ((n + kWarps - 1) / kWarps + 31) & ~31;   // multiple of 32 so batches stay aligned
         j0 = min(n, warp * per);
@@ -331,8 +341,9 @@ pair_fwd_kernel(const FwdParams p) {
     for (int t = 0; t < VPL; ++t) sp += (SCORE == RSB200_SCORE_IP) ? dot4(q[t], vp[t]) : sqdist4(q[t], vp[t]);
     sp = warp_sum(sp);
     if (SCORE == RSB200_SCORE_EUCLID) sp = -sp;
+    if (PARTIAL) sp = __ldg(p.sp_in + b);
 
-    if (!MULTI || warp == 0) {
+    if (!PARTIAL && (!MULTI || warp == 0)) {
 #pragma unroll
         for (int t = 0; t < VPL; ++t) {
             int col = lane * 4 + t * 128;
@@ -404,6 +415,16 @@ pair_fwd_kernel(const FwdParams p) {
         }
     }
 
+    if (PARTIAL) {
+        const float csum = warp_sum(st.csum) * kRepInv, lossacc = warp_sum(st.lossacc) * kRepInv;
+#pragma unroll
+        for (int t = 0; t < VPL; ++t)
+            if (act[t]) *reinterpret_cast<float4*>(p.dq_buf + (size_t)b * D + lane * 4 + t * 128) = st.acc[t];
+        if (lane == 0)
+            *reinterpret_cast<float2*>(p.stats_part + 2 * (size_t)b) =
+                (LOSS == RSB200_LOSS_BPR) ? make_float2(csum, lossacc) : make_float2(st.m_run, st.l_run);
+        return;
+    }
     finish_query<VPL, LOSS, SCORE, MULTI>(p, st, s_q, s_vp, s_acc, s_stat, act, sp, b, uid, pid, lane, warp);
 }
 
@@ -618,6 +639,39 @@ int32_t launch_pair_fwd(const FwdParams& p, int loss, int score, int variant, cu
     if (p.D <= 128) return pipe ? launch_fwd_v<1, true>(p, loss, score, st) : launch_fwd_v<1, false>(p, loss, score, st);
     if (p.D <= 256) return launch_fwd_v<2, false>(p, loss, score, st);
     if (p.D <= 512) return launch_fwd_v<4, false>(p, loss, score, st);
+    set_error("embedding dim %d > 512 is not supported", p.D);
+    return RSB200_EUNSUPPORTED;
+}
+
+template <int VPL>
+static int32_t launch_partial_v(const FwdParams& p, int loss, int score, cudaStream_t st) {
+    const size_t smem = (size_t)kWarps * (3 * p.D + 4) * sizeof(float);
+    const unsigned grid = (unsigned)cdiv(p.B, kWarps);
+#define RSB_PARTIAL(LOSS, SCORE)                                                                                      \
+    do {                                                                                                              \
+        if (smem > 48 * 1024)                                                                                         \
+            RSB_CUDA(cudaFuncSetAttribute(pair_fwd_kernel<VPL, LOSS, SCORE, false, false, true>,                      \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        pair_fwd_kernel<VPL, LOSS, SCORE, false, false, true><<<grid, kThreads, smem, st>>>(p);                       \
+    } while (0)
+    if (loss == RSB200_LOSS_BPR) {
+        if (score == RSB200_SCORE_IP) RSB_PARTIAL(RSB200_LOSS_BPR, RSB200_SCORE_IP);
+        else RSB_PARTIAL(RSB200_LOSS_BPR, RSB200_SCORE_EUCLID);
+    } else {
+        if (score == RSB200_SCORE_IP) RSB_PARTIAL(RSB200_LOSS_SSM, RSB200_SCORE_IP);
+        else RSB_PARTIAL(RSB200_LOSS_SSM, RSB200_SCORE_EUCLID);
+    }
+#undef RSB_PARTIAL
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// owner-compute forward of the row-sharded step (one query per warp, see PARTIAL above)
+int32_t launch_pair_fwd_partial(const FwdParams& p, int loss, int score, cudaStream_t st) {
+    if (p.B == 0) return 0;
+    if (p.D <= 128) return launch_partial_v<1>(p, loss, score, st);
+    if (p.D <= 256) return launch_partial_v<2>(p, loss, score, st);
+    if (p.D <= 512) return launch_partial_v<4>(p, loss, score, st);
     set_error("embedding dim %d > 512 is not supported", p.D);
     return RSB200_EUNSUPPORTED;
 }

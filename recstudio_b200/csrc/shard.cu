@@ -1,0 +1,269 @@
+// shard.cu -- owner-compute training step of the ROW-SHARDED item table ("ship
+// queries, not rows").
+//
+// The reference has no table sharding (its only multi-GPU mode replicates every parameter each
+// step, recstudio/utils/data_parallel.py:151).  Row lookup over NVLink (sharded.py: ShardedRows)
+// moves 512 B per touched row each way; here nothing row-sized ever leaves its owner:
+//
+//   every owner sees the GLOBAL batch (G = world x B queries: query vectors, positive ids, negative
+//   ids -- all-gathered by the caller) and does the part of the reference step
+//   (baseretriever.py:142-176,399-404 + loss.backward(), recommender.py:638) that touches ITS rows:
+//
+//   PREP    per query: keep the negatives whose row this owner holds (stable ballot compaction to
+//           LOCAL row ids), count touches per local row (the COUNT phase of group.cu fused in),
+//           score the positive if it is owned;  then the usual exclusive scan -> CSR offsets.
+//           --> caller: all-reduce(SUM) of sp[G] (every positive has exactly one owner)
+//   FWD     pair_fwd_kernel<PARTIAL>: the unchanged streaming gather/score/loss loop over the owned
+//           negatives; leaves per query the raw dq accumulator and {sum c, sum loss} (BPR) or the
+//           online-softmax state {m, l} (SampledSoftmax) in stats_all[rank].
+//           --> caller: all-gather of the [G, 2] stats slices
+//   FINISH  per query: merge the owners' stats (same arithmetic on every owner, in owner order ->
+//           identical lse / loss everywhere), turn the raw accumulator into this owner's share of
+//           d loss / d query, add the positive's term and emit the positive's gradient entry if owned.
+//           --> caller: all-reduce(SUM) of dq[G, d]
+//   SCATTER the unchanged segmented scatter over the owner's rows (scatter.cu): gradient rows of
+//           OWNED rows only, so dV never crosses NVLink.
+//
+// Bytes on the wire per rank and step: ids (4 B per negative) + 8 B + 4 B + d*4 B per query, instead
+// of 2 x 512 B per touched row.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rsb {
+
+constexpr int kPrepWarps = 8;
+
+__device__ __forceinline__ float warp_sum_s(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+struct PrepParams {
+    const float* w_local; const float* q_all;
+    const int64_t* pos; const int32_t* neg; const float* logq_neg;
+    uint32_t* cnt;                 // [local_rows + 1] zeroed histogram
+    int32_t* neg_c; uint32_t* slot_neg; float* lq_c; int32_t* ncount;
+    int32_t* pos_local; uint32_t* slot_pos; float* sp;
+    uint32_t* err;
+    int64_t num_items, row0, local_rows;
+    int G, n, D, euclid;
+};
+
+// one warp per query
+__global__ void __launch_bounds__(kPrepWarps * 32)
+shard_prep_kernel(const PrepParams p) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
+    if (b >= p.G) return;
+    const int D = p.D;
+
+    // ---- positive: owned? -> score + slot ---------------------------------------------------
+    int64_t gp = __ldg(p.pos + b);
+    if (gp < 0 || gp >= p.num_items) { if (lane == 0) atomicOr(p.err, 1u); gp = 0; }
+    const int64_t lp = gp - p.row0;
+    const bool own = lp >= 0 && lp < p.local_rows;        // warp-uniform
+    float sp = 0.f;
+    if (own) {
+        for (int c = lane * 4; c < D; c += 128) {
+            const float4 qv = ldg128(p.q_all + (size_t)b * D + c);
+            const float4 vv = ldg128(p.w_local + (size_t)lp * D + c);
+            sp += p.euclid ? sqdist4(qv, vv) : dot4(qv, vv);
+        }
+        sp = warp_sum_s(sp);
+        if (p.euclid) sp = -sp;
+    }
+    if (lane == 0) {
+        p.sp[b] = own ? sp : 0.f;
+        p.pos_local[b] = own ? (int32_t)lp : -1;
+        p.slot_pos[b] = (own && gp != 0) ? atomicAdd(p.cnt + lp, 1u) : kNoSlot;     // padding row: no gradient
+    }
+
+    // ---- negatives: stable compaction of the owned ids + per-row slot --------------------------
+    const size_t base = (size_t)b * p.n;
+    int kept = 0;
+    bool bad = false;
+    for (int jb = 0; jb < p.n; jb += 32) {
+        const int j = jb + lane;
+        const bool valid = j < p.n;
+        int64_t gid = valid ? (int64_t)__ldg(p.neg + base + j) : -1;
+        if (valid && (gid < 0 || gid >= p.num_items)) { bad = true; gid = 0; }
+        const int64_t lid = gid - p.row0;
+        const bool mine = valid && lid >= 0 && lid < p.local_rows;
+        const uint32_t mask = __ballot_sync(kFull, mine);
+        if (mine) {
+            const int k = kept + __popc(mask & ((1u << lane) - 1u));
+            p.neg_c[base + k] = (int32_t)lid;
+            p.slot_neg[base + k] = (gid != 0) ? atomicAdd(p.cnt + lid, 1u) : kNoSlot;
+            if (p.lq_c) p.lq_c[base + k] = __ldg(p.logq_neg + base + j);
+        }
+        kept += __popc(mask);
+    }
+    if (bad) atomicOr(p.err, 1u);
+    if (lane == 0) p.ncount[b] = kept;
+}
+
+struct FinishParams {
+    const float* w_local; const float* q_all;
+    const float* stats_all;        // [world, G, 2]
+    const float* sp; const float* logq_pos;
+    const int32_t* pos_local; const uint32_t* slot_pos; const uint32_t* off;
+    uint64_t* ent; float* dq; float* loss_part; float* lse;
+    int G, D, world, rank, ssm, euclid;
+    float coef_scale, loss_scale;
+};
+
+// one warp per query
+__global__ void __launch_bounds__(kPrepWarps * 32)
+shard_finish_kernel(const FinishParams p) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
+    if (b >= p.G) return;
+    const int D = p.D;
+    const size_t G = (size_t)p.G;
+
+    // ---- merge the owners' statistics (every owner runs exactly this sequence) -------------------
+    float cpos, mul_own, cs_own, loss_b, lse_b = 0.f;
+    const float2 mine = *reinterpret_cast<const float2*>(p.stats_all + 2 * ((size_t)p.rank * G + b));
+    if (!p.ssm) {
+        float CS = 0.f, LS = 0.f;
+        for (int o = 0; o < p.world; ++o) {
+            const float2 s = *reinterpret_cast<const float2*>(p.stats_all + 2 * ((size_t)o * G + b));
+            CS += s.x; LS += s.y;
+        }
+        cpos = -CS; mul_own = 1.f; cs_own = mine.x;
+        loss_b = LS * p.loss_scale;
+    } else {
+        float M = -INFINITY;
+        for (int o = 0; o < p.world; ++o) M = fmaxf(M, p.stats_all[2 * ((size_t)o * G + b)]);
+        float L = 0.f;
+        for (int o = 0; o < p.world; ++o) {
+            const float2 s = *reinterpret_cast<const float2*>(p.stats_all + 2 * ((size_t)o * G + b));
+            if (s.x != -INFINITY) L += s.y * expf(s.x - M);
+        }
+        const float z0 = p.sp[b] - (p.logq_pos ? p.logq_pos[b] : 0.f);
+        const float M2 = fmaxf(M, z0);
+        const float L2 = ((M == -INFINITY) ? 0.f : L * expf(M - M2)) + expf(z0 - M2);
+        lse_b = M2 + logf(L2);
+        cpos = (expf(z0 - lse_b) - 1.f) * p.coef_scale;
+        mul_own = (mine.x == -INFINITY) ? 0.f : expf(mine.x - lse_b) * p.coef_scale;    // accumulator is relative to m_own
+        cs_own = mine.y * mul_own;
+        loss_b = (lse_b - z0) * p.loss_scale;
+    }
+
+    const int lp = p.pos_local[b];
+    for (int c = lane * 4; c < D; c += 128) {
+        float4 a = *reinterpret_cast<const float4*>(p.dq + (size_t)b * D + c);
+        a.x *= mul_own; a.y *= mul_own; a.z *= mul_own; a.w *= mul_own;
+        if (p.euclid) {
+            const float4 q = ldg128(p.q_all + (size_t)b * D + c);
+            a.x = 2.f * (a.x - cs_own * q.x); a.y = 2.f * (a.y - cs_own * q.y);
+            a.z = 2.f * (a.z - cs_own * q.z); a.w = 2.f * (a.w - cs_own * q.w);
+            if (lp >= 0) {
+                const float4 v = ldg128(p.w_local + (size_t)lp * D + c);
+                const float t = 2.f * cpos;
+                a.x += t * (v.x - q.x); a.y += t * (v.y - q.y); a.z += t * (v.z - q.z); a.w += t * (v.w - q.w);
+            }
+        } else if (lp >= 0) {
+            fma4(a, cpos, ldg128(p.w_local + (size_t)lp * D + c));
+        }
+        *reinterpret_cast<float4*>(p.dq + (size_t)b * D + c) = a;
+    }
+    if (lane == 0) {
+        p.loss_part[b] = loss_b;
+        p.lse[b] = lse_b;
+        if (lp >= 0) {
+            const uint32_t sl = p.slot_pos[b];
+            if (sl != kNoSlot)
+                p.ent[__ldg(p.off + lp) + sl] = (uint64_t)((uint32_t)b | kDirect) | ((uint64_t)__float_as_uint(cpos) << 32);
+        }
+    }
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" size_t rsb200_sizeof_shard_args(void) { return sizeof(rsb200_shard_args); }
+extern "C" int64_t rsb200_scan_tmp_elems(int64_t num_rows) { return scan_tmp_elems(num_rows); }
+
+extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases, void* stream) {
+    RSB_REQUIRE(a != nullptr, RSB200_EINVAL, "null args");
+    RSB_REQUIRE(a->d >= 4 && a->d % 4 == 0 && a->d <= 512, a->d > 512 ? RSB200_EUNSUPPORTED : RSB200_EINVAL,
+                "embedding dim must be a multiple of 4 in [4, 512], got %lld", (long long)a->d);
+    RSB_REQUIRE(a->G >= 0 && a->n >= 0 && a->num_items >= 1 && a->local_rows >= 1 && a->row0 >= 0 &&
+                a->row0 + a->local_rows <= a->num_items, RSB200_EINVAL, "bad sizes / row block");
+    RSB_REQUIRE(a->world >= 1 && a->rank >= 0 && a->rank < a->world, RSB200_EINVAL, "bad world / rank");
+    RSB_REQUIRE(a->G * (a->n + 1) < ((int64_t)1 << 31), RSB200_EUNSUPPORTED, "G*(n+1) must be < 2^31");
+    RSB_REQUIRE(a->num_items < ((int64_t)1 << 31), RSB200_EUNSUPPORTED, "table rows must be < 2^31");
+    RSB_REQUIRE(a->loss_kind == RSB200_LOSS_BPR || a->loss_kind == RSB200_LOSS_SSM, RSB200_EINVAL, "bad loss_kind");
+    RSB_REQUIRE(a->score_kind == RSB200_SCORE_IP || a->score_kind == RSB200_SCORE_EUCLID, RSB200_EINVAL, "bad score_kind");
+    RSB_REQUIRE(a->sink == RSB200_SINK_COMPACT || a->sink == RSB200_SINK_DENSE, RSB200_EINVAL, "bad sink");
+    RSB_REQUIRE(a->w_local && a->q_all && a->pos && (a->n == 0 || a->neg) && a->sp && a->stats_all && a->dq && a->loss,
+                RSB200_EINVAL, "null table / batch / exchange pointer");
+    RSB_REQUIRE(a->neg_c && a->slot_neg && a->ncount && a->pos_local && a->slot_pos && a->off && a->urow && a->ent &&
+                a->loss_part && a->lse && a->scan_tmp && a->totals && a->err_flag, RSB200_EINVAL, "null workspace pointer");
+    RSB_REQUIRE(a->logq_neg == nullptr || a->lq_c != nullptr, RSB200_EINVAL, "logq_neg needs the lq_c workspace");
+    RSB_REQUIRE(aligned16(a->w_local) && aligned16(a->q_all) && aligned16(a->dq) && aligned16(a->item_vals) &&
+                (reinterpret_cast<uintptr_t>(a->stats_all) & 7u) == 0, RSB200_EINVAL, "row buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t G = a->G, n = a->n;
+    const bool ssm = a->loss_kind == RSB200_LOSS_SSM, eu = a->score_kind == RSB200_SCORE_EUCLID;
+    const double denom = ssm ? (double)(G > 0 ? G : 1) : (double)(G > 0 ? G : 1) * (double)(n > 0 ? n : 1);
+    const float coef_scale = (float)((double)a->grad_scale / denom), loss_scale = (float)(1.0 / denom);
+    const unsigned qblocks = (unsigned)cdiv(G > 0 ? G : 1, kPrepWarps);
+    int32_t rc;
+
+    if (phases & RSB200_SHARD_PREP) {
+        RSB_CUDA(cudaMemsetAsync(a->off, 0, sizeof(uint32_t) * (size_t)(a->local_rows + 1), st));
+        if (G > 0) {
+            PrepParams p;
+            p.w_local = a->w_local; p.q_all = a->q_all; p.pos = a->pos; p.neg = a->neg; p.logq_neg = a->logq_neg;
+            p.cnt = a->off; p.neg_c = a->neg_c; p.slot_neg = a->slot_neg; p.lq_c = a->logq_neg ? a->lq_c : nullptr;
+            p.ncount = a->ncount; p.pos_local = a->pos_local; p.slot_pos = a->slot_pos; p.sp = a->sp; p.err = a->err_flag;
+            p.num_items = a->num_items; p.row0 = a->row0; p.local_rows = a->local_rows;
+            p.G = (int)G; p.n = (int)n; p.D = (int)a->d; p.euclid = eu;
+            shard_prep_kernel<<<qblocks, kPrepWarps * 32, 0, st>>>(p);
+            RSB_LAUNCH_CHECK();
+        }
+        rc = launch_scan(a->off, a->local_rows, a->urow, a->cap, a->totals, a->scan_tmp, a->scan_tmp_elems, st);
+        if (rc) return rc;
+    }
+    if ((phases & RSB200_SHARD_FWD) && G > 0) {
+        FwdParams p;
+        p.w_item = a->w_local; p.w_user = a->q_all; p.user = nullptr; p.pos = nullptr; p.neg = a->neg_c;
+        p.logq_pos = nullptr; p.logq_neg = a->logq_neg ? a->lq_c : nullptr;
+        p.off_item = a->off; p.off_user = nullptr; p.slot_neg = a->slot_neg; p.slot_pos = nullptr; p.slot_user = nullptr;
+        p.ent_item = a->ent; p.ent_user = nullptr; p.q_buf = nullptr; p.dq_buf = a->dq; p.loss_part = nullptr; p.lse = nullptr;
+        p.pos_score = nullptr; p.neg_score = nullptr;
+        p.num_items = (int)a->local_rows; p.num_users = (int)G; p.B = (int)G; p.n = (int)n; p.D = (int)a->d;
+        p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0;
+        p.ncount = a->ncount; p.sp_in = a->sp; p.stats_part = a->stats_all + 2 * (size_t)a->rank * (size_t)G;
+        rc = launch_pair_fwd_partial(p, a->loss_kind, a->score_kind, st);
+        if (rc) return rc;
+    }
+    if (phases & RSB200_SHARD_FINISH) {
+        if (G > 0) {
+            FinishParams f;
+            f.w_local = a->w_local; f.q_all = a->q_all; f.stats_all = a->stats_all; f.sp = a->sp; f.logq_pos = a->logq_pos;
+            f.pos_local = a->pos_local; f.slot_pos = a->slot_pos; f.off = a->off; f.ent = a->ent; f.dq = a->dq;
+            f.loss_part = a->loss_part; f.lse = a->lse; f.G = (int)G; f.D = (int)a->d; f.world = a->world; f.rank = a->rank;
+            f.ssm = ssm; f.euclid = eu; f.coef_scale = coef_scale; f.loss_scale = loss_scale;
+            shard_finish_kernel<<<qblocks, kPrepWarps * 32, 0, st>>>(f);
+            RSB_LAUNCH_CHECK();
+        }
+        rc = launch_loss_sum(a->loss_part, (int)G, a->loss, st);
+        if (rc) return rc;
+    }
+    if (phases & RSB200_SHARD_SCATTER) {
+        RSB_REQUIRE(a->item_rows && a->item_vals, RSB200_EINVAL, "SCATTER needs item_rows / item_vals");
+        ScatterParams s;
+        s.off = a->off; s.urow = a->urow; s.totals = a->totals; s.ent = a->ent; s.src = a->q_all; s.lse = a->lse;
+        s.w = a->w_local; s.gscale = a->grad_scale_dev; s.rows_out = a->item_rows; s.vals = a->item_vals; s.cap = a->cap;
+        s.D = (int)a->d; s.ssm_scale = coef_scale;
+        s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = eu;
+        rc = launch_scatter(s, a->cap, st);
+        if (rc) return rc;
+    }
+    return 0;
+}

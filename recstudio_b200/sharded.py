@@ -19,8 +19,10 @@ whom) is plain torch tensor code with no device assumptions, so the same functio
 ``gloo`` on CPU tensors in the tests; the arithmetic (gather / fused step / coalesce) is CUDA only
 and is injected through ``ops``.
 
-This is the literal design of the north star (row lookup over NVLink).  Shipping queries instead
-of rows moves ~60x fewer bytes and is the planned replacement.
+This is the literal design of the north star (row lookup over NVLink): 512 B per touched row
+each way.  ``owner_compute_step`` below is the cheaper formulation of SURVEY.md 8(e): ship the
+QUERIES (and 4-byte ids), let every owner score / accumulate the negatives it holds in place
+(rsb200_shard_step, csrc/shard.cu) and exchange only per-query scalars and ``d loss / d query``.
 """
 from __future__ import annotations
 
@@ -193,3 +195,133 @@ def make_fused_step(B: int, n: int, d: int, num_users: int, device):
         return loss, ri, vi, ru, vu
     step.loss_kind, step.score_kind = _lib.LOSS_BPR, _lib.SCORE_IP
     return step
+
+
+# ------------------------------------------------------------------- owner-compute ("ship queries")
+def _all_gather_cat(x: torch.Tensor, group=None) -> torch.Tensor:
+    """[m, ...] per rank -> [world * m, ...] in rank order (works under nccl and gloo)."""
+    world = dist.get_world_size(group)
+    out = x.new_empty((world * x.shape[0],) + tuple(x.shape[1:]))
+    dist.all_gather(list(out.chunk(world, dim=0)), x.contiguous(), group=group)
+    return out
+
+
+class OwnerComputeCuda:
+    """One owner's workspace and the four kernel phases of ``rsb200_shard_step`` (csrc/shard.cu).
+
+    Nothing here talks to other ranks: ``owner_compute_step`` (or a test that loops over the owners
+    on one device) performs the three exchanges between the phases."""
+
+    def __init__(self, num_items: int, row0: int, local_rows: int, weight: torch.Tensor, world: int, rank: int,
+                 G: int, n: int, with_logq: bool = False):
+        _lib.require_cuda()
+        dev, d = weight.device, weight.shape[1]
+        self.weight, self.world, self.rank, self.G, self.n, self.d = weight, world, rank, G, n, d
+        self.num_items, self.row0, self.local_rows = num_items, row0, local_rows
+        i32, f32, i64 = torch.int32, torch.float32, torch.int64
+        E = lambda *shape, dtype=f32: torch.empty(*shape, dtype=dtype, device=dev)
+        self.cap = max(1, min(G * (n + 1), local_rows))
+        self.neg_c, self.slot_neg = E(max(G * n, 1), dtype=i32), E(max(G * n, 1), dtype=i32)
+        self.lq_c = E(max(G * n, 1)) if with_logq else None
+        self.ncount, self.pos_local, self.slot_pos = E(max(G, 1), dtype=i32), E(max(G, 1), dtype=i32), E(max(G, 1), dtype=i32)
+        self.off, self.urow = E(local_rows + 1, dtype=i32), E(self.cap, dtype=i32)
+        self.ent = E(max(G * (n + 1), 1), dtype=i64)
+        self.loss_part, self.lse = E(max(G, 1)), E(max(G, 1))
+        self.scan_elems = int(_lib.lib().rsb200_scan_tmp_elems(local_rows))
+        self.scan_tmp = E(self.scan_elems, dtype=i64)
+        self.err, self.totals = torch.zeros(1, dtype=i32, device=dev), torch.zeros(2, dtype=i32, device=dev)
+        self.sp, self.stats_all, self.dq = E(max(G, 1)), E(world, max(G, 1), 2), E(max(G, 1), d)
+        self.loss = E(1)
+        self.item_rows, self.item_vals = E(self.cap, dtype=i64), E(self.cap, d)
+        self._args = None
+
+    def bind(self, q_all, pos_all, neg_all, loss_kind, score_kind, logq_pos=None, logq_neg=None, grad_scale: float = 1.0):
+        G, n, d = self.G, self.n, self.d
+        assert q_all.shape == (G, d) and q_all.dtype == torch.float32 and pos_all.shape == (G,) and pos_all.dtype == torch.int64
+        assert neg_all.shape == (G, n) and neg_all.dtype == torch.int32
+        if logq_neg is not None and self.lq_c is None:
+            raise _lib.Rsb200Error("OwnerComputeCuda was built without the logq workspace (with_logq=True)")
+        self._keep = [t.contiguous() if t is not None else None for t in (q_all, pos_all, neg_all, logq_pos, logq_neg)]
+        q_all, pos_all, neg_all, logq_pos, logq_neg = self._keep
+        a = _lib.ShardArgs()
+        P = _lib.ptr
+        a.w_local, a.q_all, a.pos, a.neg = P(self.weight), P(q_all), P(pos_all), P(neg_all)
+        a.logq_pos = P(logq_pos) if logq_pos is not None else None
+        a.logq_neg = P(logq_neg) if logq_neg is not None else None
+        a.grad_scale_dev = None
+        a.sp, a.stats_all, a.dq, a.loss = P(self.sp), P(self.stats_all), P(self.dq), P(self.loss)
+        a.item_rows, a.item_vals, a.totals = P(self.item_rows), P(self.item_vals), P(self.totals)
+        a.neg_c, a.slot_neg = P(self.neg_c), P(self.slot_neg)
+        a.lq_c = P(self.lq_c) if self.lq_c is not None else None
+        a.ncount, a.pos_local, a.slot_pos = P(self.ncount), P(self.pos_local), P(self.slot_pos)
+        a.off, a.urow, a.ent = P(self.off), P(self.urow), P(self.ent)
+        a.loss_part, a.lse, a.scan_tmp, a.err_flag = P(self.loss_part), P(self.lse), P(self.scan_tmp), P(self.err)
+        a.G, a.n, a.d, a.num_items, a.row0, a.local_rows = G, n, d, self.num_items, self.row0, self.local_rows
+        a.cap, a.scan_tmp_elems, a.grad_scale = self.cap, self.scan_elems, float(grad_scale)
+        a.world, a.rank, a.loss_kind, a.score_kind = self.world, self.rank, int(loss_kind), int(score_kind)
+        a.sink, a.accumulate = _lib.SINK_COMPACT, 0
+        self._args = a
+
+    def _run(self, phases: int, what: str):
+        with torch.cuda.device(self.weight.device):
+            _lib.check(_lib.lib().rsb200_shard_step(C.byref(self._args), phases, _lib.stream_ptr()), what)
+
+    def prep(self) -> torch.Tensor:            # -> sp[G]   (all-reduce SUM next)
+        self._run(_lib.SHARD_PREP, "shard_step(PREP)")
+        return self.sp[:self.G]
+
+    def fwd(self) -> torch.Tensor:             # -> this owner's stats slice [G, 2]   (all-gather next)
+        self._run(_lib.SHARD_FWD, "shard_step(FWD)")
+        return self.stats_all[self.rank, :self.G]
+
+    def finish(self):                          # -> (loss[1], dq[G, d])   (all-reduce SUM of dq next)
+        self._run(_lib.SHARD_FINISH, "shard_step(FINISH)")
+        return self.loss, self.dq[:self.G]
+
+    def scatter(self):                         # -> (rows[cap], vals[cap, d], totals): R = totals[1] on the device
+        self._run(_lib.SHARD_SCATTER, "shard_step(SCATTER)")
+        return self.item_rows, self.item_vals, self.totals
+
+    def check(self):
+        if int(self.err.item()):
+            raise _lib.Rsb200Error("shard_step: item id outside [0, num_items)")
+
+
+def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, loss_kind: int, score_kind: int,
+                       logq_pos: Optional[torch.Tensor] = None, logq_neg: Optional[torch.Tensor] = None, group=None,
+                       gathered=None):
+    """One data-parallel step over the row-sharded item table WITHOUT moving rows.
+
+    Every rank passes its own B queries (vectors ``q`` [B, d], GLOBAL ids ``pos`` [B], ``neg`` [B, n] int32);
+    ``engine`` holds this rank's row block (``OwnerComputeCuda`` on GPUs).  Returns
+    ``(loss, (rows, vals, totals), dq_all)``: the global mean loss (identical on every rank), the gradient rows
+    of the rows THIS rank owns (LOCAL ids, ``R = totals[1]`` valid rows) and ``d loss / d query`` of all
+    ``G = world x B`` queries (rank r's queries are ``dq_all[r*B:(r+1)*B]``).  No host synchronisation."""
+    if gathered is None:
+        q_all, pos_all, neg_all = _all_gather_cat(q, group), _all_gather_cat(pos, group), _all_gather_cat(neg, group)
+        lqp = _all_gather_cat(logq_pos, group) if logq_pos is not None else None
+        lqn = _all_gather_cat(logq_neg, group) if logq_neg is not None else None
+    else:
+        q_all, pos_all, neg_all, lqp, lqn = gathered
+    engine.bind(q_all, pos_all, neg_all, loss_kind, score_kind, lqp, lqn)
+    sp = engine.prep()
+    dist.all_reduce(sp, group=group)                                   # every positive has exactly one owner
+    mine = engine.fwd()
+    world = dist.get_world_size(group)
+    dist.all_gather([engine.stats_all[r, :engine.G] for r in range(world)], mine.clone(), group=group)
+    loss, dq = engine.finish()
+    rows = engine.scatter()                                            # owner-local: overlaps the dq reduction
+    dist.all_reduce(dq, group=group)
+    return loss, rows, dq
+
+
+def owner_compute_training_step(items: ShardedRows, engine, w_user: torch.Tensor, user: torch.Tensor, pos: torch.Tensor,
+                                neg: torch.Tensor, loss_kind: int, score_kind: int, logq_pos=None, logq_neg=None):
+    """Same contract as ``sharded_training_step`` (replicated user table), on the owner-compute path."""
+    q = items.ops.gather_rows(w_user, user)
+    user_all = _all_gather_cat(user, items.group)
+    loss, (rows, vals, totals), dq_all = owner_compute_step(engine, q, pos, neg.to(torch.int32), loss_kind, score_kind,
+                                                            logq_pos, logq_neg, group=items.group)
+    r = int(totals[1].item())
+    ur, uv = items.ops.coalesce_rows(user_all, dq_all, w_user.shape[0], skip_row0=True)
+    return loss, (rows[:r], vals[:r]), (ur, uv)

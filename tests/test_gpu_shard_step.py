@@ -1,0 +1,130 @@
+"""rsb200_shard_step (owner-compute step of the row-sharded table, csrc/shard.cu) on ONE GPU: the
+owners are emulated one after the other on the same device and the three exchanges (sum of the
+positive scores, gather of the statistics, sum of dq) are done by hand, so the kernels are checked
+without NCCL.  Sum over owners must equal the reference step on the whole table
+(oracle.retriever.training_step_aten = baseretriever.py:142-176,399-404 op for op) and, at a
+larger size, the single-table fused step (rsb200_pair_step)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retriever as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_owners(w_item, q_all, pos, neg, world, loss_kind, score_kind, lqp=None, lqn=None):
+    """-> (loss, dense d_item [N, d], dq [G, d]) assembled from `world` owners run back to back."""
+    from recstudio_b200 import sharded
+    N, d = w_item.shape
+    G, n = neg.shape
+    per = sharded.rows_per_rank(N, world)
+    engines = []
+    for r in range(world):
+        row0 = r * per
+        local = max(0, min(per, N - row0))
+        e = sharded.OwnerComputeCuda(N, row0, local, w_item[row0:row0 + local].contiguous(), world, r, G, n,
+                                     with_logq=lqn is not None)
+        e.bind(q_all, pos, neg, loss_kind, score_kind, lqp, lqn)
+        engines.append(e)
+    sp = torch.stack([e.prep().clone() for e in engines]).sum(0)          # all-reduce SUM
+    for e in engines:
+        e.sp[:G] = sp
+    stats = torch.stack([e.fwd().clone() for e in engines])               # all-gather
+    for e in engines:
+        e.stats_all[:, :G] = stats
+    losses, dq = [], torch.zeros(G, d, device=DEV, dtype=torch.float64)
+    d_item = torch.zeros(N, d, device=DEV)
+    for e in engines:
+        loss, dqe = e.finish()
+        losses.append(loss.item()); dq += dqe.double()                    # all-reduce SUM
+        rows, vals, totals = e.scatter()
+        R_ = int(totals[1].item())
+        rr = rows[:R_]
+        assert torch.all(rr[1:] > rr[:-1]) and (R_ == 0 or (rr[0] >= 0 and rr[-1] < e.local_rows))
+        d_item[rr + e.row0] += vals[:R_]
+        e.check()
+    assert max(losses) - min(losses) == 0.0, "every owner must compute the identical global loss"
+    return losses[0], d_item, dq.float()
+
+
+def _case(N, U, d, G, n, seed, pad=True):
+    g = torch.Generator().manual_seed(seed)
+    w_item = torch.randn(N, d, generator=g) * 0.4; w_item[0] = 0
+    w_user = torch.randn(U, d, generator=g) * 0.4; w_user[0] = 0
+    user = torch.randint(1, U, (G,), generator=g)
+    pos = torch.randint(1, N, (G,), generator=g)
+    neg = torch.randint(0 if pad else 1, N, (G, n), generator=g)
+    if pad:
+        pos[0] = 0
+    lqp, lqn = torch.randn(G, generator=g), torch.randn(G, n, generator=g)
+    return w_item, w_user, user, pos, neg, lqp, lqn
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 7])
+@pytest.mark.parametrize("loss_kind,score_kind", [(R.BPR, R.IP), (R.BPR, R.EUCLID), (R.SSM, R.IP), (R.SSM, R.EUCLID)])
+def test_owners_sum_to_the_reference_step(world, loss_kind, score_kind):
+    N, U, d, G, n = 211, 40, 24, 37, 45          # n not a multiple of 32, d < 128, ids include the padding row
+    w_item, w_user, user, pos, neg, lqp, lqn = _case(N, U, d, G, n, seed=world)
+    ssm = loss_kind == R.SSM
+    kw = dict(log_pos_prob=lqp, log_neg_prob=lqn) if ssm else {}
+    ref = R.training_step_aten(w_item, w_user, user, pos, neg, loss=loss_kind, scorer=score_kind, **kw)
+    q_all = w_user[user].to(DEV)
+    loss, d_item, dq = run_owners(w_item.to(DEV), q_all, pos.to(DEV), neg.to(DEV).int(), world, loss_kind, score_kind,
+                                  lqp.to(DEV) if ssm else None, lqn.to(DEV) if ssm else None)
+    assert abs(loss - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+    gi = ref["d_item"].numpy()
+    assert np.abs(d_item.cpu().numpy() - gi).max() <= 1e-5 * np.abs(gi).max()
+    assert torch.all(d_item[0] == 0)
+    # d loss / d query  ->  user-table gradient
+    du = torch.zeros(U, d, dtype=torch.float64).index_add_(0, user, dq.cpu().double()); du[0] = 0
+    gu = ref["d_user"].numpy()
+    assert np.abs(du.numpy() - gu).max() <= 1e-5 * np.abs(gu).max()
+
+
+def test_owner_without_any_owned_negative_and_wide_rows():
+    """d = 256 (two 16-byte loads per lane), more owners than most queries have negatives: several owners hold
+    nothing of a query (empty lists, m = -inf in the SampledSoftmax merge)."""
+    N, U, d, G, n = 64, 9, 256, 10, 3
+    w_item, w_user, user, pos, neg, lqp, lqn = _case(N, U, d, G, n, seed=3, pad=False)
+    for loss_kind in (R.BPR, R.SSM):
+        ref = R.training_step_aten(w_item, w_user, user, pos, neg, loss=loss_kind, scorer=R.IP)
+        loss, d_item, dq = run_owners(w_item.to(DEV), w_user[user].to(DEV), pos.to(DEV), neg.to(DEV).int(), 8, loss_kind, R.IP)
+        assert abs(loss - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+        gi = ref["d_item"].numpy()
+        assert np.abs(d_item.cpu().numpy() - gi).max() <= 1e-5 * np.abs(gi).max()
+
+
+def test_bad_ids_are_reported():
+    from recstudio_b200 import _lib, sharded
+    N, d, G, n = 50, 8, 4, 5
+    w = torch.zeros(N, d, device=DEV)
+    e = sharded.OwnerComputeCuda(N, 0, N, w, 1, 0, G, n)
+    neg = torch.full((G, n), 3, dtype=torch.int32, device=DEV); neg[1, 2] = N + 4
+    e.bind(torch.zeros(G, d, device=DEV), torch.ones(G, dtype=torch.int64, device=DEV), neg, R.BPR, R.IP)
+    e.prep()
+    with pytest.raises(_lib.Rsb200Error):
+        e.check()
+
+
+@pytest.mark.parametrize("loss_kind", [R.BPR, R.SSM])
+def test_matches_the_single_table_fused_step(loss_kind):
+    """Config-2-like shape scaled down (n = 1024, d = 128): 4 owners vs rsb200_pair_step on the whole table."""
+    from recstudio_b200 import _lib, fused
+    N, U, d, G, n = 200_001, 5_001, 128, 512, 1024
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    w_item = torch.randn(N, d, device=DEV, generator=gen) * 0.1; w_item[0] = 0
+    w_user = torch.randn(U, d, device=DEV, generator=gen) * 0.1; w_user[0] = 0
+    user = torch.randint(1, U, (G,), device=DEV, generator=gen)
+    pos = torch.randint(1, N, (G,), device=DEV, generator=gen)
+    neg = torch.randint(1, N, (G, n), device=DEV, generator=gen).int()
+    ws = fused.PairWorkspace(N, U, G, n, d, torch.device(DEV))
+    loss_ref = fused.pair_step(ws, w_item, w_user, user, pos, neg, loss_kind, _lib.SCORE_IP).item()
+    (ri, vi), (ru, vu) = fused.sparse_grads(ws)
+    ref_item = torch.zeros(N, d, device=DEV); ref_item[ri] = vi
+    ref_dq = ws.dq_buf.view(G, d).clone()
+    loss, d_item, dq = run_owners(w_item, w_user[user], pos, neg, 4, loss_kind, _lib.SCORE_IP)
+    assert abs(loss - loss_ref) <= 2e-6 * abs(loss_ref)
+    assert (d_item - ref_item).abs().max().item() <= 1e-5 * ref_item.abs().max().item()
+    assert (dq - ref_dq).abs().max().item() <= 1e-5 * ref_dq.abs().max().item()

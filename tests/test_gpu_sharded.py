@@ -79,3 +79,55 @@ def test_sharded_step_on_two_gpus(loss_kind):
         du = np.zeros((U, D)); du[urow] = uval
         assert np.abs(du - ref["d_user"].numpy()).max() <= 1e-5 * np.abs(ref["d_user"].numpy()).max()
     assert np.abs(d_item - ref["d_item"].numpy()).max() <= 1e-5 * np.abs(ref["d_item"].numpy()).max()
+
+
+def _oc_worker(rank, port, loss_kind, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=WORLD, device_id=dev)
+    try:
+        from recstudio_b200 import sampling, sharded
+        w_item, w_user, user, pos = _data()
+        items = sharded.ShardedRows(N, D, dev)
+        items.weight.copy_(w_item[items.row0:items.row0 + items.local_rows])
+        torch.manual_seed(100 + rank)
+        _, neg32 = sampling.uniform_draw(N, B, NNEG, dev, want_i64=False, want_i32=True)
+        eng = sharded.OwnerComputeCuda(N, items.row0, items.local_rows, items.weight, WORLD, rank, WORLD * B, NNEG)
+        loss, (orow, oval), (urow, uval) = sharded.owner_compute_training_step(
+            items, eng, w_user.to(dev), user[rank].to(dev), pos[rank].to(dev), neg32, loss_kind, R.IP)
+        eng.check()
+        torch.cuda.synchronize()
+        q.put((rank, loss.item(), neg32.cpu().numpy(), (orow + items.row0).cpu().numpy(), oval.cpu().numpy(),
+               urow.cpu().numpy(), uval.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("loss_kind", [R.BPR, R.SSM])
+def test_owner_compute_step_on_two_gpus(loss_kind):
+    """The query-shipping formulation (rsb200_shard_step + three small NCCL exchanges): same contract, same answer."""
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_oc_worker, args=(r, port, loss_kind, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(WORLD))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w_item, w_user, user, pos = _data()
+    neg = torch.from_numpy(np.concatenate([r[2] for r in res])).long()
+    ref = R.training_step_aten(w_item, w_user, user.reshape(-1), pos.reshape(-1), neg, loss=loss_kind, scorer=R.IP)
+    d_item = np.zeros((N, D))
+    for rank, loss, _, orow, oval, urow, uval in res:
+        assert abs(loss - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
+        assert np.all(np.diff(orow) > 0) and np.all(orow // ((N + WORLD - 1) // WORLD) == rank)
+        d_item[orow] += oval
+        du = np.zeros((U, D)); du[urow] = uval
+        assert np.abs(du - ref["d_user"].numpy()).max() <= 1e-5 * np.abs(ref["d_user"].numpy()).max()
+    assert np.abs(d_item - ref["d_item"].numpy()).max() <= 1e-5 * np.abs(ref["d_item"].numpy()).max()

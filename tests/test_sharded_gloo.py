@@ -107,6 +107,60 @@ def test_sharded_step_equals_single_process(loss_kind, score_kind):
     assert np.all(d_item[0] == 0)
 
 
+def _oc_worker(rank, port, loss_kind, score_kind, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from oracle import shard_step as S
+        from recstudio_b200 import sharded
+        w_item, w_user, user, pos, neg = _data()
+        items = sharded.ShardedRows(N, D, "cpu", ops=TorchOps)
+        items.weight.copy_(w_item[items.row0:items.row0 + items.local_rows])
+        g = torch.Generator().manual_seed(5)
+        lqp, lqn = torch.randn(WORLD, B, generator=g), torch.randn(WORLD, B, NNEG, generator=g)
+        eng = S.OwnerComputeOracle(N, items.row0, items.local_rows, items.weight, WORLD, rank, WORLD * B, NNEG, with_logq=True)
+        loss, (orow, oval), (urow, uval) = sharded.owner_compute_training_step(
+            items, eng, w_user, user[rank], pos[rank], neg[rank], loss_kind, score_kind,
+            logq_pos=lqp[rank] if loss_kind == R.SSM else None, logq_neg=lqn[rank] if loss_kind == R.SSM else None)
+        q.put((rank, loss.item(), (orow + items.row0).numpy(), oval.numpy(), urow.numpy(), uval.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("loss_kind,score_kind", [(R.BPR, R.IP), (R.BPR, R.EUCLID), (R.SSM, R.IP), (R.SSM, R.EUCLID)])
+def test_owner_compute_step_equals_single_process(loss_kind, score_kind):
+    """The owner-compute ("ship queries, not rows") choreography of sharded.owner_compute_step: all-gather of
+    the batch, all-reduce of the positive scores, all-gather of the per-owner statistics, all-reduce of dq --
+    with the per-owner arithmetic injected from oracle/shard_step.py.  Sum over owners == the reference step
+    on the whole table."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_oc_worker, args=(r, port, loss_kind, score_kind, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(WORLD))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    w_item, w_user, user, pos, neg = _data()
+    g = torch.Generator().manual_seed(5)
+    lqp, lqn = torch.randn(WORLD, B, generator=g), torch.randn(WORLD, B, NNEG, generator=g)
+    kw = dict(log_pos_prob=lqp.reshape(-1), log_neg_prob=lqn.reshape(-1, NNEG)) if loss_kind == R.SSM else {}
+    ref = R.training_step_aten(w_item, w_user, user.reshape(-1), pos.reshape(-1), neg.reshape(-1, NNEG),
+                               loss=loss_kind, scorer=score_kind, **kw)
+    d_item = np.zeros((N, D))
+    for rank, loss, orow, oval, urow, uval in res:
+        assert abs(loss - ref["loss"].item()) < 2e-6 * max(1.0, abs(ref["loss"].item()))
+        assert np.all(np.diff(orow) > 0) and np.all(orow // ((N + WORLD - 1) // WORLD) == rank)
+        d_item[orow] += oval
+        du = np.zeros((U, D)); du[urow] = uval
+        np.testing.assert_allclose(du, ref["d_user"].numpy(), rtol=1e-4, atol=2e-7)
+    np.testing.assert_allclose(d_item, ref["d_item"].numpy(), rtol=1e-4, atol=2e-7)
+    assert np.all(d_item[0] == 0)
+
+
 def test_owner_counts_plan():
     from recstudio_b200 import sharded
     ids = torch.tensor([0, 3, 4, 5, 9, 10, 11, 19])

@@ -1,0 +1,89 @@
+"""Developer timing of the OWNER-COMPUTE step of the row-sharded table (sharded.owner_compute_step:
+ship queries, not rows) -- run with torchrun, one process per GPU (or plain python for world 1).
+Reports whole-job interactions/s (max over ranks, CUDA events), the per-phase split of one rank and
+the bytes each rank puts on NVLink per step.  RSB_N = global rows (default 10 000 001; 100 000 001 =
+BASELINE config 5), RSB_LOSS = 0 BPR | 1 SSM."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from recstudio_b200 import _lib, sampling, sharded  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    N = int(os.environ.get("RSB_N", 10_000_001)); U, d, B, n = 1_000_001, 128, 8192, 1024
+    loss_kind = int(os.environ.get("RSB_LOSS", 0))
+    steps, warm = int(os.environ.get("RSB_STEPS", 20)), 3
+    items = sharded.ShardedRows(N, d, dev, init_std=0.05, seed=1)
+    wu = torch.empty(U, d, device=dev).normal_(0, 0.05); wu[0] = 0
+    G = world * B
+    eng = sharded.OwnerComputeCuda(N, items.row0, items.local_rows, items.weight, world, rank, G, n)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    users = torch.randint(1, U, (steps + warm, B), device=dev, generator=gen)
+    poss = torch.randint(1, N, (steps + warm, B), device=dev, generator=gen)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(i, marks=None):
+        _, neg = sampling.uniform_draw(N, B, n, dev, want_i64=False, want_i32=True)
+        q = wu[users[i]]
+        if marks: marks[0].record()
+        q_all, pos_all, neg_all = (sharded._all_gather_cat(t) for t in (q, poss[i], neg))
+        if marks: marks[1].record()
+        eng.bind(q_all, pos_all, neg_all, loss_kind, _lib.SCORE_IP)
+        sp = eng.prep()
+        if marks: marks[2].record()
+        dist.all_reduce(sp)
+        mine = eng.fwd()
+        if marks: marks[3].record()
+        dist.all_gather([eng.stats_all[r, :G] for r in range(world)], mine.clone())
+        loss, dq = eng.finish()
+        if marks: marks[4].record()
+        rows = eng.scatter()
+        if marks: marks[5].record()
+        dist.all_reduce(dq)
+        if marks: marks[6].record()
+        return loss
+
+    for i in range(warm):
+        step(i)
+    dist.barrier(); torch.cuda.synchronize()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for i in range(steps):
+        loss = step(warm + i)
+    t1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    marks = [ev() for _ in range(7)]
+    s0 = ev(); s0.record()
+    step(warm, marks)
+    torch.cuda.synchronize()
+    names = ["sample+q", "allgather(batch)", "prep(filter+count+scan)", "allreduce(sp)+fwd", "allgather(stats)+finish", "scatter", "allreduce(dq)"]
+    split = {names[0]: s0.elapsed_time(marks[0])}
+    for k in range(1, 7):
+        split[names[k]] = marks[k - 1].elapsed_time(marks[k])
+    t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eng.check()
+    if rank == 0:
+        wire = (world - 1) * B * (d * 4 + 8 + n * 4) + 2 * (world - 1) / world * G * (4 + d * 4) + (world - 1) * G * 8
+        print(json.dumps({"path": "owner-compute (queries shipped)", "world": world, "N": N, "loss_kind": loss_kind,
+                          "ms_per_step": t.item(), "interactions_per_s": G / t.item() * 1e3, "loss": float(loss),
+                          "owned_unique_rows_rank0": int(eng.totals[1].item()), "phase_ms_rank0": split,
+                          "approx_nvlink_bytes_per_rank_per_step": int(wire)}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
