@@ -202,7 +202,10 @@ def _all_gather_cat(x: torch.Tensor, group=None) -> torch.Tensor:
     """[m, ...] per rank -> [world * m, ...] in rank order (works under nccl and gloo)."""
     world = dist.get_world_size(group)
     out = x.new_empty((world * x.shape[0],) + tuple(x.shape[1:]))
-    dist.all_gather(list(out.chunk(world, dim=0)), x.contiguous(), group=group)
+    if x.is_cuda:
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)        # one NCCL all-gather, no staging copies
+    else:
+        dist.all_gather(list(out.chunk(world, dim=0)), x.contiguous(), group=group)
     return out
 
 
@@ -307,12 +310,22 @@ def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: torch.Te
     sp = engine.prep()
     dist.all_reduce(sp, group=group)                                   # every positive has exactly one owner
     mine = engine.fwd()
-    world = dist.get_world_size(group)
-    dist.all_gather([engine.stats_all[r, :engine.G] for r in range(world)], mine.clone(), group=group)
+    exchange_stats(engine, mine, group)
     loss, dq = engine.finish()
-    rows = engine.scatter()                                            # owner-local: overlaps the dq reduction
-    dist.all_reduce(dq, group=group)
+    work = dist.all_reduce(dq, group=group, async_op=True)             # runs on the communicator's stream ...
+    rows = engine.scatter()                                            # ... while the owner-local scatter runs here
+    work.wait()
     return loss, rows, dq
+
+
+def exchange_stats(engine, mine: torch.Tensor, group=None):
+    """all-gather of the per-owner [G, 2] statistics into engine.stats_all[world, G, 2]"""
+    world = dist.get_world_size(group)
+    st = engine.stats_all
+    if st.is_cuda and st.shape[1] == engine.G:
+        dist.all_gather_into_tensor(st, mine.clone(), group=group)
+    else:
+        dist.all_gather([st[r, :engine.G] for r in range(world)], mine.clone(), group=group)
 
 
 def owner_compute_training_step(items: ShardedRows, engine, w_user: torch.Tensor, user: torch.Tensor, pos: torch.Tensor,

@@ -47,7 +47,7 @@ def main():
         dist.all_reduce(sp)
         mine = eng.fwd()
         if marks: marks[3].record()
-        dist.all_gather([eng.stats_all[r, :G] for r in range(world)], mine.clone())
+        sharded.exchange_stats(eng, mine)
         loss, dq = eng.finish()
         if marks: marks[4].record()
         rows = eng.scatter()
@@ -56,16 +56,49 @@ def main():
         if marks: marks[6].record()
         return loss
 
-    for i in range(warm):
-        step(i)
-    dist.barrier(); torch.cuda.synchronize()
-    t0, t1 = ev(), ev()
-    t0.record()
-    for i in range(steps):
-        loss = step(warm + i)
-    t1.record()
-    dist.barrier(); torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / steps
+    # the API call itself, and the same with the negative ids of step i+1 drawn + all-gathered on a side stream
+    # while step i computes (ids do not depend on the weights; queries / positives are gathered in-step)
+    side = torch.cuda.Stream()
+
+    def produce(i):
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _, neg = sampling.uniform_draw(N, B, n, dev, want_i64=False, want_i32=True)
+            neg_all = sharded._all_gather_cat(neg)
+            e = ev(); e.record()
+        return neg_all, e
+
+    def api_step(i, pre=None):
+        q = wu[users[i]]
+        if pre is None:
+            _, neg = sampling.uniform_draw(N, B, n, dev, want_i64=False, want_i32=True)
+            return sharded.owner_compute_step(eng, q, poss[i], neg, loss_kind, _lib.SCORE_IP)[0]
+        neg_all, e = pre
+        torch.cuda.current_stream().wait_event(e)
+        neg_all.record_stream(torch.cuda.current_stream())
+        g = (sharded._all_gather_cat(q), sharded._all_gather_cat(poss[i]), neg_all, None, None)
+        return sharded.owner_compute_step(eng, q, poss[i], None, loss_kind, _lib.SCORE_IP, gathered=g)[0]
+
+    results = {}
+    for mode in ("plain", "prefetch"):
+        for i in range(warm):
+            api_step(i)
+        dist.barrier(); torch.cuda.synchronize()
+        t0, t1 = ev(), ev()
+        pre = produce(warm) if mode == "prefetch" else None
+        t0.record()
+        for i in range(steps):
+            if mode == "prefetch":
+                nxt = produce(warm + i + 1) if i + 1 < steps else None
+                loss = api_step(warm + i, pre)
+                pre = nxt
+            else:
+                loss = api_step(warm + i)
+        t1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([t0.elapsed_time(t1) / steps], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        results[mode] = t.item()
+    ms = results["plain"]
     marks = [ev() for _ in range(7)]
     s0 = ev(); s0.record()
     step(warm, marks)
@@ -74,12 +107,13 @@ def main():
     split = {names[0]: s0.elapsed_time(marks[0])}
     for k in range(1, 7):
         split[names[k]] = marks[k - 1].elapsed_time(marks[k])
-    t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     eng.check()
     if rank == 0:
         wire = (world - 1) * B * (d * 4 + 8 + n * 4) + 2 * (world - 1) / world * G * (4 + d * 4) + (world - 1) * G * 8
         print(json.dumps({"path": "owner-compute (queries shipped)", "world": world, "N": N, "loss_kind": loss_kind,
-                          "ms_per_step": t.item(), "interactions_per_s": G / t.item() * 1e3, "loss": float(loss),
+                          "ms_per_step": ms, "interactions_per_s": G / ms * 1e3,
+                          "ms_per_step_prefetch_ids": results["prefetch"], "interactions_per_s_prefetch_ids": G / results["prefetch"] * 1e3,
+                          "loss": float(loss),
                           "owned_unique_rows_rank0": int(eng.totals[1].item()), "phase_ms_rank0": split,
                           "approx_nvlink_bytes_per_rank_per_step": int(wire)}))
     dist.destroy_process_group()
