@@ -19,8 +19,11 @@ draw -> row grouping -> fused gather/score/loss -> segmented gradient scatter (s
            timed on the host cores on a bounded sample of the same workload.
 
 N > 1: one process per GPU (torchrun), every rank owns a full replica of the tables and its
-own B interactions per step (weak scaling, "replicas": see DESIGN.md 8(e) for the row-sharded
-design that replaces this once the table exceeds one GPU).
+own B interactions per step (weak scaling, "replicas": the 5.1 GB table fits one GPU).
+
+    python bench.py --workload c5-sharded --gpus N ...       # BASELINE configs[4]: 100,000,001 x 128 rows
+runs the ROW-SHARDED table instead: every rank owns N_rows/N contiguous rows, draws its
+own B interactions, and the step is sharded.owner_compute_step (queries shipped, rows never move).
 """
 import argparse
 import json
@@ -267,6 +270,109 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_sharded(args):
+    """BASELINE configs[4] (100M x 128 rows, BPR, uniform sampler) on the row-sharded table, owner-compute path."""
+    import torch
+    import torch.distributed as dist
+    from recstudio_b200 import _lib, build, sampling, sharded
+    build.build()
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the b200 arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world == 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    N5 = 100_000_001
+    items = sharded.ShardedRows(N5, DIM, dev, init_std=INIT_STD, seed=2022)
+    wu = torch.empty(N_USERS, DIM, device=dev).normal_(0, INIT_STD, generator=torch.Generator(device=dev).manual_seed(7)); wu[0] = 0
+    G = world * BATCH
+    eng = sharded.OwnerComputeCuda(N5, items.row0, items.local_rows, items.weight, world, rank, G, NEG)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    users = torch.randint(1, N_USERS, (K + W, BATCH), device=dev, generator=gen)
+    poss = torch.randint(1, N5, (K + W, BATCH), device=dev, generator=gen)
+    L = _lib.lib()
+
+    def barrier():
+        dist.barrier(); torch.cuda.synchronize()
+
+    def step(u, p_, ev=None):
+        """one pass of the hot path over one batch; ev brackets the owner-compute forward kernel"""
+        _, neg = sampling.uniform_draw(N5, BATCH, NEG, dev, want_i64=False, want_i32=True)
+        q = sharded.CudaOps.gather_rows(wu, u)
+        q_all, pos_all, neg_all = (sharded._all_gather_cat(t) for t in (q, p_, neg))
+        eng.bind(q_all, pos_all, neg_all, _lib.LOSS_BPR, _lib.SCORE_IP)
+        sp = eng.prep()
+        dist.all_reduce(sp)
+        if ev: ev[0].record()
+        mine = eng.fwd()
+        if ev: ev[1].record()
+        sharded.exchange_stats(eng, mine)
+        loss, dq = eng.finish()
+        work = dist.all_reduce(dq, async_op=True)
+        eng.scatter()
+        work.wait()
+        return loss
+
+    for i in range(W):
+        step(users[i], poss[i])
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    l0 = L.rsb200_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(K):
+        loss = step(users[W + i], poss[W + i], evs[i])
+    t1.record()
+    barrier()
+    launches = L.rsb200_launch_count() - l0
+    total_ms = t0.elapsed_time(t1)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    owned_touches = int(eng.totals[0].item())
+    # e2e: host (pinned) id batches -> H2D -> the public sharded step -> D2H of the loss
+    hb = [(users[i].cpu().pin_memory(), poss[i].cpu().pin_memory()) for i in range(K + W)]
+    h2d = 2 * BATCH * 8
+    for i in range(W):
+        step(hb[i][0].to(dev, non_blocking=True), hb[i][1].to(dev, non_blocking=True)).item()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        _ = step(hb[W + i][0].to(dev, non_blocking=True), hb[W + i][1].to(dev, non_blocking=True)).item()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    eng.check()
+    stats = torch.tensor([total_ms, e0.elapsed_time(e1), fwd_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, fwd_ms = stats.tolist()
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_fwd = (owned_touches + BATCH) * DIM * 4 + G * DIM * 4      # owned rows + owned positives + all queries, rank 0
+        line = {"metric": "interactions/sec (BPR 100M x d128 row-sharded gather-score-loss-scatter)", "value": G * K / (total_ms / 1e3),
+                "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[4]: BPR + InnerProduct + in-kernel UniformSampler, items 100,000,001 x 128 "
+                                       "row-sharded over %d GPU(s) (%d rows each), users 1,000,001 x 128 replicated, B=8192 per rank, "
+                                       "n=1024, owner-compute step (queries shipped, rows never move)" % (world, items.per_rank),
+                           "global_batch": G, "parallelism": "row-sharded x%d" % world,
+                           "l2": "inputs (%.1f GB table block, random rows) exceed the 126 MB L2; no flush needed" % (items.local_rows * DIM * 4 / 1e9)},
+                "e2e": {"value": G * K / (e2e_ms / 1e3), "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": e2e_ms / K, "api": "sharded owner-compute step on host id batches + loss.item()"},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "pair_fwd_kernel<PARTIAL>", "bound": "hbm", "achieved": alg_fwd / (fwd_ms / 1e3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": alg_fwd / (fwd_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": fwd_ms, "algorithmic_bytes_per_launch": alg_fwd, "owned_touches_rank0": owned_touches},
+                "clocks": clk, "loss": float(loss.item())}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,9 +381,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development only)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5-sharded"],
+                    help="c2 = BASELINE configs[1] (default, the metric's config); c5-sharded = configs[4] on the row-sharded table")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5-sharded":
+        run_sharded(args)
     else:
         run_b200(args)
 

@@ -83,21 +83,41 @@ shard_prep_kernel(const PrepParams p) {
     const size_t base = (size_t)b * p.n;
     int kept = 0;
     bool bad = false;
-    for (int jb = 0; jb < p.n; jb += 32) {
-        const int j = jb + lane;
-        const bool valid = j < p.n;
-        int64_t gid = valid ? (int64_t)__ldg(p.neg + base + j) : -1;
-        if (valid && (gid < 0 || gid >= p.num_items)) { bad = true; gid = 0; }
-        const int64_t lid = gid - p.row0;
-        const bool mine = valid && lid >= 0 && lid < p.local_rows;
-        const uint32_t mask = __ballot_sync(kFull, mine);
-        if (mine) {
-            const int k = kept + __popc(mask & ((1u << lane) - 1u));
-            p.neg_c[base + k] = (int32_t)lid;
-            p.slot_neg[base + k] = (gid != 0) ? atomicAdd(p.cnt + lid, 1u) : kNoSlot;
-            if (p.lq_c) p.lq_c[base + k] = __ldg(p.logq_neg + base + j);
+    // kU batches of 32 ids per iteration: the loads, then the atomics, of kU batches are independent and in
+    // flight together (the one-batch loop was latency-bound: 0.37 ms for 67 M ids at 8 owners)
+    constexpr int kU = 4;
+    for (int jb = 0; jb < p.n; jb += 32 * kU) {
+        int32_t raw[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int j = jb + u * 32 + lane;
+            raw[u] = (j < p.n) ? __ldg(p.neg + base + j) : -1;
         }
-        kept += __popc(mask);
+        int kpos[kU]; int64_t lids[kU]; bool mines[kU]; bool zero[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int j = jb + u * 32 + lane;
+            const bool valid = j < p.n;
+            int64_t gid = raw[u];
+            if (valid && (gid < 0 || gid >= p.num_items)) { bad = true; gid = 0; }
+            const int64_t lid = gid - p.row0;
+            const bool mine = valid && lid >= 0 && lid < p.local_rows;
+            const uint32_t mask = __ballot_sync(kFull, mine);
+            kpos[u] = kept + __popc(mask & ((1u << lane) - 1u));
+            kept += __popc(mask);
+            lids[u] = lid; mines[u] = mine; zero[u] = gid == 0;
+        }
+        uint32_t sl[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) sl[u] = (mines[u] && !zero[u]) ? atomicAdd(p.cnt + lids[u], 1u) : kNoSlot;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (mines[u]) {
+                p.neg_c[base + kpos[u]] = (int32_t)lids[u];
+                p.slot_neg[base + kpos[u]] = sl[u];
+                if (p.lq_c) p.lq_c[base + kpos[u]] = __ldg(p.logq_neg + base + jb + u * 32 + lane);
+            }
+        }
     }
     if (bad) atomicOr(p.err, 1u);
     if (lane == 0) p.ncount[b] = kept;
