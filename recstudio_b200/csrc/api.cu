@@ -148,6 +148,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         const double denom = (a->loss_kind == RSB200_LOSS_BPR) ? (double)B * (double)(n > 0 ? n : 1) : (double)B;
         p.loss_scale = (float)(1.0 / (denom > 0 ? denom : 1.0));
         p.prefetch = (a->variant == 3) ? 1 : 0;
+        p.hint = (a->variant >= 16 && a->variant < 32) ? (a->variant & 7) : 0;   // variants 16..31: L2 eviction hints
         p.ncount = nullptr; p.sp_in = nullptr; p.stats_part = nullptr;
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
@@ -162,6 +163,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         s.cap = a->cap_item;
         s.ssm_scale = (float)((double)a->grad_scale / (double)(B > 0 ? B : 1));
         s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = a->score_kind == RSB200_SCORE_EUCLID;
+        s.hint = (a->variant >= 16 && a->variant < 32) ? ((a->variant >> 3) & 1) : 0;
         rc = launch_scatter(s, a->cap_item, st);
         if (rc) return rc;
         ScatterParams u = s;

@@ -72,6 +72,46 @@ __device__ __forceinline__ void stg128_stream(float* p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- L2 eviction-priority hints (createpolicy + .L2::cache_hint).  The gathered table rows are read once
+// (evict_first) while the grouping metadata (CSR offsets, entry list, query matrix) is small enough to
+// live in the 126 MB L2 between the kernels of one step (evict_last).
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 normal, 1 evict_first, 2 evict_last
+    uint64_t pn, pf, pl;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pl));
+    return kind == 1 ? pf : (kind == 2 ? pl : pn);
+}
+__device__ __forceinline__ float4 ldg128_stream_hint(const float* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ldg128_hint(const float* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg32_hint(const uint32_t* p, uint64_t pol) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint64_t ldg64_stream_hint(const uint64_t* p, uint64_t pol) {
+    uint64_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg64_hint(uint64_t* p, uint64_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg128_stream_hint(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ float dot4(float4 a, float4 b) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }

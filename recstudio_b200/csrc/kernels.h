@@ -17,6 +17,7 @@ struct FwdParams {
     float coef_scale;   // grad_scale / (B n) for BPR, grad_scale / B for SSM
     float loss_scale;   // 1 / (B n)              for BPR, 1 / B              for SSM
     int prefetch;       // variant 3: L2-prefetch the next batch's rows
+    int hint;           // L2 eviction hints: bit 0 rows evict_first, bit 1 offsets evict_last, bit 2 entries evict_last
     // owner-compute (PARTIAL) mode of the row-sharded step, see shard.cu
     const int32_t* ncount;   // [B] length of each query's compacted negative list (stride n)
     const float* sp_in;      // [B] positive score (computed by the positive's owner)
@@ -38,6 +39,7 @@ struct ScatterParams {
     int D;
     float ssm_scale;
     int dense, accumulate, euclid;
+    int hint;                 // L2 eviction hints (PLAIN kernel): entries / output rows evict_first, src evict_last
 };
 
 // group.cu

@@ -108,9 +108,9 @@ struct RowBuf {
 };
 
 // fetch the LOADS rows of group g of a batch (ids live one per lane in `id`)
-template <int VPL>
+template <int VPL, bool HINT = false>
 __device__ __forceinline__ void load_group(RowBuf<VPL>& buf, const FwdParams& p, int id, int g, int lane,
-                                           const bool (&act)[VPL]) {
+                                           const bool (&act)[VPL], uint64_t pol = 0) {
     constexpr int LOADS = Cfg<VPL>::LOADS;
 #pragma unroll
     for (int k = 0; k < LOADS; ++k) {
@@ -118,7 +118,8 @@ __device__ __forceinline__ void load_group(RowBuf<VPL>& buf, const FwdParams& p,
         const float* row = p.w_item + (size_t)rid * p.D + lane * 4;
 #pragma unroll
         for (int t = 0; t < VPL; ++t)
-            buf.v[k][t] = act[t] ? ldg128_stream(row + t * 128) : make_float4(0, 0, 0, 0);
+            buf.v[k][t] = act[t] ? (HINT ? ldg128_stream_hint(row + t * 128, pol) : ldg128_stream(row + t * 128))
+                                 : make_float4(0, 0, 0, 0);
     }
 }
 
@@ -276,10 +277,20 @@ __device__ __forceinline__ void finish_query(const FwdParams& p, WarpState<VPL>&
 // query matrix (query b = row b), the negatives are this owner's compacted sub-list of ncount[b] LOCAL row
 // ids, the positive score comes from its owner through sp_in, and instead of the final loss / dq the warp
 // leaves its partial state (raw accumulator + {csum, loss} | {m, l}) for shard_finish_kernel.
-template <int VPL, int LOSS, int SCORE, bool MULTI, bool PIPE, bool PARTIAL = false>
-__global__ void __launch_bounds__(kThreads, (VPL == 1 && !PIPE) ? 3 : 2)
+//
+// MODE: 0 = load-then-reduce loop; 1 = software-pipelined stream (PIPE); 2 = mode 0 with L2 eviction-priority
+// hints (HINT): table rows evict_first, CSR offsets / entry list evict_last (p.hint selects which).
+template <int VPL, int LOSS, int SCORE, bool MULTI, int MODE, bool PARTIAL = false>
+__global__ void __launch_bounds__(kThreads, (VPL == 1 && MODE != 1) ? 3 : 2)
 pair_fwd_kernel(const FwdParams p) {
+    constexpr bool PIPE = MODE == 1, HINT = MODE == 2;
     static_assert(!PARTIAL || (!MULTI && !PIPE), "the owner-compute step runs one query per warp");
+    uint64_t pol_row = 0, pol_off = 0, pol_ent = 0;
+    if (HINT) {
+        pol_row = l2_policy((p.hint & 1) ? 1 : 0);
+        pol_off = l2_policy((p.hint & 2) ? 2 : 0);
+        pol_ent = l2_policy((p.hint & 4) ? 2 : 0);
+    }
     constexpr int LOADS = Cfg<VPL>::LOADS, REP = Cfg<VPL>::REP, NG = Cfg<VPL>::NG;
     constexpr float kRepInv = 1.0f / REP;
     static_assert(NG % 2 == 0, "the pipelined loop alternates two row buffers");
@@ -363,7 +374,8 @@ pair_fwd_kernel(const FwdParams p) {
     for (int jb = j0; jb < j1; jb += 32) {
         const bool valid = (jb + lane) < j1;
         uint32_t epos = 0;
-        if (cur.slot != kNoSlot) epos = __ldg(p.off_item + cur.id) + cur.slot;   // consumed after the groups
+        if (cur.slot != kNoSlot)                                                  // consumed after the groups
+            epos = (HINT ? ldg32_hint(p.off_item + cur.id, pol_off) : __ldg(p.off_item + cur.id)) + cur.slot;
         st.val_out = 0.f; st.sc_out = 0.f;
 
         if (PIPE) {
@@ -401,14 +413,17 @@ pair_fwd_kernel(const FwdParams p) {
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 if (jb + g * LOADS < j1) {            // warp-uniform
-                    load_group<VPL>(bufA, p, cur.id, g, lane, act);
+                    load_group<VPL, HINT>(bufA, p, cur.id, g, lane, act, pol_row);
                     compute_group<VPL, LOSS, SCORE>(bufA, st, p, q, sp, cur.lq, g, jb, j1, lane);
                 }
             }
             if (valid) {
                 if (p.neg_score) p.neg_score[rowbase + jb + lane] = st.sc_out;
-                if (cur.slot != kNoSlot)
-                    p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
+                if (cur.slot != kNoSlot) {
+                    const uint64_t en = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
+                    if (HINT) stg64_hint(p.ent_item + epos, en, pol_ent);
+                    else p.ent_item[epos] = en;
+                }
             }
             if (p.prefetch) cur = nxt;
             else if (jb + 32 < j1) cur = load_meta<LOSS>(p, rowbase, jb + 32, j1, lane);
@@ -603,7 +618,7 @@ static int32_t launch_fwd_tma(const FwdParams& p, int loss, int score, cudaStrea
                                     : launch_fwd_tma_ls<RSB200_LOSS_SSM, RSB200_SCORE_EUCLID>(p, st);
 }
 
-template <int VPL, int LOSS, int SCORE, bool PIPE>
+template <int VPL, int LOSS, int SCORE, int PIPE>
 static int32_t launch_fwd_vlsp(const FwdParams& p, cudaStream_t st) {
     const bool multi = p.n >= 256;
     if (multi) {
@@ -619,7 +634,7 @@ static int32_t launch_fwd_vlsp(const FwdParams& p, cudaStream_t st) {
     return 0;
 }
 
-template <int VPL, bool PIPE>
+template <int VPL, int PIPE>
 static int32_t launch_fwd_v(const FwdParams& p, int loss, int score, cudaStream_t st) {
     if (loss == RSB200_LOSS_BPR) {
         return score == RSB200_SCORE_IP ? launch_fwd_vlsp<VPL, RSB200_LOSS_BPR, RSB200_SCORE_IP, PIPE>(p, st)
@@ -636,9 +651,12 @@ int32_t launch_pair_fwd(const FwdParams& p, int loss, int score, int variant, cu
     if (p.B == 0) return 0;
     const bool pipe = variant == 1;
     if (variant == 2 && p.D <= 128) return launch_fwd_tma(p, loss, score, st);   // TMA (cp.async.bulk) ring
-    if (p.D <= 128) return pipe ? launch_fwd_v<1, true>(p, loss, score, st) : launch_fwd_v<1, false>(p, loss, score, st);
-    if (p.D <= 256) return launch_fwd_v<2, false>(p, loss, score, st);
-    if (p.D <= 512) return launch_fwd_v<4, false>(p, loss, score, st);
+    if (p.D <= 128) {
+        if (p.hint) return launch_fwd_v<1, 2>(p, loss, score, st);               // variants 4..7: L2 eviction hints
+        return pipe ? launch_fwd_v<1, 1>(p, loss, score, st) : launch_fwd_v<1, 0>(p, loss, score, st);
+    }
+    if (p.D <= 256) return launch_fwd_v<2, 0>(p, loss, score, st);
+    if (p.D <= 512) return launch_fwd_v<4, 0>(p, loss, score, st);
     set_error("embedding dim %d > 512 is not supported", p.D);
     return RSB200_EUNSUPPORTED;
 }
@@ -650,9 +668,9 @@ static int32_t launch_partial_v(const FwdParams& p, int loss, int score, cudaStr
 #define RSB_PARTIAL(LOSS, SCORE)                                                                                      \
     do {                                                                                                              \
         if (smem > 48 * 1024)                                                                                         \
-            RSB_CUDA(cudaFuncSetAttribute(pair_fwd_kernel<VPL, LOSS, SCORE, false, false, true>,                      \
+            RSB_CUDA(cudaFuncSetAttribute(pair_fwd_kernel<VPL, LOSS, SCORE, false, 0, true>,                      \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
-        pair_fwd_kernel<VPL, LOSS, SCORE, false, false, true><<<grid, kThreads, smem, st>>>(p);                       \
+        pair_fwd_kernel<VPL, LOSS, SCORE, false, 0, true><<<grid, kThreads, smem, st>>>(p);                       \
     } while (0)
     if (loss == RSB200_LOSS_BPR) {
         if (score == RSB200_SCORE_IP) RSB_PARTIAL(RSB200_LOSS_BPR, RSB200_SCORE_IP);

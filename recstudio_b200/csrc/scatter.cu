@@ -24,9 +24,13 @@ namespace rsb {
 constexpr int kScatWarps = 8;
 
 // PLAIN = compact sink, overwrite, inner-product: the hot configuration with all options compiled out
-template <int VPL, bool PLAIN>
+// HINT (PLAIN only) = L2 eviction priorities: the entry list and the gradient rows are touched once
+// (evict_first), the query matrix is re-read by every entry (evict_last).
+template <int VPL, bool PLAIN, bool HINT = false>
 __global__ void __launch_bounds__(kScatWarps * 32)
 scatter_kernel(const ScatterParams p) {
+    uint64_t pol_first = 0, pol_last = 0;
+    if (HINT) { pol_first = l2_policy(1); pol_last = l2_policy(2); }
     const int lane = threadIdx.x & 31;
     const int D = p.D;
     const uint32_t R = (uint32_t)min((int64_t)p.totals[1], p.cap);
@@ -70,7 +74,8 @@ scatter_kernel(const ScatterParams p) {
             const uint32_t e = eb + lane;
             uint32_t bq = 0; float c = 0.f;
             if (e < e_end) {
-                const uint64_t en = __ldg(reinterpret_cast<const unsigned long long*>(p.ent) + e);
+                const uint64_t en = HINT ? ldg64_stream_hint(p.ent + e, pol_first)
+                                         : __ldg(reinterpret_cast<const unsigned long long*>(p.ent) + e);
                 const uint32_t lo = (uint32_t)en;
                 const float val = __uint_as_float((uint32_t)(en >> 32));
                 bq = lo & 0x7FFFFFFFu;
@@ -90,7 +95,8 @@ scatter_kernel(const ScatterParams p) {
                     const float* srow = p.src + (size_t)bt * D + lane * 4;
 #pragma unroll
                     for (int x = 0; x < VPL; ++x)
-                        v[k][x] = act[x] ? ldg128(srow + x * 128) : make_float4(0, 0, 0, 0);
+                        v[k][x] = act[x] ? (HINT ? ldg128_hint(srow + x * 128, pol_last) : ldg128(srow + x * 128))
+                                         : make_float4(0, 0, 0, 0);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -117,7 +123,8 @@ scatter_kernel(const ScatterParams p) {
                                     const float4 o = *reinterpret_cast<const float4*>(dst);
                                     a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
                                 }
-                                stg128_stream(dst, a);
+                                if (HINT) stg128_stream_hint(dst, a, pol_first);
+                                else stg128_stream(dst, a);
                             }
                             acc[x] = make_float4(0, 0, 0, 0);
                         }
@@ -147,7 +154,8 @@ loss_sum_kernel(const float* __restrict__ part, int B, float* __restrict__ loss)
 template <int VPL>
 static void launch_scatter_v(const ScatterParams& p, unsigned blocks, cudaStream_t st) {
     const bool plain = !p.dense && !p.accumulate && !p.euclid;
-    if (plain) scatter_kernel<VPL, true><<<blocks, kScatWarps * 32, 0, st>>>(p);
+    if (plain && p.hint && VPL == 1) scatter_kernel<VPL, true, true><<<blocks, kScatWarps * 32, 0, st>>>(p);
+    else if (plain) scatter_kernel<VPL, true><<<blocks, kScatWarps * 32, 0, st>>>(p);
     else scatter_kernel<VPL, false><<<blocks, kScatWarps * 32, 0, st>>>(p);
 }
 

@@ -257,7 +257,7 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         p.ent_item = a->ent; p.ent_user = nullptr; p.q_buf = nullptr; p.dq_buf = a->dq; p.loss_part = nullptr; p.lse = nullptr;
         p.pos_score = nullptr; p.neg_score = nullptr;
         p.num_items = (int)a->local_rows; p.num_users = (int)G; p.B = (int)G; p.n = (int)n; p.D = (int)a->d;
-        p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0;
+        p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0; p.hint = 0;
         p.ncount = a->ncount; p.sp_in = a->sp; p.stats_part = a->stats_all + 2 * (size_t)a->rank * (size_t)G;
         rc = launch_pair_fwd_partial(p, a->loss_kind, a->score_kind, st);
         if (rc) return rc;
@@ -281,7 +281,7 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         s.off = a->off; s.urow = a->urow; s.totals = a->totals; s.ent = a->ent; s.src = a->q_all; s.lse = a->lse;
         s.w = a->w_local; s.gscale = a->grad_scale_dev; s.rows_out = a->item_rows; s.vals = a->item_vals; s.cap = a->cap;
         s.D = (int)a->d; s.ssm_scale = coef_scale;
-        s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = eu;
+        s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = eu; s.hint = 0;
         rc = launch_scatter(s, a->cap, st);
         if (rc) return rc;
     }

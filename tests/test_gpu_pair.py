@@ -24,7 +24,7 @@ def _cfg(name):
 
 
 def _run(w_item, w_user, user, pos, neg, loss, scorer, lqp=None, lqn=None, sink="compact", neg_dtype=torch.int64,
-         want_scores=True):
+         want_scores=True, variant=0):
     from recstudio_b200 import fused
     dev = torch.device("cuda:0")
     wi = torch.as_tensor(w_item, dtype=torch.float32).to(dev).contiguous()
@@ -42,7 +42,7 @@ def _run(w_item, w_user, user, pos, neg, loss, scorer, lqp=None, lqn=None, sink=
     if sink == "dense":
         kw["dense_item_grad"] = torch.zeros_like(wi)
         kw["dense_user_grad"] = torch.zeros_like(wu)
-    loss_t = fused.pair_step(ws, wi, wu, u, p, ng, loss, scorer, **kw)
+    loss_t = fused.pair_step(ws, wi, wu, u, p, ng, loss, scorer, variant=variant, **kw)
     torch.cuda.synchronize()
     assert int(ws.err_flag.item()) == 0
     out = {"loss": float(loss_t.item()), "ws": ws}
@@ -94,6 +94,21 @@ def test_dense_sink_and_int32_ids(name):
     out = _run(g["w_item"], g["w_user"], g["user"], g["pos"], g["neg"], loss, scorer, lqp=g["log_pos_prob"],
                lqn=g["log_neg_prob"], sink="dense", neg_dtype=torch.int32, want_scores=False)
     assert abs(out["loss"] - g["loss"].item()) <= RTOL * abs(g["loss"].item())
+    _check_grads(out, g["d_item"], g["d_user"])
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 17, 19, 22, 23, 31])
+@pytest.mark.parametrize("name", ["step_d128_bpr_ip", "step_d128_ssm_eu", "step_d64dup_ssm_ip"])
+def test_kernel_variants_match_golden(name, variant):
+    """The experimental forward variants (rsb200_pair_args.variant: 1 pipelined, 2 TMA ring, 3 L2 prefetch,
+    16..31 L2 eviction-priority hints) change the memory schedule only: same golden outputs."""
+    g = load_golden(name)
+    loss, scorer = _cfg(name)
+    out = _run(g["w_item"], g["w_user"], g["user"], g["pos"], g["neg"], loss, scorer,
+               lqp=g["log_pos_prob"], lqn=g["log_neg_prob"], variant=variant)
+    assert abs(out["loss"] - g["loss"].item()) <= RTOL * abs(g["loss"].item())
+    sc = max(1.0, np.abs(g["neg_score"]).max())
+    assert np.abs(out["neg_score"] - g["neg_score"]).max() <= RTOL * sc
     _check_grads(out, g["d_item"], g["d_user"])
 
 

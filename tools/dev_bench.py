@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--score", type=int, default=0)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variants", type=str, default="", help="comma list: time each variant in this process")
     ap.add_argument("--sampler", default="uniform", choices=["uniform", "popular"])
     ap.add_argument("--mode", type=int, default=0, help="PopularSamplerModel mode (0 log, 2 count^0.75)")
     a = ap.parse_args()
@@ -41,6 +42,12 @@ def main():
         counts[0] = 0
         pop = plugins.FusedPopularSampler(counts, mode=a.mode).to(dev)
     names = ["sample", "count", "scan", "fwd", "scatter"]
+    for variant in ([int(v) for v in a.variants.split(",")] if a.variants else [a.variant]):
+        a.variant = variant
+        run_variant(a, dev, wi, wu, user, pos, ws, pop, names)
+
+
+def run_variant(a, dev, wi, wu, user, pos, ws, pop, names):
     tot = {k: 0.0 for k in names}
     for it in range(a.steps + 3):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
@@ -62,7 +69,7 @@ def main():
     rows = (a.n + 2) * a.B
     alg = 2 * rows * a.d * 4
     t = ws.totals.tolist()
-    print(json.dumps({"ms": ms, "step_ms": step, "loss": float(loss.item()), "interactions_per_s": a.B / step * 1e3,
+    print(json.dumps({"variant": a.variant, "ms": ms, "step_ms": step, "loss": float(loss.item()), "interactions_per_s": a.B / step * 1e3,
                       "fwd_GBps": rows * a.d * 4 / ms["fwd"] / 1e6, "step_alg_GBps": alg / step / 1e6,
                       "unique_item_rows": t[1], "entries": t[0], "ws_GB": ws.nbytes() / 1e9}))
 
