@@ -114,6 +114,22 @@ int32_t rsb200_sample_popular(uint64_t seed, uint64_t philox_offset,
 int32_t rsb200_popular_logq(const float* pop_prob, int64_t num_items, const int64_t* ids, int64_t numel,
                             float* out, void* stream);
 
+/* S3  MaskedUniformSampler.forward / uniform_sample_masked_hist   recstudio/ann/sampler.py:117-147,187-214
+ * Uniform over the items a user has NOT interacted with: user_hist is [num_users, hist_len] int64,
+ * right- or left-padded with 0, hist_len <= 4096.  Draws per_user ids per row (per_user =
+ * num_query_per_user * num_neg; the [.., n_q, num_neg] reshape of the reference is a view).
+ * Bit-identical to the reference on a CUDA device for the same generator (seed, offset): the seeds are
+ * torch.rand(num_users, per_user), the history row is sorted, shifted and searched exactly as
+ * sampler.py:137-144 does (ATen upper_bound loop, so duplicate history items behave the same too).
+ * num_items = table rows INCLUDING the padding row (the sampler draws from [1, num_items-1] minus history).
+ * Workspace: adj_ws int64 [num_users*hist_len], cnt_ws int32 [num_users]. */
+int32_t rsb200_masked_workspace_elems(int64_t num_users, int64_t hist_len, int64_t* adj_elems, int64_t* cnt_elems);
+int32_t rsb200_sample_uniform_masked(uint64_t seed, uint64_t philox_offset, int64_t num_items,
+                                     const int64_t* user_hist, int64_t num_users, int64_t hist_len,
+                                     int64_t per_user, int32_t sm_count, int32_t max_threads_per_sm,
+                                     int64_t* adj_ws, int32_t* cnt_ws,
+                                     int64_t* neg_out_i64, int32_t* neg_out_i32, void* stream);
+
 /* -------------------------------------------------------------------------
  * R1 + E1 + Q1/Q2 + L1/L2 + E2: the fused retriever training step
  *   BaseRetriever.forward (sampler branch) + training_step + loss.backward()

@@ -215,3 +215,34 @@ def dict_to_dense(d, shape):
     for r, v in d.items():
         out[r] = v
     return out
+
+
+# ------------------------------------------------------------------ sampling methods (8(f)-2)
+def select_from_pool(method: str, query, w_item, pool, num_keep: int, scorer: int = IP, resampled_id=None):
+    """The pool stage of ``BaseRetriever.sampling`` for ``method`` 'dns' / 'sir'
+    (recstudio/model/basemodel/baseretriever.py:331-355) given the drawn pool:
+      scores = score_func(query, item_encoder(pool))                       :323-324
+      dns: neg = pool[topk(scores, num_keep)], log_neg_prob = int64 zeros  :326-330
+      sir: p = softmax(scores + eps); idx = multinomial(p, num_keep); neg = pool[idx],
+           log_neg_prob = scores[idx]                                      :336-342
+    ``resampled_id`` injects the multinomial outcome (its stream is device specific).
+    Returns dict(scores, neg_id, log_neg_prob, probs)."""
+    pool = torch.as_tensor(pool, dtype=torch.int64)
+    vec = F.embedding(pool, w_item, padding_idx=0)
+    scores = score(scorer, query, vec)
+    out = {"scores": scores}
+    if method == "dns":
+        _, topk_id = torch.topk(scores, num_keep)
+        out["neg_id"] = torch.gather(pool, -1, topk_id)
+        out["log_neg_prob"] = torch.zeros_like(out["neg_id"])
+    elif method == "sir":
+        probs = torch.softmax(scores + torch.finfo(torch.float32).eps, dim=-1)
+        out["probs"] = probs
+        if resampled_id is None:
+            resampled_id = torch.multinomial(probs, num_keep, replacement=True)
+        resampled_id = torch.as_tensor(resampled_id, dtype=torch.int64)
+        out["neg_id"] = torch.gather(pool, -1, resampled_id)
+        out["log_neg_prob"] = torch.gather(scores, -1, resampled_id)
+    else:
+        raise ValueError(method)
+    return out

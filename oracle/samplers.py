@@ -94,3 +94,51 @@ def popular_sampler(seed: int, offset: int, table: np.ndarray, pop_prob: np.ndar
         pos = torch.as_tensor(np.asarray(pos_items))
         log_pos = torch.log(torch.from_numpy(pop_prob)[pos]).numpy()
     return log_pos, idx.reshape(num_queries, num_neg), logq.reshape(num_queries, num_neg), new_offset
+
+
+# --------------------------------------------------------------------------- S3
+def _upper_bound(row: np.ndarray, val: int) -> int:
+    """ATen ``upper_bound`` (aten/src/ATen/native/cuda/Bucketization.cu; same loop on CPU):
+    the exact bisection, so NON-monotone rows (duplicate history items) give the reference's answer."""
+    start, end = 0, row.shape[0]
+    while start < end:
+        mid = start + ((end - start) >> 1)
+        if not (row[mid] > val):
+            start = mid + 1
+        else:
+            end = mid
+    return start
+
+
+def masked_uniform_from_seeds(num_items: int, user_hist: np.ndarray, seeds: np.ndarray) -> np.ndarray:
+    """``uniform_sample_masked_hist`` (recstudio/ann/sampler.py:117-147) given the
+    ``torch.rand(num_user, n_q * num_neg)`` seeds.  ``num_items`` is ``Sampler.num_items``
+    (real items, padding excluded).  Integer work in numpy; the one fp32 product
+    ``rand * (num_items - count)`` is an fp32 multiply exactly as torch promotes it."""
+    user_hist = np.asarray(user_hist, dtype=np.int64)
+    seeds = np.asarray(seeds, dtype=np.float32)
+    num_user, hist_len = user_hist.shape
+    nz = np.count_nonzero(user_hist, axis=-1)                                        # :131
+    span = (num_items - nz).astype(np.float32)[:, None]                              # int64 -> fp32 promotion
+    neg = np.floor(seeds * span).astype(np.int64) + 1                                # :133
+    sorted_hist = np.sort(user_hist, axis=-1)                                        # :134
+    offset = np.arange(hist_len, dtype=np.int64)[None, :] - (hist_len - nz)[:, None]  # :135-136
+    offset[offset < 0] = 0                                                           # :137
+    adj = sorted_hist - offset                                                       # :138
+    out = np.empty_like(neg)
+    for b in range(num_user):                                                        # :139-141
+        pad = hist_len - nz[b]
+        for j in range(neg.shape[1]):
+            out[b, j] = neg[b, j] + _upper_bound(adj[b], int(neg[b, j])) - pad
+    return out
+
+
+def masked_uniform_sampler(seed: int, offset: int, num_items_with_pad: int, user_hist: np.ndarray, per_user: int,
+                           sm_count: int, max_threads_per_sm: int):
+    """``MaskedUniformSampler.forward`` on CUDA (sampler.py:187-214): seeds are
+    ``torch.rand(num_user, per_user, device=cuda)``.  Returns (neg [num_user, per_user], new_offset)."""
+    num_user = user_hist.shape[0]
+    numel = num_user * per_user
+    seeds = philox.torch_cuda_rand(seed, offset, numel, sm_count, max_threads_per_sm).reshape(num_user, per_user)
+    neg = masked_uniform_from_seeds(num_items_with_pad - 1, user_hist, seeds)
+    return neg, offset + philox.torch_cuda_counter_offset(numel, sm_count, max_threads_per_sm)

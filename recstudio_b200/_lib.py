@@ -114,6 +114,8 @@ def lib():
             "rsb200_popular_build_guide": [v, i64, i32, v, v],
             "rsb200_sample_popular": [u64, u64, v, v, i64, i64, i64, i32, i32, v, i32, v, v, v, v],
             "rsb200_popular_logq": [v, i64, v, i64, v, v],
+            "rsb200_masked_workspace_elems": [i64, i64, v, v],
+            "rsb200_sample_uniform_masked": [u64, u64, i64, v, i64, i64, i64, i32, i32, v, v, v, v, v],
             "rsb200_pair_workspace_sizes": [i64, i64, i64, i64, i64, C.POINTER(PairSizes)],
             "rsb200_pair_step": [C.POINTER(PairArgs), i32, v],
             "rsb200_shard_step": [C.POINTER(ShardArgs), i32, v],

@@ -71,6 +71,60 @@ score_ids_kernel(const float* __restrict__ q, const float* __restrict__ w, int64
     if (lane == 0) out[i] = (SCORE == RSB200_SCORE_IP) ? a : -a;
 }
 
+// Q1/Q2 on ids, d <= 128, streaming form (the pool scoring of sampling_method dns / sir, baseretriever.py:
+// 323-324): a warp takes 32 ids of one query, keeps 8 row requests (8 x 512 B) in flight, and reduces the 8
+// partial dot products with a transposed butterfly (lane L ends up with row L / 4 of the group).
+template <int SCORE>
+__global__ void __launch_bounds__(256)
+score_ids_stream_kernel(const float* __restrict__ q, const float* __restrict__ w, int64_t num_rows, int D,
+                        const int64_t* __restrict__ ids, int64_t B, int64_t n, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chunks = (n + 31) / 32;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (wid >= B * chunks) return;
+    const int64_t b = wid / chunks;
+    const int64_t jb = (wid - b * chunks) * 32;
+    const int cnt = (int)min((int64_t)32, n - jb);
+    const bool act = lane * 4 < D;
+    const float4 qv = act ? ldg128(q + (size_t)b * D + lane * 4) : make_float4(0, 0, 0, 0);
+    int64_t id = (lane < cnt) ? ids[b * n + jb + lane] : 0;
+    if (id < 0 || id >= num_rows) id = 0;
+    float mine = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (g * 8 < cnt) {                                  // warp-uniform
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t rid = __shfl_sync(kFull, id, g * 8 + k);
+                v[k] = act ? ldg128_stream(w + (size_t)rid * D + lane * 4) : make_float4(0, 0, 0, 0);
+            }
+            float pr[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pr[k] = (SCORE == RSB200_SCORE_IP) ? dot4(qv, v[k]) : sqdist4(qv, v[k]);
+            // transposed butterfly: 8 partials per lane -> lane L holds the full sum of row L / 4
+#pragma unroll
+            for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < half) {
+                        const float send = up ? pr[i] : pr[i + half];
+                        const float keep = up ? pr[i + half] : pr[i];
+                        pr[i] = keep + __shfl_xor_sync(kFull, send, off);
+                    }
+                }
+            }
+            float s = pr[0];
+            s += __shfl_xor_sync(kFull, s, 2);
+            s += __shfl_xor_sync(kFull, s, 1);
+            const float ts = __shfl_sync(kFull, s, (lane & 7) * 4);
+            if ((lane >> 3) == g) mine = ts;
+        }
+    }
+    if (lane < cnt) out[b * n + jb + lane] = (SCORE == RSB200_SCORE_IP) ? mine : -mine;
+}
+
 // L1/L2 on score tensors: one warp per query; loss and d loss/d score in one pass.
 template <int LOSS>
 __global__ void __launch_bounds__(256)
@@ -164,6 +218,15 @@ extern "C" int32_t rsb200_score_ids(int32_t score_kind, const float* q, const fl
     RSB_REQUIRE(q && ids && out && aligned16(q), RSB200_EINVAL, "null / misaligned pointer");
     RSB_REQUIRE(score_kind == RSB200_SCORE_IP || score_kind == RSB200_SCORE_EUCLID, RSB200_EINVAL, "bad score_kind");
     if (B * n == 0) return 0;
+    if (d <= 128 && n >= 8) {
+        unsigned sgrid = (unsigned)cdiv(B * cdiv(n, 32), 8);
+        if (score_kind == RSB200_SCORE_IP)
+            score_ids_stream_kernel<RSB200_SCORE_IP><<<sgrid, 256, 0, (cudaStream_t)stream>>>(q, w, num_rows, (int)d, ids, B, n, out);
+        else
+            score_ids_stream_kernel<RSB200_SCORE_EUCLID><<<sgrid, 256, 0, (cudaStream_t)stream>>>(q, w, num_rows, (int)d, ids, B, n, out);
+        RSB_LAUNCH_CHECK();
+        return 0;
+    }
     unsigned grid = (unsigned)cdiv(B * n, 8);
     if (score_kind == RSB200_SCORE_IP)
         score_ids_kernel<RSB200_SCORE_IP><<<grid, 256, 0, (cudaStream_t)stream>>>(q, w, num_rows, (int)d, ids, B, n, out);

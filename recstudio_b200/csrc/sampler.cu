@@ -104,6 +104,90 @@ logq_kernel(const float* __restrict__ pop_prob, int64_t num_items, const int64_t
     out[i] = logf(__ldg(pop_prob + id));
 }
 
+
+// ------------------------------------------------------------------------------------------
+// S3  MaskedUniformSampler (sampler.py:117-147,187-214): uniform over the items a user has NOT
+// interacted with.  Reference arithmetic per user row b (H = history width, c_b = nonzero count):
+//   neg   = floor(rand * float(num_items - c_b)) + 1                      (:133-136)
+//   adj   = sort(hist_b) - max(i - (H - c_b), 0)                          (:137-141)
+//   neg  += searchsorted(adj, neg, right=True) - (H - c_b)                (:142-144)
+// masked_prep_kernel sorts one history row per CTA (bitonic, shared memory) and stores `adj`;
+// masked_draw_kernel reproduces torch.rand's Philox element map and runs ATen's upper_bound loop
+// (ATen/native/cuda/Bucketization.cu) over the FULL adjusted row, so results match the reference
+// even for histories with duplicate items (where `adj` is not monotone).
+constexpr int kMaskMaxHist = 4096;
+
+__global__ void __launch_bounds__(256)
+masked_prep_kernel(const int64_t* __restrict__ hist, int H, int P /* pow2 >= H */, int64_t* __restrict__ adj,
+                   int32_t* __restrict__ cnt_out) {
+    extern __shared__ long long sh_hist[];
+    __shared__ int sh_cnt;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) sh_cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        long long v = (i < H) ? (long long)hist[(size_t)b * H + i] : 0x7FFFFFFFFFFFFFFFll;
+        sh_hist[i] = v;
+        local += (i < H && v != 0) ? 1 : 0;
+    }
+    if (local) atomicAdd(&sh_cnt, local);
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    long long a = sh_hist[i], c = sh_hist[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > c) == up) { sh_hist[i] = c; sh_hist[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int c = sh_cnt;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        int off = i - (H - c);
+        adj[(size_t)b * H + i] = (int64_t)sh_hist[i] - (off > 0 ? off : 0);
+    }
+    if (threadIdx.x == 0) cnt_out[b] = c;
+}
+
+__global__ void __launch_bounds__(256)
+masked_draw_kernel(uint64_t seed, uint64_t ctr_base, int64_t T, int64_t rounds, int64_t numel, int64_t per_user,
+                   int64_t num_items /* real items, padding excluded (Sampler.num_items) */,
+                   const int64_t* __restrict__ adj, const int32_t* __restrict__ cnt, int H,
+                   int64_t* __restrict__ out64, int32_t* __restrict__ out32) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T * rounds) return;
+    int64_t r = t / T, idx = t - r * T;
+    uint4 w = Philox::gen(seed, (uint64_t)idx, ctr_base + (uint64_t)r);
+    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    int64_t li = r * 4 * T + idx;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii, li += T) {
+        if (li < numel) {
+            float u = curand_uniform_from_u32(words[ii]);
+            u = u * 1.0f + 0.0f;
+            if (u == 1.0f) u = 0.0f;                                   // torch.rand: [0, 1)
+            const int64_t b = li / per_user;
+            const int c = __ldg(cnt + b);
+            const float span = (float)(num_items - (int64_t)c);        // int64 -> fp32 promotion of the reference
+            int64_t neg = (int64_t)floorf(__fmul_rn(u, span)) + 1;
+            const int64_t* row = adj + (size_t)b * H;
+            int start = 0, end = H;                                    // upper_bound: first adj[i] > neg
+            while (start < end) {
+                const int mid = start + ((end - start) >> 1);
+                if (!(__ldg(row + mid) > neg)) start = mid + 1; else end = mid;
+            }
+            neg += (int64_t)start - (int64_t)(H - c);
+            if (out64) out64[li] = neg;
+            if (out32) out32[li] = (int32_t)neg;
+        }
+    }
+}
+
 }  // namespace rsb
 
 using namespace rsb;
@@ -178,6 +262,38 @@ extern "C" int32_t rsb200_popular_logq(const float* pop_prob, int64_t num_items,
     RSB_REQUIRE(pop_prob && ids && out, RSB200_EINVAL, "null pointer");
     if (numel == 0) return 0;
     logq_kernel<<<(unsigned)cdiv(numel, 256), 256, 0, (cudaStream_t)stream>>>(pop_prob, num_items, ids, numel, out);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t rsb200_masked_workspace_elems(int64_t num_users, int64_t hist_len, int64_t* adj_elems, int64_t* cnt_elems) {
+    RSB_REQUIRE(adj_elems && cnt_elems && num_users >= 0 && hist_len >= 0, RSB200_EINVAL, "bad arguments");
+    *adj_elems = num_users * hist_len;
+    *cnt_elems = num_users;
+    return 0;
+}
+
+extern "C" int32_t rsb200_sample_uniform_masked(uint64_t seed, uint64_t philox_offset, int64_t num_items,
+                                                const int64_t* user_hist, int64_t num_users, int64_t hist_len,
+                                                int64_t per_user, int32_t sm_cnt, int32_t max_tpsm,
+                                                int64_t* adj_ws, int32_t* cnt_ws,
+                                                int64_t* neg64, int32_t* neg32, void* stream) {
+    int32_t rc = check_draw(philox_offset, num_items, num_users, per_user, sm_cnt, max_tpsm);
+    if (rc) return rc;
+    RSB_REQUIRE(user_hist && adj_ws && cnt_ws, RSB200_EINVAL, "null history / workspace pointer");
+    RSB_REQUIRE(hist_len >= 1 && hist_len <= kMaskMaxHist, RSB200_EUNSUPPORTED,
+                "history width %lld outside [1, %d]", (long long)hist_len, kMaskMaxHist);
+    int64_t numel = num_users * per_user;
+    if (numel == 0) return 0;
+    int P = 1;
+    while (P < hist_len) P <<= 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    masked_prep_kernel<<<(unsigned)num_users, 256, (size_t)P * sizeof(long long), st>>>(user_hist, (int)hist_len, P, adj_ws, cnt_ws);
+    RSB_LAUNCH_CHECK();
+    DrawPolicy p = make_policy(numel, sm_cnt, max_tpsm);
+    int64_t threads = p.T * p.rounds;
+    masked_draw_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(seed, philox_offset / 4, p.T, p.rounds, numel, per_user,
+                                                                     num_items - 1, adj_ws, cnt_ws, (int)hist_len, neg64, neg32);
     RSB_LAUNCH_CHECK();
     return 0;
 }

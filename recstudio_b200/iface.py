@@ -19,6 +19,7 @@ import torch
 HAVE_RECSTUDIO = False
 try:  # pragma: no cover - depends on the environment
     import recstudio.model  # noqa: F401  (must come first, see above)
+    from recstudio.ann.sampler import MaskedUniformSampler as RefMaskedUniformSampler
     from recstudio.ann.sampler import PopularSamplerModel as RefPopularSamplerModel
     from recstudio.ann.sampler import Sampler
     from recstudio.ann.sampler import UniformSampler as RefUniformSampler
@@ -76,6 +77,9 @@ except Exception:  # recstudio (or one of its hard deps: nni, torchmetrics) is a
         pass
 
     class RefPopularSamplerModel(Sampler):
+        pass
+
+    class RefMaskedUniformSampler(Sampler):
         pass
 
     class RefBPRLoss(PairwiseLoss):

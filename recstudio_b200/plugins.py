@@ -162,6 +162,40 @@ class FusedPopularSampler(iface.Sampler):
         return neg32, logq
 
 
+class FusedMaskedUniformSampler(iface.Sampler):
+    """MaskedUniformSampler (sampler.py:187-214): uniform negatives that exclude each user's history.
+    ``query`` is [B, d] (one draw row per user) or [B, L, d] (``L`` queries per user, result [B, L, n]);
+    ``user_hist`` is the 0-padded int64 history matrix of the batch.  Ids are bit-identical to the reference
+    on a CUDA device for the same generator state (rsb200_sample_uniform_masked); the log-probabilities are
+    the reference's ``-log(ones_like(ids))`` (float32 negative zeros)."""
+
+    def forward(self, query, num_neg: int, pos_items: Optional[Tensor] = None, user_hist: Optional[Tensor] = None):
+        if user_hist is None:
+            raise ValueError("MaskedUniformSampler needs `user_hist` (train with excluding_hist=True)")
+        if query.dim() == 2:
+            per_user, shape = num_neg, (user_hist.shape[0], num_neg)
+        elif query.dim() == 3:
+            per_user, shape = query.size(1) * num_neg, (user_hist.shape[0], query.size(1), num_neg)
+        else:
+            raise ValueError("`query` need to be 2-dimensional or 3-dimensional.")
+        _need_cuda(user_hist, "user_hist")
+        neg, _ = sampling.masked_uniform_draw(self.num_items + 1, user_hist, per_user)
+        neg = neg.reshape(shape)
+        neg_prob = self.compute_item_p(query, neg)
+        if pos_items is not None:
+            return self.compute_item_p(query, pos_items), neg, neg_prob
+        return neg, neg_prob
+
+    def compute_item_p(self, query, pos_items):
+        return -torch.log(torch.ones_like(pos_items))
+
+    def fused_draw(self, num_queries: int, num_neg: int, device, user_hist: Optional[Tensor] = None):
+        if user_hist is None or user_hist.shape[0] != num_queries:
+            raise ValueError("MaskedUniformSampler.fused_draw needs the batch's user_hist [B, H]")
+        _, neg32 = sampling.masked_uniform_draw(self.num_items + 1, user_hist.to(device), num_neg, want_i64=False, want_i32=True)
+        return neg32, None
+
+
 # ============================================================================ Q1 / Q2
 class _ScoreDenseFn(torch.autograd.Function):
     @staticmethod
@@ -406,7 +440,22 @@ class _FusedHeadFn(torch.autograd.Function):
         return (gi, dquery) + nones
 
 
-_FUSABLE_SAMPLERS = (FusedUniformSampler, FusedPopularSampler)
+_FUSABLE_SAMPLERS = (FusedUniformSampler, FusedPopularSampler, FusedMaskedUniformSampler)
+_FUSABLE_METHODS = ("none", "dns", "sir", "toprand", "top&rand", "brute")
+
+
+def score_ids(kind: int, query: Tensor, w_item: Tensor, ids: Tensor) -> Tensor:
+    """score_func(query[b], W[ids[b, j]]) for a [B, n] id matrix without building the [B, n, d] tensor
+    (rsb200_score_ids): the pool scoring of the dns / sir sampling methods (baseretriever.py:323-324)."""
+    _need_cuda(query, "query")
+    q = query.detach().contiguous().float()
+    ids = ids.to(q.device, torch.int64).contiguous()
+    B, n = ids.shape
+    out = torch.empty(B, n, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(lib().rsb200_score_ids(kind, ptr(q), ptr(w_item.detach()), w_item.shape[0], w_item.shape[1], ptr(ids), B, n,
+                                     ptr(out), stream_ptr()), "score_ids")
+    return out
 _LOSS_KIND = {FusedBPRLoss: LOSS_BPR, FusedSampledSoftmaxLoss: LOSS_SSM}
 _SCORE_KIND = {FusedInnerProductScorer: SCORE_IP, FusedEuclideanScorer: SCORE_EUCLID}
 
@@ -424,15 +473,114 @@ class FusedRetrieverMixin:
     """
     fused_grad = "dense"
 
+    # --- BaseRetriever.sampling (baseretriever.py:248-369) on the CUDA ops -----------------------------------
+    def _pool_scores(self, query, pool):
+        """scores of a [B, n0] candidate pool: ids -> rows -> score in one kernel when the item tower is a
+        plain table and the scorer is IP / Euclid, else through the (standalone) plugins like the reference."""
+        sk = _SCORE_KIND.get(type(self.score_func))
+        if sk is not None and isinstance(self.item_encoder, torch.nn.Embedding) and query.dim() == 2 and pool.dim() == 2 \
+                and len(getattr(self, "item_fields", [self.fiid])) == 1 and self.item_encoder.weight.is_cuda:
+            return score_ids(sk, query, self.item_encoder.weight, pool)
+        with torch.no_grad():
+            return self.score_func(query.detach(), self.item_encoder(self._get_item_feat(pool)))
+
+    def sampling(self, batch, num_neg, method="none", excluding_hist=False, t=1, return_query=False, query=None):
+        """All six sampling methods of the reference with identical semantics and RNG call order
+        (baseretriever.py:248-369): 'none' draws from the sampler; 'dns' / 'sir' draw a pool of num_neg[0] ids,
+        score it (rsb200_score_ids: no [B, n0, d] tensor) and keep the top num_neg[1] / resample with
+        softmax(score) weights; 'toprand' / 'top&rand' take candidates from the fused full-catalog top-k
+        (rsb200_topk_full); 'brute' samples from softmax(all scores / t)."""
+        pos_items = batch.get(self.fiid, None)
+        if pos_items is not None and pos_items.dim() == 1:
+            pos_items = pos_items.view(-1, 1)                                     # :255-258
+        user_hist = batch.get("user_hist", None)
+        if user_hist is None:
+            user_hist = batch.get(self.fiid, None)                                # :260-262
+        if isinstance(num_neg, int):
+            num_neg = [num_neg, num_neg]
+        elif isinstance(num_neg, (list, tuple)):
+            assert len(num_neg) == 2, "length of negative_count must be 2 when it's list type for retriever_dns sampler."
+            assert num_neg[0] >= num_neg[1], "the first element of negative_count must be larger than the second element."
+        else:
+            raise TypeError("num_neg only support int and List/Tuple type.")
+        if method not in _FUSABLE_METHODS:
+            raise NotImplementedError("sampling method only support one of none/brute/is/dns/top/toprand/top&rand")
+
+        if method == "none":
+            assert self.sampler is not None, "excepted sampler of retriever to be Sampler, but get None."
+            log_pos_prob, neg_id, log_neg_prob, query = self._sample(batch, num_neg[1], excluding_hist, True)
+        elif method == "toprand":                                                 # :281-287
+            _, topk_items, query = self.topk(batch, k=num_neg[0], user_h=user_hist, return_query=True)
+            rand_idx = torch.randint(0, num_neg[0], (topk_items.size(0), num_neg[1]), device=topk_items.device)
+            neg_id = torch.gather(topk_items, -1, rand_idx)
+            log_neg_prob = torch.zeros_like(neg_id)
+            log_pos_prob = None if pos_items is None else torch.zeros_like(pos_items)
+        elif method == "top&rand":                                                # :289-299
+            num_neg_0 = num_neg[1] // 2
+            _, neg_id, query = self.topk(batch, k=num_neg_0, user_h=user_hist, return_query=True)
+            num_queries = int(np.prod(query.shape[:-1]))
+            n_items = self._get_item_vector().size(0) + 1
+            rand_id, _ = sampling.uniform_draw(n_items, num_queries, num_neg[1] - num_neg_0, query.device)
+            neg_id = torch.cat((neg_id, rand_id), dim=-1)
+            log_neg_prob = torch.zeros_like(neg_id)
+            log_pos_prob = None if pos_items is None else torch.zeros_like(pos_items)
+        elif method == "brute":                                                   # :301-329
+            query = self.query_encoder(self._get_query_feat(batch)) if query is None else query
+            item_vector = self._get_item_vector()
+            with torch.no_grad():
+                all_prob = torch.softmax(self.score_func(query.detach(), item_vector.detach()) / t, dim=-1)
+                all_prob = torch.nn.functional.pad(all_prob, pad=(1, 0))
+                sampling_prob = all_prob
+                num_pos = 1
+                if pos_items is not None:
+                    log_pos_prob = torch.log(torch.gather(all_prob, dim=-1, index=pos_items))
+                    num_pos = pos_items.size(-1)
+                if excluding_hist:
+                    sampling_prob = torch.scatter(all_prob, -1, user_hist, 0.0)   # mask_with_hist(prob, hist, 0), utils.py:474-499
+                neg_id = torch.multinomial(sampling_prob, num_neg[1] * num_pos, replacement=True)
+                log_neg_prob = torch.log(torch.gather(sampling_prob, dim=-1, index=neg_id))
+        else:                                                                     # 'sir' / 'dns'  :331-355
+            if pos_items is not None:
+                log_pos_prob, neg_id_pool, _, query = self._sample(batch, num_neg[0], excluding_hist, True)
+            else:
+                neg_id_pool, _, query = self._sample(batch, num_neg[0], excluding_hist, True)
+            scores_on_pool_items = self._pool_scores(query, neg_id_pool)
+            if method == "dns":
+                _, topk_id = torch.topk(scores_on_pool_items, num_neg[1])
+                neg_id = torch.gather(neg_id_pool, -1, topk_id)
+                log_neg_prob = torch.zeros_like(neg_id)
+                log_pos_prob = None if pos_items is None else torch.zeros_like(pos_items)
+            else:
+                if pos_items is not None:
+                    with torch.no_grad():
+                        log_pos_prob = self.score_func(query.detach(), self.item_encoder(self._get_item_feat(batch)))
+                probs_on_pool_items = torch.softmax(scores_on_pool_items + torch.finfo(torch.float32).eps, dim=-1)
+                resampled_id = torch.multinomial(probs_on_pool_items, num_neg[1], replacement=True)
+                neg_id = torch.gather(neg_id_pool, dim=-1, index=resampled_id)
+                log_neg_prob = torch.gather(scores_on_pool_items, dim=-1, index=resampled_id)
+
+        if pos_items is not None:
+            log_pos_prob = log_pos_prob.view_as(batch.get(self.fiid))
+            result = (log_pos_prob.detach(), neg_id, log_neg_prob.detach())
+        else:
+            result = (None, neg_id, log_neg_prob.detach())
+        return (result, query) if return_query else (result, None)
+
     def _fused_combo(self, batch):
         """(loss_kind, score_kind, two_tables) when the kernels implement this plugin combination, else None.
         two_tables: both towers are plain embedding tables (BPR-style); otherwise the query encoder is an
         arbitrary module (SASRec ...) and only the head is fused."""
         cfg = self.config["train"] if hasattr(self, "config") else {}
-        if cfg.get("sampling_method", "none") != "none" or cfg.get("excluding_hist", False):
+        method, excl = cfg.get("sampling_method", "none"), bool(cfg.get("excluding_hist", False))
+        if method not in _FUSABLE_METHODS:
             return None
-        if type(self.sampler) not in _FUSABLE_SAMPLERS:
-            return None
+        if method in ("none", "dns", "sir"):
+            if type(self.sampler) not in _FUSABLE_SAMPLERS:
+                return None
+            if excl != isinstance(self.sampler, FusedMaskedUniformSampler):
+                return None              # history exclusion is the masked sampler's job (and it needs user_hist)
+            if excl and batch.get("user_hist", None) is None:
+                return None
         lk, sk = _LOSS_KIND.get(type(self.loss_fn)), _SCORE_KIND.get(type(self.score_func))
         if lk is None or sk is None:
             return None
@@ -493,20 +641,42 @@ class FusedRetrieverMixin:
                 self.query_encoder.weight.register_post_accumulate_grad_hook(self._restore_coalesced)
             self.__dict__["_fused_hooks"] = True
         pos = batch[self.fiid].to(wi.device, non_blocking=True).contiguous()
-        B, n = pos.numel(), int(self.neg_count)
+        nc = self.neg_count
+        B, n = pos.numel(), int(nc[1] if isinstance(nc, (list, tuple)) else nc)
+        cfg = self.config["train"] if hasattr(self, "config") else {}
+        method, excl = cfg.get("sampling_method", "none"), bool(cfg.get("excluding_hist", False))
+        query = None
+        if method != "none":
+            # candidate selection (dns / sir / toprand / top&rand / brute) runs on the CUDA ops of sampling(); the
+            # selected ids and their proposal log-probabilities then take the same fused step as given negatives.
+            # sampling() also returns the query it encoded (with its autograd graph), as the reference's forward uses it.
+            dev_batch = {k: (v.to(wi.device, non_blocking=True) if isinstance(v, Tensor) else v) for k, v in batch.items()}
+            (lqp, neg32, lqn), query = self.sampling(dev_batch, nc, method, excl, return_query=True)
+            neg32 = neg32.reshape(B, -1).contiguous()
+            if neg32.shape[1] != n:
+                raise _lib.Rsb200Error("sampling() returned %d negatives per query, expected %d" % (neg32.shape[1], n))
+            lqp = lqp.reshape(B).float() if (lqp is not None and lqp.is_floating_point()) else None
+            lqn = lqn.reshape(B, n).float().contiguous() if lqn.is_floating_point() else None
         if two_tables:
             wu = self.query_encoder.weight
             user = batch[self.fuid].to(wi.device, non_blocking=True).contiguous()
             ws = self._fused_ws(B, n, wu.shape[0])
         else:
-            query = self.query_encoder(self._get_query_feat(batch))      # [B, d], keeps its own autograd graph
+            if query is None:
+                query = self.query_encoder(self._get_query_feat(batch))  # [B, d], keeps its own autograd graph
             if query.dim() != 2 or query.shape[0] != B:
+                if method != "none":
+                    raise _lib.Rsb200Error("fused sampling methods need a [B, d] query encoder output")
                 return super().training_step(batch)
             ws = self._fused_ws(B, n, B + 1)
-        neg32, lqn = self.sampler.fused_draw(B, n, wi.device)
-        lqp = self.sampler.compute_item_p(None, pos) if (lqn is not None and loss_kind == LOSS_SSM) else None
+        if method == "none":
+            if excl:
+                neg32, lqn = self.sampler.fused_draw(B, n, wi.device, user_hist=batch["user_hist"])
+            else:
+                neg32, lqn = self.sampler.fused_draw(B, n, wi.device)
+            lqp = self.sampler.compute_item_p(None, pos) if (lqn is not None and loss_kind == LOSS_SSM) else None
         if loss_kind != LOSS_SSM:
-            lqn = None
+            lqp = lqn = None
         if two_tables:
             return _FusedStepFn.apply(wi, wu, self, ws, user, pos, neg32, lqp, lqn, loss_kind, score_kind)
         return _FusedHeadFn.apply(wi, query, self, ws, pos, neg32, lqp, lqn, loss_kind, score_kind)

@@ -124,11 +124,12 @@ class MiniRetriever(torch.nn.Module):
         pos_prob, neg_id, neg_prob = self.sampler(**kwargs)
         return (pos_prob, neg_id, neg_prob, query) if return_query else (pos_prob, neg_id, neg_prob)
 
-    # --- baseretriever.py:248-369 (method 'none' only; the other methods are out of scope) ----------
+    # --- baseretriever.py:248-278,360-369: method 'none'; dns / sir / toprand / top&rand / brute are implemented
+    # on the CUDA ops by FusedRetrieverMixin.sampling, which sits in front of this class ------------
     def sampling(self, batch, num_neg, method="none", excluding_hist=False, t=1, return_query=False, query=None):
         if method != "none":
-            raise NotImplementedError("MiniRetriever mirrors sampling_method='none' only; "
-                                      "sir/dns/toprand/brute live in the reference's BaseRetriever")
+            raise NotImplementedError("MiniRetriever.sampling mirrors sampling_method='none' only; the other "
+                                      "methods are provided by FusedRetrieverMixin.sampling")
         assert self.sampler is not None, "excepted sampler of retriever to be Sampler, but get None."
         if isinstance(num_neg, int):
             num_neg = [num_neg, num_neg]
@@ -280,21 +281,25 @@ class FusedBPR(FusedRetriever):
     """The reference's BPR (recstudio/model/mf/bpr.py:7-25) on the fused path."""
 
 
-def build_synthetic(num_users: int, num_items: int, d: int, n: int, loss: str = "bpr", scorer: str = "ip",
+def build_synthetic(num_users: int, num_items: int, d: int, n, loss: str = "bpr", scorer: str = "ip",
                     sampler: str = "uniform", pop_count=None, fused_grad: str = "dense", device="cuda:0",
-                    init_std: Optional[float] = None, seed: int = 2022) -> FusedRetriever:
+                    init_std: Optional[float] = None, seed: int = 2022, sampling_method: str = "none",
+                    excluding_hist: bool = False) -> FusedRetriever:
     """A FusedRetriever over plain embedding towers without a dataset object (bench / tests):
     the kwargs construction of test/test_retriever.py with synthetic table sizes."""
     loss_m = plugins.FusedBPRLoss() if loss == "bpr" else plugins.FusedSampledSoftmaxLoss()
     score_m = plugins.FusedInnerProductScorer() if scorer == "ip" else plugins.FusedEuclideanScorer()
-    samp_m = plugins.FusedUniformSampler(num_items) if sampler == "uniform" else plugins.FusedPopularSampler(pop_count)
+    samp_m = {"uniform": lambda: plugins.FusedUniformSampler(num_items),
+              "masked": lambda: plugins.FusedMaskedUniformSampler(num_items),
+              "popular": lambda: plugins.FusedPopularSampler(pop_count)}[sampler]()
     item = plugins.FusedEmbedding(num_items, d, padding_idx=0)
     user = plugins.FusedEmbedding(num_users, d, padding_idx=0)
-    cfg = {"model": {"embed_dim": d}, "train": {"negative_count": n, "seed": seed}}
+    extra = {"sampling_method": sampling_method, "excluding_hist": excluding_hist}
+    cfg = {"model": {"embed_dim": d}, "train": {"negative_count": n, "seed": seed, **extra}}
     if iface.HAVE_RECSTUDIO:
         from recstudio.utils import get_model
         conf = get_model("BPR")[1]
-        conf["train"].update({"negative_count": n, "gpu": None, "seed": seed})
+        conf["train"].update({"negative_count": n, "gpu": None, "seed": seed, **extra})
         conf["model"]["embed_dim"] = d
         m = FusedRetriever(conf, fused_grad=fused_grad, item_encoder=item, query_encoder=user, scorer=score_m,
                            sampler=samp_m, loss=loss_m)

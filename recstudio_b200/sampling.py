@@ -50,6 +50,32 @@ def uniform_draw(num_items: int, num_queries: int, num_neg: int, device, want_i6
     return o64, o32
 
 
+def masked_uniform_draw(num_items: int, user_hist: torch.Tensor, per_user: int, want_i64: bool = True,
+                        want_i32: bool = False, generator: Optional[torch.Generator] = None):
+    """``uniform_sample_masked_hist`` (recstudio/ann/sampler.py:117-147) on the CUDA generator's stream:
+    ``per_user`` ids per history row, uniform over ``[1, num_items-1]`` minus the row's non-zero history.
+    ``num_items`` counts the padding row.  Returns (neg_i64 | None, neg_i32 | None) of shape [rows, per_user]."""
+    _lib.require_cuda()
+    if not user_hist.is_cuda or user_hist.dim() != 2 or user_hist.dtype != torch.int64:
+        raise _lib.Rsb200Error("user_hist must be a CUDA int64 [num_users, hist_len] tensor (no CPU fallback)")
+    device = user_hist.device
+    user_hist = user_hist.contiguous()
+    rows, hlen = user_hist.shape
+    gen = _generator(device, generator)
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    sm, mt = _policy(device)
+    o64 = torch.empty(rows, per_user, dtype=torch.int64, device=device) if want_i64 else None
+    o32 = torch.empty(rows, per_user, dtype=torch.int32, device=device) if want_i32 else None
+    adj = torch.empty(rows * hlen, dtype=torch.int64, device=device)
+    cnt = torch.empty(rows, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib().rsb200_sample_uniform_masked(seed, offset, int(num_items), ptr(user_hist), rows, hlen, int(per_user),
+                                                 sm, mt, ptr(adj), ptr(cnt), ptr(o64), ptr(o32), stream_ptr()),
+              "sample_uniform_masked")
+    gen.set_offset(offset + counter_offset(rows * per_user, device))
+    return o64, o32
+
+
 def build_guide(table: torch.Tensor, guide_bits: Optional[int] = None):
     """guide[k] = searchsorted(table, k / 2^bits): O(1)-expected replacement of the bisection."""
     n = table.numel()

@@ -274,10 +274,106 @@ def golden_full_softmax():
          d_item=m.item_encoder.weight.grad, d_user=m.query_encoder.weight.grad)
 
 
+def golden_masked_uniform():
+    """uniform_sample_masked_hist / MaskedUniformSampler (sampler.py:117-147,187-214): the torch.rand
+    seeds are recorded (CPU mt19937 here, Philox on CUDA) so the integer arithmetic after the
+    draw is pinned independently of the generator."""
+    out = {}
+    real_rand = torch.rand
+    rec = {}
+
+    def rand_spy(*a, **k):
+        rec["seeds"] = real_rand(*a, **k)
+        return rec["seeds"]
+
+    g = torch.Generator().manual_seed(21)
+    N = 400                                                     # Sampler.num_items (real items)
+    hist_a = torch.zeros(12, 9, dtype=torch.long)               # distinct items, right-padded
+    for b in range(12):
+        c = int(torch.randint(0, 10, (1,), generator=g))
+        hist_a[b, :c] = torch.randperm(N, generator=g)[:c] + 1
+    hist_b = hist_a.clone(); hist_b[:, 1] = hist_b[:, 0]        # duplicate items -> non-monotone adjusted row
+    hist_c = torch.flip(hist_a, dims=[1])                       # left-padded
+    hist_d = torch.stack([torch.randperm(30, generator=g)[:16] + 1 for _ in range(5)])   # full rows, tiny catalog
+    cases = (("a", N, hist_a, 7, None), ("b", N, hist_b, 7, None), ("c", N, hist_c, 4, 3), ("d", 30, hist_d, 40, None))
+    torch.rand = rand_spy
+    try:
+        for tag, n_items, hist, n, nq in cases:
+            torch.manual_seed(100 + len(tag) + n)
+            neg = rs_sampler.uniform_sample_masked_hist(n_items, n, hist, nq)
+            out[f"{tag}_num_items"] = n_items; out[f"{tag}_hist"] = hist; out[f"{tag}_seeds"] = rec["seeds"]
+            out[f"{tag}_neg"] = neg
+        smp = rs_sampler.MaskedUniformSampler(N + 1)
+        torch.manual_seed(9)
+        lp, neg, ln = smp(torch.zeros(12, 8), 5, pos_items=torch.arange(12), user_hist=hist_a)
+        out.update(s_seeds=rec["seeds"], s_neg=neg, s_log_pos=lp, s_log_neg=ln)
+    finally:
+        torch.rand = real_rand
+    save("masked_uniform", **out)
+
+
+def golden_sampling_methods():
+    """BaseRetriever.sampling methods dns / sir / toprand / top&rand / brute (baseretriever.py:248-369)
+    inside a full training_step + backward.  Every random draw is recorded (pool ids, multinomial /
+    randint outcomes) so the same step can be replayed on another device's generator."""
+    U, N, d, B = 23, 301, 32, 14
+    H = 6
+    for method, loss_cls, lname, nc in (("dns", rs_loss.BPRLoss, "bpr", [12, 4]), ("sir", rs_loss.SampledSoftmaxLoss, "ssm", [12, 5]),
+                                        ("toprand", rs_loss.BPRLoss, "bpr", [10, 4]), ("top&rand", rs_loss.BPRLoss, "bpr", 6),
+                                        ("brute", rs_loss.SampledSoftmaxLoss, "ssm", 5)):
+        m = build_retriever(U, N, d, nc, loss_cls(), rs_scorer.InnerProductScorer())
+        m.config["train"]["sampling_method"] = method
+        g = torch.Generator().manual_seed(31)
+        with torch.no_grad():
+            m.item_encoder.weight.copy_(torch.randn(N, d, generator=g) * 0.4)
+            m.query_encoder.weight.copy_(torch.randn(U, d, generator=g) * 0.4)
+            m.item_encoder.weight[0] = 0; m.query_encoder.weight[0] = 0
+        m._update_item_vector()
+        hist = torch.stack([torch.randperm(N - 1, generator=g)[:H] + 1 for _ in range(B)])
+        hist[:, -2:] = 0
+        batch = {"user_id": torch.randint(1, U, (B,), generator=g), "item_id": torch.randint(1, N, (B,), generator=g),
+                 "rating": torch.ones(B), "user_hist": hist}
+        rec = {}
+        real_fwd, real_mult, real_randint = m.sampler.forward, torch.multinomial, torch.randint
+
+        def fwd_spy(*a, **k):
+            r = real_fwd(*a, **k)
+            rec["pool"] = r[-2]
+            return r
+
+        def mult_spy(*a, **k):
+            rec["multinomial"] = real_mult(*a, **k)
+            return rec["multinomial"]
+
+        def randint_spy(*a, **k):
+            rec["randint"] = real_randint(*a, **k)
+            return rec["randint"]
+
+        m.sampler.forward = fwd_spy
+        torch.multinomial, torch.randint = mult_spy, randint_spy
+        try:
+            torch.manual_seed(55)
+            loss = m.training_step(batch)
+            loss.backward()
+            pool_train = {k: v.clone() for k, v in rec.items()}
+            torch.manual_seed(55)
+            o = m.forward(batch, return_neg_id=True, return_query=True)
+        finally:
+            m.sampler.forward = real_fwd
+            torch.multinomial, torch.randint = real_mult, real_randint
+        tag = method.replace("&", "and")
+        extra = {f"rec_{k}": v for k, v in pool_train.items()}
+        save(f"sampling_{tag}", w_item=m.item_encoder.weight, w_user=m.query_encoder.weight, user=batch["user_id"],
+             pos=batch["item_id"], hist=hist, neg=o["neg_id"], loss=loss, pos_score=o["score"]["pos_score"],
+             neg_score=o["score"]["neg_score"], log_pos_prob=o["score"]["log_pos_prob"],
+             log_neg_prob=o["score"]["log_neg_prob"], d_item=m.item_encoder.weight.grad,
+             d_user=m.query_encoder.weight.grad, negative_count=np.asarray(nc), **extra)
+
+
 if __name__ == "__main__":
-    golden_appendix_a()
-    golden_training_steps()
-    golden_popular()
-    golden_uniform_cpu()
-    golden_topk_eval()
-    golden_full_softmax()
+    ALL = [golden_appendix_a, golden_training_steps, golden_popular, golden_uniform_cpu, golden_topk_eval,
+           golden_full_softmax, golden_masked_uniform, golden_sampling_methods]
+    want = sys.argv[1:]                       # optional: names of the generators to (re)run
+    for fn in ALL:
+        if not want or fn.__name__ in want:
+            fn()

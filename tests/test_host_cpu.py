@@ -125,8 +125,10 @@ def test_mini_retriever_surface_and_asserts():
         retriever.FusedRetriever(None, sampler=object())
     with pytest.raises(AssertionError):
         retriever.FusedRetriever(None, loss=torch.nn.Identity())
-    with pytest.raises(NotImplementedError):
-        m.sampling({"user_id": torch.tensor([1]), "item_id": torch.tensor([1])}, 3, method="dns")
+    with pytest.raises(NotImplementedError):                      # the reference's message for an unknown method
+        m.sampling({"user_id": torch.tensor([1]), "item_id": torch.tensor([1])}, 3, method="is")
+    with pytest.raises(AssertionError):                           # baseretriever.py:266-270
+        m.sampling({"user_id": torch.tensor([1]), "item_id": torch.tensor([1])}, [2, 3], method="dns")
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="needs the read-only reference checkout")

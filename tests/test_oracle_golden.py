@@ -176,3 +176,59 @@ def test_full_softmax_step():
     assert out["loss"].item() == g["loss"].item()
     np.testing.assert_array_equal(out["d_item"].numpy(), g["d_item"])
     np.testing.assert_array_equal(out["d_user"].numpy(), g["d_user"])
+
+
+# ---------------------------------------------------------------- 8(f)-2: masked sampler + sampling methods
+def test_masked_uniform_matches_reference():
+    """uniform_sample_masked_hist / MaskedUniformSampler (sampler.py:117-147,187-214): the oracle reproduces
+    the reference's ids bit for bit from the recorded torch.rand seeds -- distinct, duplicate (non-monotone
+    adjusted row), left-padded and full histories, and the [B, n_q, n] multi-query shape."""
+    g = load_golden("masked_uniform")
+    for tag in "abcd":
+        want = g[f"{tag}_neg"]
+        got = S.masked_uniform_from_seeds(int(g[f"{tag}_num_items"]), g[f"{tag}_hist"], g[f"{tag}_seeds"])
+        np.testing.assert_array_equal(got.reshape(want.shape), want)
+        if tag in "acd":        # distinct histories: never a history item, always a real item
+            for b in range(want.shape[0]):
+                assert not set(want[b].ravel().tolist()) & set(g[f"{tag}_hist"][b][g[f"{tag}_hist"][b] > 0].tolist())
+            assert want.min() >= 1 and want.max() <= int(g[f"{tag}_num_items"])
+    got = S.masked_uniform_from_seeds(400, g["a_hist"], g["s_seeds"])
+    np.testing.assert_array_equal(got, g["s_neg"])
+    assert g["s_log_neg"].dtype == np.float32 and np.all(g["s_log_neg"] == 0) and g["s_log_pos"].dtype == np.float32
+
+
+@pytest.mark.parametrize("method", ["dns", "sir", "toprand", "topandrand", "brute"])
+def test_sampling_methods_match_reference(method):
+    """BaseRetriever.sampling methods (baseretriever.py:280-355) inside training_step: the oracle re-derives
+    the selected negatives / proposal log-probabilities from the recorded draws, and the step on those
+    negatives reproduces the reference's loss and dense gradients."""
+    g = load_golden("sampling_" + method)
+    wi, wu = torch.from_numpy(g["w_item"]), torch.from_numpy(g["w_user"])
+    user, pos, hist = (torch.from_numpy(g[k]) for k in ("user", "pos", "hist"))
+    query = wu[user]
+    nc = g["negative_count"].tolist()
+    n0, n1 = (nc, nc) if isinstance(nc, int) else nc
+    loss_kind = R.SSM if method in ("sir", "brute") else R.BPR
+    if method in ("dns", "sir"):
+        np.testing.assert_array_equal(g["rec_pool"], g["rec_randint"])       # the pool IS the sampler's randint draw
+        sel = R.select_from_pool(method, query, wi, g["rec_pool"], n1, R.IP, resampled_id=g.get("rec_multinomial"))
+        np.testing.assert_array_equal(sel["neg_id"].numpy(), g["neg"])
+        np.testing.assert_array_equal(sel["log_neg_prob"].numpy(), g["log_neg_prob"])
+        if method == "sir":
+            np.testing.assert_array_equal(g["log_pos_prob"], g["pos_score"])  # :335 proposal log-prob of the positive = its score
+    elif method == "toprand":
+        _, cand = T.topk_aten(query, wi[1:], n0, hist)
+        np.testing.assert_array_equal(torch.gather(cand, -1, torch.from_numpy(g["rec_randint"])).numpy(), g["neg"])
+    elif method == "topandrand":
+        _, cand = T.topk_aten(query, wi[1:], n1 // 2, hist)
+        np.testing.assert_array_equal(torch.cat([cand, torch.from_numpy(g["rec_randint"])], -1).numpy(), g["neg"])
+    else:                                                                     # brute: softmax over the catalog
+        prob = torch.nn.functional.pad(torch.softmax(R.score(R.IP, query, wi[1:]), -1), (1, 0))
+        np.testing.assert_array_equal(g["rec_multinomial"], g["neg"])
+        np.testing.assert_allclose(torch.log(torch.gather(prob, -1, torch.from_numpy(g["neg"]))).numpy(), g["log_neg_prob"], rtol=1e-6)
+        np.testing.assert_allclose(torch.log(torch.gather(prob, -1, pos.view(-1, 1))).view(-1).numpy(), g["log_pos_prob"], rtol=1e-6)
+    ref = R.training_step_aten(wi, wu, user, pos, torch.from_numpy(g["neg"]), loss=loss_kind, scorer=R.IP,
+                               log_pos_prob=torch.from_numpy(g["log_pos_prob"]), log_neg_prob=torch.from_numpy(g["log_neg_prob"]))
+    np.testing.assert_allclose(ref["loss"].item(), g["loss"].item(), rtol=1e-6)
+    np.testing.assert_allclose(ref["d_item"].numpy(), g["d_item"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(ref["d_user"].numpy(), g["d_user"], rtol=1e-5, atol=1e-9)
