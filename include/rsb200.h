@@ -309,6 +309,37 @@ int32_t rsb200_attn_bwd(const float* q, const float* k, const float* v, const fl
 int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D, int64_t N, int64_t K, uint32_t* err_flag, void* stream);
 
 /* -------------------------------------------------------------------------
+ * 8(f)-4  Index build of the model-based samplers (Sampler.update, once per epoch:
+ *         recstudio/model/basemodel/recommender.py:561-570)
+ *
+ * kmeans (recstudio/ann/sampler.py:9-36), one Lloyd iteration = assign + update:
+ *   assign[i] = argmin_k |x_i - c_k|^2 evaluated as |x|^2 - 2 x.c + |c|^2 (first minimum on ties), and
+ *   *loss_out = sum_i |x_i - c_assign(i)|^2 (double).  x is [num_points, d] with row stride ldx floats (a column
+ *   chunk of the item table: torch.chunk(item_embs, 2, -1), sampler.py:275); cnorm_ws: float [num_clusters].
+ *   update: sums_out[k,:] = sum of the points assigned to k, counts_out[k] = their number (as float, like
+ *   assign_m.sum(0)); the caller divides and re-seeds empty clusters (sampler.py:31-35).
+ *   Neither the [N,K] distance matrix nor the [N,K] one-hot matrix of the reference is materialised. */
+int32_t rsb200_kmeans_assign(const float* x, int64_t ldx, int64_t num_points, int64_t d, const float* centers /* [K,d] */,
+                             int64_t num_clusters, float* cnorm_ws, int64_t* assign_out, double* loss_out, void* stream);
+int32_t rsb200_kmeans_update(const float* x, int64_t ldx, int64_t num_points, int64_t d, const int64_t* assign,
+                             int64_t num_clusters, float* sums_out /* [K,d] */, float* counts_out /* [K] */, void* stream);
+/* construct_index (sampler.py:39-45): indices = argsort(codes, stable), indptr[c] = first position of bucket c
+ * (indptr has num_buckets + 1 entries).  codes in [0, num_buckets), num_buckets <= 65536. */
+size_t  rsb200_index_workspace_bytes(int64_t num_points, int64_t num_buckets);
+int32_t rsb200_index_build(const int64_t* codes, int64_t num_points, int64_t num_buckets, int64_t* indices_out,
+                           int64_t* indptr_out, void* workspace, size_t workspace_bytes, void* stream);
+/* per-bucket normalised cumulative weights (sampler.py:300-306,417-423): cp_out[e] = cumsum within the bucket of
+ * weight[indices[e]] divided by the bucket total; total_out[c] (or NULL) = bucket total (= an entry of wkk). */
+int32_t rsb200_segment_cdf(const float* weight /* [num_points] */, const int64_t* indices, const int64_t* indptr,
+                           int64_t num_buckets, float* cp_out /* [num_points] */, float* total_out /* [num_buckets] */, void* stream);
+/* _sample_item_with_pop (sampler.py:348-365) for num_draws (bucket, uniform seed) pairs: inverse-CDF search inside
+ * the bucket.  neg_out = indices[start + idx] and logp_out = log(p[start + idx + 1]) exactly as the reference indexes
+ * them; no [num_q, neg, max_bucket] tensor. */
+int32_t rsb200_segment_search(const int64_t* k01, const float* u, int64_t num_draws, const float* cp, const int64_t* indices,
+                              const int64_t* indptr, int64_t num_buckets, const float* p /* [num_points + 1] */,
+                              int64_t* neg_out, float* logp_out, void* stream);
+
+/* -------------------------------------------------------------------------
  * 8(e)  Row-sharded item table, owner-compute ("ship queries, not rows") training step.
  *   The same step as rsb200_pair_step (baseretriever.py:142-176,399-404 + loss.backward(),
  *   recommender.py:638) for a GLOBAL batch of G = world x B interactions, restricted to the rows ONE

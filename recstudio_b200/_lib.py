@@ -107,6 +107,8 @@ def lib():
         L.rsb200_topk_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64]
         L.rsb200_fullsoftmax_workspace_bytes.restype = C.c_size_t
         L.rsb200_fullsoftmax_workspace_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+        L.rsb200_index_workspace_bytes.restype = C.c_size_t
+        L.rsb200_index_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
         v, i64, i32, u64, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_float
         sigs = {
             "rsb200_device_info": [v, v, v, v],
@@ -116,6 +118,11 @@ def lib():
             "rsb200_popular_logq": [v, i64, v, i64, v, v],
             "rsb200_masked_workspace_elems": [i64, i64, v, v],
             "rsb200_sample_uniform_masked": [u64, u64, i64, v, i64, i64, i64, i32, i32, v, v, v, v, v],
+            "rsb200_kmeans_assign": [v, i64, i64, i64, v, i64, v, v, v, v],
+            "rsb200_kmeans_update": [v, i64, i64, i64, v, i64, v, v, v],
+            "rsb200_index_build": [v, i64, i64, v, v, v, C.c_size_t, v],
+            "rsb200_segment_cdf": [v, v, v, i64, v, v, v],
+            "rsb200_segment_search": [v, v, i64, v, v, v, i64, v, v, v, v],
             "rsb200_pair_workspace_sizes": [i64, i64, i64, i64, i64, C.POINTER(PairSizes)],
             "rsb200_pair_step": [C.POINTER(PairArgs), i32, v],
             "rsb200_shard_step": [C.POINTER(ShardArgs), i32, v],

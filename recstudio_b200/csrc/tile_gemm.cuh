@@ -43,15 +43,17 @@ __device__ __forceinline__ void mma_slab(float (&acc)[8][8], const float (*As)[L
 // As / Bs: shared staging [2][TK][LDS_].  All 256 threads must call; ends with a __syncthreads().
 __device__ __forceinline__ void gemm_nt(float (&acc)[8][8], const float* __restrict__ A, int rowsA, int m0,
                                         const float* __restrict__ B, int rowsB, int n0, int K,
-                                        float (*As)[TK][LDS_], float (*Bs)[TK][LDS_]) {
+                                        float (*As)[TK][LDS_], float (*Bs)[TK][LDS_], int lda = 0, int ldb = 0) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int lr = tid >> 2, lk = (tid & 3) * 4;
-    auto gload = [&](const float* base, int rows, int r, int k0) -> float4 {
-        if (r < rows && k0 + lk < K) return ldg128(base + (size_t)r * K + k0 + lk);
+    if (lda == 0) lda = K;                 // row strides (a column slice of a wider matrix has ld > K)
+    if (ldb == 0) ldb = K;
+    auto gload = [&](const float* base, int rows, int ld, int r, int k0) -> float4 {
+        if (r < rows && k0 + lk < K) return ldg128(base + (size_t)r * ld + k0 + lk);
         return make_float4(0, 0, 0, 0);
     };
-    float4 ra0 = gload(A, rowsA, m0 + lr, 0), ra1 = gload(A, rowsA, m0 + lr + 64, 0);
-    float4 rb0 = gload(B, rowsB, n0 + lr, 0), rb1 = gload(B, rowsB, n0 + lr + 64, 0);
+    float4 ra0 = gload(A, rowsA, lda, m0 + lr, 0), ra1 = gload(A, rowsA, lda, m0 + lr + 64, 0);
+    float4 rb0 = gload(B, rowsB, ldb, n0 + lr, 0), rb1 = gload(B, rowsB, ldb, n0 + lr + 64, 0);
     const int ksteps = (K + TK - 1) / TK;
     for (int ks = 0; ks < ksteps; ++ks) {
         const int buf = ks & 1;
@@ -62,8 +64,8 @@ __device__ __forceinline__ void gemm_nt(float (&acc)[8][8], const float* __restr
         __syncthreads();
         if (ks + 1 < ksteps) {
             const int k0 = (ks + 1) * TK;
-            ra0 = gload(A, rowsA, m0 + lr, k0); ra1 = gload(A, rowsA, m0 + lr + 64, k0);
-            rb0 = gload(B, rowsB, n0 + lr, k0); rb1 = gload(B, rowsB, n0 + lr + 64, k0);
+            ra0 = gload(A, rowsA, lda, m0 + lr, k0); ra1 = gload(A, rowsA, lda, m0 + lr + 64, k0);
+            rb0 = gload(B, rowsB, ldb, n0 + lr, k0); rb1 = gload(B, rowsB, ldb, n0 + lr + 64, k0);
         }
         mma_slab(acc, As[buf], Bs[buf], tx, ty);
     }

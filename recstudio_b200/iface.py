@@ -28,7 +28,7 @@ try:  # pragma: no cover - depends on the environment
     from recstudio.model.loss_func import FullScoreLoss, PairwiseLoss, PointwiseLoss
     from recstudio.model.loss_func import SampledSoftmaxLoss as RefSampledSoftmaxLoss
     from recstudio.model.loss_func import SoftmaxLoss as RefSoftmaxLoss
-    from recstudio.model.scorer import EuclideanScorer, InnerProductScorer
+    from recstudio.model.scorer import CosineScorer, EuclideanScorer, InnerProductScorer
     HAVE_RECSTUDIO = True
 except Exception:  # recstudio (or one of its hard deps: nni, torchmetrics) is absent
     class Sampler(torch.nn.Module):
@@ -71,6 +71,9 @@ except Exception:  # recstudio (or one of its hard deps: nni, torchmetrics) is a
 
     class EuclideanScorer(InnerProductScorer):
         """recstudio/model/scorer.py:28-34"""
+
+    class CosineScorer(InnerProductScorer):
+        """recstudio/model/scorer.py:19-25 (marker: the samplers only test isinstance to normalise their inputs)"""
 
     # marker types so that `type(x) in (...)` checks read the same in both environments
     class RefUniformSampler(Sampler):

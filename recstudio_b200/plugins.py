@@ -575,12 +575,10 @@ class FusedRetrieverMixin:
         if method not in _FUSABLE_METHODS:
             return None
         if method in ("none", "dns", "sir"):
-            if type(self.sampler) not in _FUSABLE_SAMPLERS:
+            if not isinstance(self.sampler, iface.Sampler):
                 return None
-            if excl != isinstance(self.sampler, FusedMaskedUniformSampler):
-                return None              # history exclusion is the masked sampler's job (and it needs user_hist)
-            if excl and batch.get("user_hist", None) is None:
-                return None
+            if isinstance(self.sampler, FusedMaskedUniformSampler) and (not excl or batch.get("user_hist", None) is None):
+                return None              # the masked sampler needs excluding_hist=True and the batch's user_hist
         lk, sk = _LOSS_KIND.get(type(self.loss_fn)), _SCORE_KIND.get(type(self.score_func))
         if lk is None or sk is None:
             return None
@@ -646,9 +644,11 @@ class FusedRetrieverMixin:
         cfg = self.config["train"] if hasattr(self, "config") else {}
         method, excl = cfg.get("sampling_method", "none"), bool(cfg.get("excluding_hist", False))
         query = None
-        if method != "none":
-            # candidate selection (dns / sir / toprand / top&rand / brute) runs on the CUDA ops of sampling(); the
-            # selected ids and their proposal log-probabilities then take the same fused step as given negatives.
+        in_kernel_draw = method == "none" and type(self.sampler) in _FUSABLE_SAMPLERS
+        if not in_kernel_draw:
+            # candidate selection (dns / sir / toprand / top&rand / brute) runs on the CUDA ops of sampling(), and any
+            # other Sampler (MIDX / Cluster / a reference sampler) draws through its own forward(); the selected ids
+            # and their proposal log-probabilities then take the same fused step as given negatives.
             # sampling() also returns the query it encoded (with its autograd graph), as the reference's forward uses it.
             dev_batch = {k: (v.to(wi.device, non_blocking=True) if isinstance(v, Tensor) else v) for k, v in batch.items()}
             (lqp, neg32, lqn), query = self.sampling(dev_batch, nc, method, excl, return_query=True)
@@ -665,12 +665,12 @@ class FusedRetrieverMixin:
             if query is None:
                 query = self.query_encoder(self._get_query_feat(batch))  # [B, d], keeps its own autograd graph
             if query.dim() != 2 or query.shape[0] != B:
-                if method != "none":
+                if not in_kernel_draw:
                     raise _lib.Rsb200Error("fused sampling methods need a [B, d] query encoder output")
                 return super().training_step(batch)
             ws = self._fused_ws(B, n, B + 1)
-        if method == "none":
-            if excl:
+        if in_kernel_draw:
+            if isinstance(self.sampler, FusedMaskedUniformSampler):
                 neg32, lqn = self.sampler.fused_draw(B, n, wi.device, user_hist=batch["user_hist"])
             else:
                 neg32, lqn = self.sampler.fused_draw(B, n, wi.device)

@@ -370,9 +370,76 @@ def golden_sampling_methods():
              d_user=m.query_encoder.weight.grad, negative_count=np.asarray(nc), **extra)
 
 
+def golden_midx():
+    """kmeans / construct_index / MIDX + Cluster samplers (sampler.py:9-45,261-559): index build (update) and the
+    deterministic parts of the draw (sample_item for recorded seeds, compute_item_p)."""
+    out = {}
+    g = torch.Generator().manual_seed(41)
+    # well separated blobs so that assignments do not sit on fp32 ties
+    cent = torch.randn(7, 16, generator=g) * 3
+    X = cent[torch.randint(0, 7, (600,), generator=g)] + torch.randn(600, 16, generator=g) * 0.5
+    for it in (1, 4, 50):
+        C, assign, assign_m, loss = rs_sampler.kmeans(X, X[:7].clone(), max_iter=it)
+        out[f"km_C_{it}"] = C; out[f"km_assign_{it}"] = assign; out[f"km_loss_{it}"] = loss
+    torch.manual_seed(3)
+    C, assign, _, loss = rs_sampler.kmeans(X, 5, max_iter=6)          # int K: centers = X[randperm(N)[:K]] on the CPU generator
+    out.update(km_X=X, km_Cr=C, km_assignr=assign, km_lossr=loss, km_next_rand=torch.rand(2))
+    codes = torch.randint(0, 37, (1000,), generator=g)
+    ind, ptr_ = rs_sampler.construct_index(codes, 37)
+    out.update(ci_codes=codes, ci_indices=ind, ci_indptr=ptr_)
+
+    N, d, K = 500, 16, 4
+    emb = cent[torch.randint(0, 7, (N,), generator=g)][:, :d] + torch.randn(N, d, generator=g) * 0.6
+    query = torch.randn(6, d, generator=g)
+    pos1 = torch.randint(1, N + 1, (6,), generator=g)
+    pos2 = torch.randint(0, N + 1, (6, 3), generator=g)
+    popc = torch.floor(torch.rand(N, generator=g) * 50)
+    real_rand_like = torch.rand_like
+    rec = {}
+
+    def spy(*a, **k):
+        rec["u"] = real_rand_like(*a, **k)
+        return rec["u"]
+
+    def dump(tag, smp, has_cp):
+        for name in ("c0", "c1", "cd0", "cd1", "c", "cd", "indices", "indptr", "wkk", "p", "cp"):
+            if hasattr(smp, name):
+                out[f"{tag}_{name}"] = getattr(smp, name)
+        k01 = torch.randint(0, smp.indptr.numel() - 1, (6, 9), generator=g)
+        sizes = smp.indptr[1:] - smp.indptr[:-1]
+        k01 = torch.where(sizes[k01] > 0, k01, torch.argmax(sizes).expand_as(k01))     # only non-empty buckets are ever drawn
+        p01 = torch.randn(6, 9, generator=g)
+        torch.rand_like = spy
+        try:
+            neg, prob = smp.sample_item(k01, p01)
+        finally:
+            torch.rand_like = real_rand_like
+        out.update({f"{tag}_k01": k01, f"{tag}_p01": p01, f"{tag}_u": rec["u"], f"{tag}_neg": neg, f"{tag}_negprob": prob})
+        out[f"{tag}_pos1_p"] = smp.compute_item_p(query, pos1) if not (has_cp and tag.startswith("cl")) else torch.zeros(1)
+        out[f"{tag}_pos2_p"] = smp.compute_item_p(query, pos2)
+
+    out.update(mx_emb=emb, mx_query=query, mx_pos1=pos1, mx_pos2=pos2, mx_pop=popc)
+    for tag, make, has_cp in (
+            ("mu_ip", lambda: rs_sampler.MIDXSamplerUniform(N + 1, K, rs_scorer.InnerProductScorer()), False),
+            ("mu_eu", lambda: rs_sampler.MIDXSamplerUniform(N + 1, K, rs_scorer.EuclideanScorer()), True),
+            ("mp_ip", lambda: rs_sampler.MIDXSamplerPop(popc, K, rs_scorer.InnerProductScorer(), mode=1), True),
+            ("cl_ip", lambda: rs_sampler.ClusterSamplerUniform(N + 1, K * 2, rs_scorer.InnerProductScorer()), False),
+            ("cp_ip", lambda: rs_sampler.ClusterSamplerPop(popc, K * 2, rs_scorer.InnerProductScorer(), mode=2), True)):
+        smp = make()
+        torch.manual_seed(17)
+        smp.update(emb, max_iter=8)
+        dump(tag, smp, has_cp)
+        if tag == "mu_ip":                    # a second update starts k-means from the previous centers (sampler.py:276-279)
+            emb2 = emb + 0.05 * torch.randn(N, d, generator=g)
+            smp.update(emb2, max_iter=3)
+            out.update(mu_ip2_emb=emb2, mu_ip2_c0=smp.c0, mu_ip2_c1=smp.c1, mu_ip2_indices=smp.indices, mu_ip2_wkk=smp.wkk)
+    save("midx", **out)
+
+
 if __name__ == "__main__":
     ALL = [golden_appendix_a, golden_training_steps, golden_popular, golden_uniform_cpu, golden_topk_eval,
-           golden_full_softmax, golden_masked_uniform, golden_sampling_methods]
+           golden_full_softmax, golden_masked_uniform, golden_sampling_methods,
+           golden_midx]
     want = sys.argv[1:]                       # optional: names of the generators to (re)run
     for fn in ALL:
         if not want or fn.__name__ in want:

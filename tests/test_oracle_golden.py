@@ -232,3 +232,54 @@ def test_sampling_methods_match_reference(method):
     np.testing.assert_allclose(ref["loss"].item(), g["loss"].item(), rtol=1e-6)
     np.testing.assert_allclose(ref["d_item"].numpy(), g["d_item"], rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(ref["d_user"].numpy(), g["d_user"], rtol=1e-5, atol=1e-9)
+
+
+# ---------------------------------------------------------------- 8(f)-4: kmeans / construct_index / MIDX samplers
+def test_midx_oracle_matches_reference():
+    from oracle import midx as M
+    g = load_golden("midx")
+    X = torch.from_numpy(g["km_X"])
+    for it in (1, 4, 50):
+        C, assign, loss, _ = M.kmeans(X, X[:7].clone(), max_iter=it)
+        np.testing.assert_array_equal(assign.numpy(), g[f"km_assign_{it}"])
+        np.testing.assert_allclose(C.numpy(), g[f"km_C_{it}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(loss, g[f"km_loss_{it}"].item(), rtol=1e-6)
+    torch.manual_seed(3)                                     # int K: randperm on the CPU generator, same stream afterwards
+    C, assign, loss, _ = M.kmeans(X, 5, max_iter=6)
+    np.testing.assert_array_equal(assign.numpy(), g["km_assignr"])
+    np.testing.assert_allclose(C.numpy(), g["km_Cr"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(torch.rand(2).numpy(), g["km_next_rand"])
+    ind, ptr_ = M.construct_index(g["ci_codes"], 37)
+    np.testing.assert_array_equal(ind, g["ci_indices"]); np.testing.assert_array_equal(ptr_, g["ci_indptr"])
+
+    emb, query = torch.from_numpy(g["mx_emb"]), torch.from_numpy(g["mx_query"])
+    pos1, pos2 = torch.from_numpy(g["mx_pos1"]), torch.from_numpy(g["mx_pos2"])
+    K = 4
+    norms = {"mu_ip": None, "mu_eu": torch.exp(-0.5 * torch.sum(emb ** 2, -1)).numpy(),
+             "mp_ip": (torch.log(torch.from_numpy(g["mx_pop"]) + 1) + 1e-6).numpy()}
+    for tag, norm in norms.items():
+        torch.manual_seed(17)
+        b = M.midx_build(emb, K, None, None, 8, norm)
+        for name in ("cd0", "cd1"):
+            np.testing.assert_array_equal(b[name].numpy(), g[f"{tag}_{name}"])
+        np.testing.assert_array_equal(b["indices"], g[f"{tag}_indices"]); np.testing.assert_array_equal(b["indptr"], g[f"{tag}_indptr"])
+        np.testing.assert_allclose(b["c0"].numpy(), g[f"{tag}_c0"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(b["wkk"], g[f"{tag}_wkk"], rtol=1e-5)
+        if norm is None:
+            neg, prob = M.sample_item_uniform(g[f"{tag}_k01"], g[f"{tag}_p01"], g[f"{tag}_u"], b["indices"], b["indptr"])
+        else:
+            np.testing.assert_allclose(b["cp"], g[f"{tag}_cp"], rtol=1e-5)
+            np.testing.assert_allclose(b["p"], g[f"{tag}_p"], rtol=1e-6)
+            neg, prob = M.sample_item_with_pop(g[f"{tag}_k01"], g[f"{tag}_p01"], g[f"{tag}_u"], g[f"{tag}_cp"], b["indices"],
+                                               b["indptr"], g[f"{tag}_p"])
+        np.testing.assert_array_equal(neg, g[f"{tag}_neg"])
+        np.testing.assert_allclose(prob, g[f"{tag}_negprob"], rtol=1e-5, atol=1e-6)
+        for pos, key in ((pos1, "pos1_p"), (pos2, "pos2_p")):
+            got = M.midx_item_p(query, pos, b["c0"], b["c1"], b["cd0"], b["cd1"], b.get("p"))
+            np.testing.assert_allclose(got.numpy(), g[f"{tag}_{key}"], rtol=1e-5, atol=1e-6)
+    # second update warm-starts from the previous centers
+    torch.manual_seed(17)
+    b = M.midx_build(emb, K, None, None, 8, None)
+    b2 = M.midx_build(torch.from_numpy(g["mu_ip2_emb"]), K, b["c0"], b["c1"], 3, None)
+    np.testing.assert_array_equal(b2["indices"], g["mu_ip2_indices"])
+    np.testing.assert_allclose(b2["wkk"], g["mu_ip2_wkk"])
