@@ -271,7 +271,7 @@ def run_b200(args):
 
 
 def run_sharded(args):
-    """BASELINE configs[4] (100M x 128 rows, BPR, uniform sampler) on the row-sharded table, owner-compute path."""
+    """BASELINE configs[4] (100M x 128 rows, BPR, popularity | uniform sampler) on the row-sharded table, owner-compute path."""
     import torch
     import torch.distributed as dist
     from recstudio_b200 import _lib, build, sampling, sharded
@@ -294,13 +294,29 @@ def run_sharded(args):
     users = torch.randint(1, N_USERS, (K + W, BATCH), device=dev, generator=gen)
     poss = torch.randint(1, N5, (K + W, BATCH), device=dev, generator=gen)
     L = _lib.lib()
+    torch.manual_seed(2022 + rank)                       # sampler seed 2022 + rank
+    if args.c5_sampler == "popular":
+        # configs[4] names the PopularitySampler: Zipf(1.05) interaction counts, PopularSamplerModel mode 0
+        # (log(count + 1)), tables built once by the same torch ops as the reference constructor (sampler.py:225-241)
+        import numpy as np
+        from recstudio_b200 import plugins
+        counts = np.floor(np.random.RandomState(0).zipf(1.05, size=N5)).clip(max=1e9)
+        counts[0] = 0
+        pop = plugins.FusedPopularSampler(counts, mode=0).to(dev)
+        del counts
+
+        def draw():
+            return pop.fused_draw(BATCH, NEG, dev)[0]
+    else:
+        def draw():
+            return sampling.uniform_draw(N5, BATCH, NEG, dev, want_i64=False, want_i32=True)[1]
 
     def barrier():
         dist.barrier(); torch.cuda.synchronize()
 
     def step(u, p_, ev=None):
         """one pass of the hot path over one batch; ev brackets the owner-compute forward kernel"""
-        _, neg = sampling.uniform_draw(N5, BATCH, NEG, dev, want_i64=False, want_i32=True)
+        neg = draw()
         q = sharded.CudaOps.gather_rows(wu, u)
         q_all, pos_all, neg_all = (sharded._all_gather_cat(t) for t in (q, p_, neg))
         eng.bind(q_all, pos_all, neg_all, _lib.LOSS_BPR, _lib.SCORE_IP)
@@ -357,9 +373,11 @@ def run_sharded(args):
         line = {"metric": "interactions/sec (BPR 100M x d128 row-sharded gather-score-loss-scatter)", "value": G * K / (total_ms / 1e3),
                 "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[4]: BPR + InnerProduct + in-kernel UniformSampler, items 100,000,001 x 128 "
+                "config": {"workload": "BASELINE configs[4]: BPR + InnerProduct + %s, items 100,000,001 x 128 "
                                        "row-sharded over %d GPU(s) (%d rows each), users 1,000,001 x 128 replicated, B=8192 per rank, "
-                                       "n=1024, owner-compute step (queries shipped, rows never move)" % (world, items.per_rank),
+                                       "n=1024, owner-compute step (queries shipped, rows never move)"
+                                       % ("PopularSampler (Zipf(1.05) counts, mode 0)" if args.c5_sampler == "popular"
+                                          else "in-kernel UniformSampler", world, items.per_rank),
                            "global_batch": G, "parallelism": "row-sharded x%d" % world,
                            "l2": "inputs (%.1f GB table block, random rows) exceed the 126 MB L2; no flush needed" % (items.local_rows * DIM * 4 / 1e9)},
                 "e2e": {"value": G * K / (e2e_ms / 1e3), "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -381,6 +399,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development only)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores)")
+    ap.add_argument("--c5-sampler", default="popular", choices=["popular", "uniform"],
+                    help="negative sampler of the c5-sharded workload (configs[4] names the PopularitySampler)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5-sharded"],
                     help="c2 = BASELINE configs[1] (default, the metric's config); c5-sharded = configs[4] on the row-sharded table")
     args = ap.parse_args()

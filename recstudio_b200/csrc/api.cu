@@ -134,6 +134,10 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         if (rc) return rc;
         rc = launch_scan(a->off_user, a->num_users, a->urow_user, a->cap_user, a->totals + 2, a->scan_tmp, a->scan_tmp_elems, st);
         if (rc) return rc;
+        if (a->variant != 6) {       // slot -> absolute entry position while the offsets are L2-resident (variant 6: legacy lookup in FWD)
+            rc = launch_resolve(neg32, a->slot_neg, a->off_item, B * n, st);
+            if (rc) return rc;
+        }
     }
     if (phases & RSB200_PHASE_FWD) {
         FwdParams p;
@@ -148,7 +152,9 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         const double denom = (a->loss_kind == RSB200_LOSS_BPR) ? (double)B * (double)(n > 0 ? n : 1) : (double)B;
         p.loss_scale = (float)(1.0 / (denom > 0 ? denom : 1.0));
         p.prefetch = (a->variant == 3) ? 1 : 0;
+        p.slot_abs = (a->variant != 6) ? 1 : 0;
         p.hint = (a->variant >= 16 && a->variant < 32) ? (a->variant & 7) : 0;   // variants 16..31: L2 eviction hints
+        if (a->variant == 32) p.hint = 8;    // timing diagnostic: skip the offset lookups / entry writes (gradients invalid)
         p.ncount = nullptr; p.sp_in = nullptr; p.stats_part = nullptr;
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);

@@ -15,21 +15,65 @@
 
 namespace rsb {
 
+// Every thread owns kCountPer elements a grid-stride apart (coalesced) and issues their atomics back to back, so four
+// returning atomics (~1 us each) are in flight per thread instead of one: the kernel is latency-, not throughput-bound.
+constexpr int kCountPer = 4;
+
 template <typename IdT>
 __global__ void __launch_bounds__(256)
 count_kernel(const IdT* __restrict__ ids, int64_t M, int64_t num_rows, uint32_t* __restrict__ cnt,
              uint32_t* __restrict__ slot, int32_t* __restrict__ ids32_out, uint32_t* __restrict__ err_flag) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    int64_t id = (int64_t)ids[i];
-    uint32_t s = kNoSlot;
-    if (id > 0 && id < num_rows) {
-        s = atomicAdd(cnt + id, 1u);
-    } else if (id != 0) {
-        *err_flag = 1u;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t id[kCountPer];
+    uint32_t s[kCountPer];
+#pragma unroll
+    for (int k = 0; k < kCountPer; ++k) {
+        const int64_t i = i0 + k * stride;
+        id[k] = i < M ? (int64_t)ids[i] : 0;
     }
-    slot[i] = s;
-    if (ids32_out) ids32_out[i] = (id >= 0 && id < num_rows) ? (int32_t)id : 0;   // i64 -> i32 copy for pair_fwd
+#pragma unroll
+    for (int k = 0; k < kCountPer; ++k) {
+        s[k] = kNoSlot;
+        if (id[k] > 0 && id[k] < num_rows) s[k] = atomicAdd(cnt + id[k], 1u);
+        else if (id[k] != 0) *err_flag = 1u;
+    }
+#pragma unroll
+    for (int k = 0; k < kCountPer; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < M) {
+            slot[i] = s[k];
+            if (ids32_out) ids32_out[i] = (id[k] >= 0 && id[k] < num_rows) ? (int32_t)id[k] : 0;   // i64 -> i32 copy for pair_fwd
+        }
+    }
+}
+
+// slot[i] (position inside the row's segment) -> absolute entry position off[id] + slot.  Runs right after the scan,
+// while the freshly written offsets are still L2-resident, so that the forward kernel -- whose 4 GB row stream
+// evicts them -- does not have to look them up with one random DRAM sector read per touch.
+__global__ void __launch_bounds__(256)
+resolve_kernel(const int32_t* __restrict__ ids, uint32_t* __restrict__ slot, const uint32_t* __restrict__ off, int64_t M) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s[kCountPer], o[kCountPer];
+#pragma unroll
+    for (int k = 0; k < kCountPer; ++k) {
+        const int64_t i = i0 + k * stride;
+        s[k] = i < M ? slot[i] : kNoSlot;
+        o[k] = (s[k] != kNoSlot) ? __ldg(off + ids[i]) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kCountPer; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (s[k] != kNoSlot) slot[i] = o[k] + s[k];
+    }
+}
+
+int32_t launch_resolve(const int32_t* ids, uint32_t* slot, const uint32_t* off, int64_t M, cudaStream_t st) {
+    if (M == 0) return 0;
+    resolve_kernel<<<(unsigned)cdiv(M, 256 * kCountPer), 256, 0, st>>>(ids, slot, off, M);
+    RSB_LAUNCH_CHECK();
+    return 0;
 }
 
 // ---------------------------------------------------------------------------- scan
@@ -156,7 +200,7 @@ template <typename IdT>
 int32_t launch_count(const IdT* ids, int64_t M, int64_t num_rows, uint32_t* cnt, uint32_t* slot,
                      int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st) {
     if (M == 0) return 0;
-    count_kernel<IdT><<<(unsigned)cdiv(M, 256), 256, 0, st>>>(ids, M, num_rows, cnt, slot, ids32_out, err_flag);
+    count_kernel<IdT><<<(unsigned)cdiv(M, 256 * kCountPer), 256, 0, st>>>(ids, M, num_rows, cnt, slot, ids32_out, err_flag);
     RSB_LAUNCH_CHECK();
     return 0;
 }

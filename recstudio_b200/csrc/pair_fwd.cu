@@ -279,9 +279,10 @@ __device__ __forceinline__ void finish_query(const FwdParams& p, WarpState<VPL>&
 // leaves its partial state (raw accumulator + {csum, loss} | {m, l}) for shard_finish_kernel.
 //
 // MODE: 0 = load-then-reduce loop; 1 = software-pipelined stream (PIPE); 2 = mode 0 with L2 eviction-priority
-// hints (HINT): table rows evict_first, CSR offsets / entry list evict_last (p.hint selects which).
+// hints (HINT): table rows evict_first, CSR offsets / entry list evict_last (p.hint selects which); 3 = mode 0
+// compiled for 4 CTAs/SM (64 registers, 32 warps/SM instead of 24).
 template <int VPL, int LOSS, int SCORE, bool MULTI, int MODE, bool PARTIAL = false>
-__global__ void __launch_bounds__(kThreads, (VPL == 1 && MODE != 1) ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, (VPL == 1 && MODE == 3) ? 4 : ((VPL == 1 && MODE != 1) ? 3 : 2))
 pair_fwd_kernel(const FwdParams p) {
     constexpr bool PIPE = MODE == 1, HINT = MODE == 2;
     static_assert(!PARTIAL || (!MULTI && !PIPE), "the owner-compute step runs one query per warp");
@@ -374,8 +375,10 @@ pair_fwd_kernel(const FwdParams p) {
     for (int jb = j0; jb < j1; jb += 32) {
         const bool valid = (jb + lane) < j1;
         uint32_t epos = 0;
+        if (HINT && (p.hint & 8)) cur.slot = kNoSlot;        // variant 32 (timing diagnostic only): no grouping metadata
         if (cur.slot != kNoSlot)                                                  // consumed after the groups
-            epos = (HINT ? ldg32_hint(p.off_item + cur.id, pol_off) : __ldg(p.off_item + cur.id)) + cur.slot;
+            epos = p.slot_abs ? cur.slot
+                              : (HINT ? ldg32_hint(p.off_item + cur.id, pol_off) : __ldg(p.off_item + cur.id)) + cur.slot;
         st.val_out = 0.f; st.sc_out = 0.f;
 
         if (PIPE) {
@@ -559,7 +562,7 @@ pair_fwd_tma_kernel(const FwdParams p) {
     st.csum = 0.f; st.lossacc = 0.f; st.m_run = -INFINITY; st.l_run = 0.f;
     st.val_out = 0.f; st.sc_out = 0.f;
     uint32_t epos = 0;
-    if (cur.slot != kNoSlot) epos = __ldg(p.off_item + cur.id) + cur.slot;
+    if (cur.slot != kNoSlot) epos = p.slot_abs ? cur.slot : __ldg(p.off_item + cur.id) + cur.slot;
 
     int batch = 0;
     for (int gi = 0; gi < total_groups; ++gi) {
@@ -585,7 +588,7 @@ pair_fwd_tma_kernel(const FwdParams p) {
             const int jn = j0 + (batch + 2) * 32;
             if (jn < j1) nn = load_meta<LOSS>(p, rowbase, jn, j1, lane);
             epos = 0;
-            if (cur.slot != kNoSlot) epos = __ldg(p.off_item + cur.id) + cur.slot;
+            if (cur.slot != kNoSlot) epos = p.slot_abs ? cur.slot : __ldg(p.off_item + cur.id) + cur.slot;
             st.val_out = 0.f; st.sc_out = 0.f;
         }
     }
@@ -652,7 +655,8 @@ int32_t launch_pair_fwd(const FwdParams& p, int loss, int score, int variant, cu
     const bool pipe = variant == 1;
     if (variant == 2 && p.D <= 128) return launch_fwd_tma(p, loss, score, st);   // TMA (cp.async.bulk) ring
     if (p.D <= 128) {
-        if (p.hint) return launch_fwd_v<1, 2>(p, loss, score, st);               // variants 4..7: L2 eviction hints
+        if (p.hint) return launch_fwd_v<1, 2>(p, loss, score, st);               // variants 16..31: L2 eviction hints
+        if (variant == 4) return launch_fwd_v<1, 3>(p, loss, score, st);         // 4 CTAs/SM
         return pipe ? launch_fwd_v<1, 1>(p, loss, score, st) : launch_fwd_v<1, 0>(p, loss, score, st);
     }
     if (p.D <= 256) return launch_fwd_v<2, 0>(p, loss, score, st);
