@@ -170,6 +170,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         s.ssm_scale = (float)((double)a->grad_scale / (double)(B > 0 ? B : 1));
         s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = a->score_kind == RSB200_SCORE_EUCLID;
         s.hint = (a->variant >= 16 && a->variant < 32) ? ((a->variant >> 3) & 1) : 0;
+        if (a->variant >= 40 && a->variant <= 44) s.hint = a->variant - 38;   // scatter occupancy / unroll experiments
         rc = launch_scatter(s, a->cap_item, st);
         if (rc) return rc;
         ScatterParams u = s;

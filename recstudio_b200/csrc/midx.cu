@@ -10,8 +10,9 @@
 //
 // The reference materialises the [N,K] distance matrix, the [N,K] one-hot assignment matrix (a GEMM against
 // it produces the centroid sums and wkk) and, per draw, a [num_q, neg, max_cluster_size] gather.  Here:
-//   * kmeans_assign: fp32 FFMA tile GEMM (128 points x 128 centroids per CTA) with the argmin and the exact
-//     sum of squared residuals in the epilogue -- no [N,K] matrix;
+//   * kmeans_assign: argmin and the exact sum of squared residuals in the epilogue of the distance contraction -- no
+//     [N,K] matrix.  Small codebooks (the MIDX case, D <= 64): one thread per point, centroids broadcast from shared
+//     memory; otherwise an fp32 FFMA tile GEMM (128 points x 128 centroids per CTA);
 //   * kmeans_update: per-CTA shared-memory centroid accumulators (shared atomics), one global flush per CTA;
 //   * index build: stable LSD radix sort by 8-bit digits (warp match_any ranks, no atomics on the order)
 //     -> identical to torch.sort(stable=True);
@@ -118,30 +119,119 @@ kmeans_assign_kernel(const float* __restrict__ x, int ldx, int N, int D, const f
     }
 }
 
+// Small-codebook form (D in {16, 32, 64}, K * D floats in shared memory): the MIDX case, where each codebook sees one
+// HALF of the item vector (d = 128 -> D = 64) and K is a few dozen.  One thread per point: the point's D values live in
+// registers, the centroids are read from shared memory with broadcast 16-byte loads (4 FMAs per load, 4 centroids
+// interleaved), so the kernel runs on the FMA pipe instead of paying a 128 x 128 tile's prologue / epilogue per 4 k-steps.
+template <int DV>     // DV = D / 4
+__global__ void __launch_bounds__(128)
+kmeans_assign_small_kernel(const float* __restrict__ x, int ldx, int N, const float* __restrict__ c, int K,
+                           const float* __restrict__ cn, int64_t* __restrict__ assign, double* __restrict__ loss) {
+    constexpr int D = DV * 4, XS = D + 4;            // padded row stride of the staged point tile (16-byte aligned rows)
+    extern __shared__ __align__(16) float sm[];
+    float* s_c = sm;                                  // [K][D]
+    float* s_x = sm + (size_t)K * D;                  // [128][XS]
+    __shared__ double s_red[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.x * 128;
+    for (int i = tid * 4; i < K * D; i += 128 * 4) *reinterpret_cast<float4*>(s_c + i) = ldg128(c + i);
+    // coalesced staging of the tile: consecutive threads read consecutive 16-byte pieces of a row
+    for (int i = tid; i < 128 * DV; i += 128) {
+        const int r = i / DV, v = i - r * DV;
+        float4 val = make_float4(0, 0, 0, 0);
+        if (m0 + r < N) val = ldg128_stream(x + (size_t)(m0 + r) * ldx + v * 4);
+        *reinterpret_cast<float4*>(s_x + (size_t)r * XS + v * 4) = val;
+    }
+    __syncthreads();
+    float4 xv[DV];
+    float xn = 0.f;
+#pragma unroll
+    for (int v = 0; v < DV; ++v) {
+        xv[v] = *reinterpret_cast<const float4*>(s_x + (size_t)tid * XS + v * 4);
+        xn = fmaf(xv[v].x, xv[v].x, xn); xn = fmaf(xv[v].y, xv[v].y, xn);
+        xn = fmaf(xv[v].z, xv[v].z, xn); xn = fmaf(xv[v].w, xv[v].w, xn);
+    }
+    float bestv = INFINITY; int besti = 0;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int v = 0; v < DV; ++v) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = min(k0 + u, K - 1);
+                const float4 cv = *reinterpret_cast<const float4*>(s_c + (size_t)k * D + v * 4);
+                dot[u] = fmaf(xv[v].x, cv.x, dot[u]); dot[u] = fmaf(xv[v].y, cv.y, dot[u]);
+                dot[u] = fmaf(xv[v].z, cv.z, dot[u]); dot[u] = fmaf(xv[v].w, cv.w, dot[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (k0 + u < K) {
+                const float dist = (xn - 2.f * dot[u]) + __ldg(cn + k0 + u);
+                if (dist < bestv) { bestv = dist; besti = k0 + u; }
+            }
+        }
+    }
+    double part = 0.0;
+    if (m0 + tid < N) {
+        assign[m0 + tid] = besti;
+        float a = 0.f;
+#pragma unroll
+        for (int v = 0; v < DV; ++v) {
+            const float4 cv = *reinterpret_cast<const float4*>(s_c + (size_t)besti * D + v * 4);
+            const float dx = xv[v].x - cv.x, dy = xv[v].y - cv.y, dz = xv[v].z - cv.z, dw = xv[v].w - cv.w;
+            a = fmaf(dx, dx, a); a = fmaf(dy, dy, a); a = fmaf(dz, dz, a); a = fmaf(dw, dw, a);
+        }
+        part = (double)a;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    if (tid == 0) atomicAdd(loss, s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+}
+
 // sums[k, :] += x_i for assign[i] == k, counts[k] += 1  (the reference's assign_m.T @ X and assign_m.sum(0),
 // sampler.py:30-31); per-CTA accumulators in shared memory, one flush per CTA.
+// One accumulator set per CTA in shared memory (shared fp32 atomics; two warps rarely meet on the same (cluster, column)),
+// kept small so that several CTAs fit an SM, and kUpdRows independent row loads in flight per warp: the kernel streams
+// the points once and is bound by DRAM latency x bytes in flight, not by the atomics.
+constexpr int kUpdRows = 8;
+
 __global__ void __launch_bounds__(256)
 kmeans_update_kernel(const float* __restrict__ x, int ldx, int N, int D, const int64_t* __restrict__ assign, int K,
                      float* __restrict__ sums, float* __restrict__ counts) {
-    extern __shared__ float sh[];                   // [K*D] sums, then [K] counts
+    extern __shared__ float sh[];                   // [K*D] sums, [K] counts
     float* s_sum = sh;
     float* s_cnt = sh + (size_t)K * D;
     for (int i = threadIdx.x; i < K * D + K; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < N; row += gridDim.x * wpb) {
-        int64_t a = assign[row];
-        if (a < 0 || a >= K) continue;
-        const float* xr = x + (size_t)row * ldx;
-        for (int j = lane; j < D; j += 32) atomicAdd(&s_sum[(size_t)a * D + j], xr[j]);
-        if (lane == 0) atomicAdd(&s_cnt[a], 1.0f);
+    for (int row0 = (blockIdx.x * wpb + warp) * kUpdRows; row0 < N; row0 += gridDim.x * wpb * kUpdRows) {
+        int a[kUpdRows];
+#pragma unroll
+        for (int r = 0; r < kUpdRows; ++r) {
+            const int64_t v = (row0 + r < N) ? assign[row0 + r] : -1;
+            a[r] = (v >= 0 && v < K) ? (int)v : -1;
+        }
+        for (int j = lane; j < D; j += 32) {
+            float v[kUpdRows];
+#pragma unroll
+            for (int r = 0; r < kUpdRows; ++r) v[r] = (a[r] >= 0) ? x[(size_t)(row0 + r) * ldx + j] : 0.f;
+#pragma unroll
+            for (int r = 0; r < kUpdRows; ++r)
+                if (a[r] >= 0) atomicAdd(&s_sum[(size_t)a[r] * D + j], v[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kUpdRows; ++r)
+            if (lane == r && a[r] >= 0) atomicAdd(&s_cnt[a[r]], 1.0f);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < K * D; i += blockDim.x)
-        if (s_sum[i] != 0.f) atomicAdd(&sums[i], s_sum[i]);
-    for (int i = threadIdx.x; i < K; i += blockDim.x)
-        if (s_cnt[i] != 0.f) atomicAdd(&counts[i], s_cnt[i]);
+    for (int i = threadIdx.x; i < K * D + K; i += blockDim.x) {
+        const float t = sh[i];
+        if (t != 0.f) atomicAdd(i < K * D ? &sums[i] : &counts[i - K * D], t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ construct_index
@@ -324,6 +414,21 @@ extern "C" int32_t rsb200_kmeans_assign(const float* x, int64_t ldx, int64_t num
     RSB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(double), st));
     row_sqnorm_kernel<<<(unsigned)cdiv(num_clusters, 8), 256, 0, st>>>(centers, (int)num_clusters, (int)d, cnorm_ws);
     RSB_LAUNCH_CHECK();
+    const size_t small_smem = (size_t)(num_clusters * d + 128 * (d + 4)) * sizeof(float);
+    if ((d == 16 || d == 32 || d == 64) && small_smem <= 96 * 1024) {
+        const unsigned grid = (unsigned)cdiv(num_points, 128);
+#define RSB_SMALL(DV)                                                                                                       \
+        do {                                                                                                                \
+            RSB_CUDA(cudaFuncSetAttribute(kmeans_assign_small_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                          (int)small_smem));                                                                \
+            kmeans_assign_small_kernel<DV><<<grid, 128, small_smem, st>>>(x, (int)ldx, (int)num_points, centers,           \
+                                                                         (int)num_clusters, cnorm_ws, assign_out, loss_out); \
+        } while (0)
+        if (d == 16) RSB_SMALL(4); else if (d == 32) RSB_SMALL(8); else RSB_SMALL(16);
+#undef RSB_SMALL
+        RSB_LAUNCH_CHECK();
+        return 0;
+    }
     kmeans_assign_kernel<<<(unsigned)cdiv(num_points, tg::TM), 256, 0, st>>>(x, (int)ldx, (int)num_points, (int)d, centers,
                                                                             (int)num_clusters, cnorm_ws, assign_out, loss_out);
     RSB_LAUNCH_CHECK();
@@ -335,18 +440,20 @@ extern "C" int32_t rsb200_kmeans_update(const float* x, int64_t ldx, int64_t num
     RSB_REQUIRE(x && assign && sums_out && counts_out, RSB200_EINVAL, "null pointer");
     RSB_REQUIRE(d >= 1 && ldx >= d && num_points >= 1 && num_points < ((int64_t)1 << 31) && num_clusters >= 1, RSB200_EINVAL,
                 "bad kmeans shape");
-    const size_t smem = (size_t)(num_clusters * d + num_clusters) * sizeof(float);
-    RSB_REQUIRE(smem <= 200 * 1024, RSB200_EUNSUPPORTED, "num_clusters * d = %lld floats exceed the shared-memory accumulator",
+    const size_t set_bytes = (size_t)(num_clusters * d + num_clusters) * sizeof(float);
+    RSB_REQUIRE(set_bytes <= 200 * 1024, RSB200_EUNSUPPORTED, "num_clusters * d = %lld floats exceed the shared-memory accumulator",
                 (long long)(num_clusters * d));
+    const size_t smem = set_bytes;
     cudaStream_t st = (cudaStream_t)stream;
     RSB_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(float) * (size_t)(num_clusters * d), st));
     RSB_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(float) * (size_t)num_clusters, st));
+    int64_t per_sm = (int64_t)((200 * 1024) / smem);
+    if (per_sm > 8) per_sm = 8;
+    int64_t blocks = cdiv(num_points, 8 * 64);            // >= 64 points per warp before a flush
+    if (blocks > (int64_t)sm_count() * per_sm) blocks = (int64_t)sm_count() * per_sm;
+    if (blocks < 1) blocks = 1;
     if (smem > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(kmeans_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = cdiv(num_points, 8 * 64);            // >= 64 points per warp before a flush
-    const int64_t max_blocks = (int64_t)sm_count() * (smem > 100 * 1024 ? 1 : 2);
-    if (blocks > max_blocks) blocks = max_blocks;
-    if (blocks < 1) blocks = 1;
     kmeans_update_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, (int)ldx, (int)num_points, (int)d, assign, (int)num_clusters,
                                                              sums_out, counts_out);
     RSB_LAUNCH_CHECK();

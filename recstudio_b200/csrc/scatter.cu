@@ -26,8 +26,10 @@ constexpr int kScatWarps = 8;
 // PLAIN = compact sink, overwrite, inner-product: the hot configuration with all options compiled out
 // HINT (PLAIN only) = L2 eviction priorities: the entry list and the gradient rows are touched once
 // (evict_first), the query matrix is re-read by every entry (evict_last).
-template <int VPL, bool PLAIN, bool HINT = false>
-__global__ void __launch_bounds__(kScatWarps * 32)
+// OCC = CTAs per SM the kernel is compiled for (register cap), UNR = entries (query-row loads) in flight per warp.
+// FULL = every lane owns a live float4 of the row (D == 128 VPL): the column predicates compile out.
+template <int VPL, bool PLAIN, bool HINT = false, int OCC = 4, int UNR = 4, bool FULL = false>
+__global__ void __launch_bounds__(kScatWarps * 32, OCC)
 scatter_kernel(const ScatterParams p) {
     uint64_t pol_first = 0, pol_last = 0;
     if (HINT) { pol_first = l2_policy(1); pol_last = l2_policy(2); }
@@ -40,7 +42,8 @@ scatter_kernel(const ScatterParams p) {
     const bool dense = !PLAIN && p.dense, accumulate = !PLAIN && p.accumulate, euclid = !PLAIN && p.euclid;
     bool act[VPL];
 #pragma unroll
-    for (int t = 0; t < VPL; ++t) act[t] = (lane * 4 + t * 128) < D;
+    for (int t = 0; t < VPL; ++t) act[t] = FULL || (lane * 4 + t * 128) < D;
+    const float* src_lane = p.src + lane * 4;          // 32-bit row offsets below: B * D < 2^31
 
     for (uint32_t chunk = blockIdx.x * kScatWarps + (threadIdx.x >> 5); chunk < nchunks; chunk += warps_total) {
         const uint32_t u = chunk * 32 + lane;
@@ -58,6 +61,7 @@ scatter_kernel(const ScatterParams p) {
         const uint32_t last = end - 1;                 // index of this lane's row's last entry (rows have >= 1 entry)
 
         int cur = 0;                                   // row of the chunk being accumulated
+        float* dst_run = p.vals + (size_t)chunk * 32 * D + lane * 4;   // PLAIN && FULL: output pointer of the current row
         float4 acc[VPL];
 #pragma unroll
         for (int t = 0; t < VPL; ++t) acc[t] = make_float4(0, 0, 0, 0);
@@ -80,30 +84,41 @@ scatter_kernel(const ScatterParams p) {
                 const float val = __uint_as_float((uint32_t)(en >> 32));
                 bq = lo & 0x7FFFFFFFu;
                 c = (lo & kDirect) ? val : expf(val - __ldg(p.lse + bq)) * p.ssm_scale;
+                if (PLAIN) c *= gs;            // upstream gradient folded into the coefficient: no per-row scaling at flush time
             }
             // bit t set <=> entry eb+t is the last entry of its row
             const uint32_t contrib = (have && last >= eb && last < eb + 32) ? (1u << (last - eb)) : 0u;
             const uint32_t lastmask = __reduce_or_sync(kFull, contrib);
             const int cnt = min(32u, e_end - eb);
-            for (int t0 = 0; t0 < cnt; t0 += 4) {      // lanes >= cnt hold (b = 0, c = 0): harmless
-                float4 v[4][VPL];
-                float cc[4];
+            for (int t0 = 0; t0 < cnt; t0 += UNR) {    // lanes >= cnt hold (b = 0, c = 0): harmless
+                float4 v[UNR][VPL];
+                float cc[UNR];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < UNR; ++k) {
                     const uint32_t bt = __shfl_sync(kFull, bq, t0 + k);
                     cc[k] = __shfl_sync(kFull, c, t0 + k);
-                    const float* srow = p.src + (size_t)bt * D + lane * 4;
+                    const float* srow = src_lane + bt * (uint32_t)D;
 #pragma unroll
                     for (int x = 0; x < VPL; ++x)
                         v[k][x] = act[x] ? (HINT ? ldg128_hint(srow + x * 128, pol_last) : ldg128(srow + x * 128))
                                          : make_float4(0, 0, 0, 0);
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < UNR; ++k) {
 #pragma unroll
                     for (int x = 0; x < VPL; ++x) fma4(acc[x], cc[k], v[k][x]);
                     csum += cc[k];
-                    if ((lastmask >> (t0 + k)) & 1u) {                 // warp-uniform: row `cur` is complete
+                    if (PLAIN && FULL) {
+                        if ((lastmask >> (t0 + k)) & 1u) {             // warp-uniform: the current row is complete
+#pragma unroll
+                            for (int x = 0; x < VPL; ++x) {
+                                if (HINT) stg128_stream_hint(dst_run + x * 128, acc[x], pol_first);
+                                else stg128_stream(dst_run + x * 128, acc[x]);
+                                acc[x] = make_float4(0, 0, 0, 0);
+                            }
+                            dst_run += D;                              // compact sink: rows of the chunk are consecutive
+                        }
+                    } else if ((lastmask >> (t0 + k)) & 1u) {          // warp-uniform: row `cur` is complete
                         uint32_t rr = 0;
                         if (!PLAIN) rr = __shfl_sync(kFull, r, cur);
                         const size_t orow = dense ? (size_t)rr : (size_t)chunk * 32 + cur;
@@ -117,7 +132,7 @@ scatter_kernel(const ScatterParams p) {
                                     a.x = 2.f * (a.x - csum * wv.x); a.y = 2.f * (a.y - csum * wv.y);
                                     a.z = 2.f * (a.z - csum * wv.z); a.w = 2.f * (a.w - csum * wv.w);
                                 }
-                                a.x *= gs; a.y *= gs; a.z *= gs; a.w *= gs;
+                                if (!PLAIN) { a.x *= gs; a.y *= gs; a.z *= gs; a.w *= gs; }   // PLAIN: folded into c
                                 float* dst = p.vals + orow * D + col;
                                 if (accumulate) {
                                     const float4 o = *reinterpret_cast<const float4*>(dst);
@@ -154,7 +169,20 @@ loss_sum_kernel(const float* __restrict__ part, int B, float* __restrict__ loss)
 template <int VPL>
 static void launch_scatter_v(const ScatterParams& p, unsigned blocks, cudaStream_t st) {
     const bool plain = !p.dense && !p.accumulate && !p.euclid;
+    if (plain && VPL == 1 && p.hint >= 2) {          // occupancy / unroll experiments (rsb200_pair_args.variant 40..44)
+        const unsigned chunks = blocks;              // caller passes the uncapped block count for these
+        auto grid = [&](int occ) { return (unsigned)min((int64_t)chunks, (int64_t)sm_count() * occ); };
+        switch (p.hint) {
+            case 2: scatter_kernel<1, true, false, 4, 4, false><<<grid(8), kScatWarps * 32, 0, st>>>(p); break;   // previous default
+            case 3: scatter_kernel<1, true, false, 5, 4><<<grid(5), kScatWarps * 32, 0, st>>>(p); break;
+            case 4: scatter_kernel<1, true, false, 6, 4><<<grid(6), kScatWarps * 32, 0, st>>>(p); break;
+            case 5: scatter_kernel<1, true, false, 6, 2><<<grid(6), kScatWarps * 32, 0, st>>>(p); break;
+            default: scatter_kernel<1, true, false, 5, 8><<<grid(5), kScatWarps * 32, 0, st>>>(p); break;
+        }
+        return;
+    }
     if (plain && p.hint && VPL == 1) scatter_kernel<VPL, true, true><<<blocks, kScatWarps * 32, 0, st>>>(p);
+    else if (plain && p.D == 128 * VPL) scatter_kernel<VPL, true, false, 4, 4, true><<<blocks, kScatWarps * 32, 0, st>>>(p);
     else if (plain) scatter_kernel<VPL, true><<<blocks, kScatWarps * 32, 0, st>>>(p);
     else scatter_kernel<VPL, false><<<blocks, kScatWarps * 32, 0, st>>>(p);
 }
@@ -164,7 +192,7 @@ int32_t launch_scatter(const ScatterParams& p, int64_t cap_rows, cudaStream_t st
     int64_t chunks = cdiv(cap_rows, 32);
     int64_t blocks = cdiv(chunks, kScatWarps);
     int64_t max_blocks = (int64_t)sm_count() * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks > max_blocks && p.hint < 2) blocks = max_blocks;
     if (p.D <= 128) launch_scatter_v<1>(p, (unsigned)blocks, st);
     else if (p.D <= 256) launch_scatter_v<2>(p, (unsigned)blocks, st);
     else if (p.D <= 512) launch_scatter_v<4>(p, (unsigned)blocks, st);

@@ -123,6 +123,22 @@ shard_prep_kernel(const PrepParams p) {
     if (lane == 0) p.ncount[b] = kept;
 }
 
+// slot -> absolute entry position for the compacted lists (same purpose as group.cu resolve_kernel): the offsets are
+// looked up here, right after the scan wrote them, instead of inside the forward kernel's row stream.
+__global__ void __launch_bounds__(kPrepWarps * 32)
+shard_resolve_kernel(const int32_t* __restrict__ neg_c, uint32_t* __restrict__ slot_neg, const int32_t* __restrict__ ncount,
+                     const uint32_t* __restrict__ off, int G, int n) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
+    if (b >= G) return;
+    const size_t base = (size_t)b * n;
+    const int cnt = min(n, max(0, __ldg(ncount + b)));
+    for (int j = lane; j < cnt; j += 32) {
+        const uint32_t s = slot_neg[base + j];
+        if (s != kNoSlot) slot_neg[base + j] = __ldg(off + neg_c[base + j]) + s;
+    }
+}
+
 struct FinishParams {
     const float* w_local; const float* q_all;
     const float* stats_all;        // [world, G, 2]
@@ -248,6 +264,10 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         }
         rc = launch_scan(a->off, a->local_rows, a->urow, a->cap, a->totals, a->scan_tmp, a->scan_tmp_elems, st);
         if (rc) return rc;
+        if (G > 0 && n > 0) {
+            shard_resolve_kernel<<<qblocks, kPrepWarps * 32, 0, st>>>(a->neg_c, a->slot_neg, a->ncount, a->off, (int)G, (int)n);
+            RSB_LAUNCH_CHECK();
+        }
     }
     if ((phases & RSB200_SHARD_FWD) && G > 0) {
         FwdParams p;
@@ -257,7 +277,7 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         p.ent_item = a->ent; p.ent_user = nullptr; p.q_buf = nullptr; p.dq_buf = a->dq; p.loss_part = nullptr; p.lse = nullptr;
         p.pos_score = nullptr; p.neg_score = nullptr;
         p.num_items = (int)a->local_rows; p.num_users = (int)G; p.B = (int)G; p.n = (int)n; p.D = (int)a->d;
-        p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0; p.hint = 0; p.slot_abs = 0;
+        p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0; p.hint = 0; p.slot_abs = 1;
         p.ncount = a->ncount; p.sp_in = a->sp; p.stats_part = a->stats_all + 2 * (size_t)a->rank * (size_t)G;
         rc = launch_pair_fwd_partial(p, a->loss_kind, a->score_kind, st);
         if (rc) return rc;
