@@ -77,7 +77,18 @@ popular_kernel(uint64_t seed, uint64_t ctr_base, int64_t T, int64_t rounds, int6
                 int k = (int)(u * (float)(1 << guide_bits));  // exact: power-of-two scale of a 24-bit float
                 lo = guide[k]; hi = guide[k + 1];
             }
-            int id = lower_bound(table, lo, hi, u);
+            // bisect down to a bracket of <= kLinear entries, then count the entries below u with INDEPENDENT loads:
+            // every bisection step is a dependent random DRAM access (~1 us each at a 400 MB table), the final
+            // bracket is one or two adjacent sectors.  Same result as a full bisection on a non-decreasing table.
+            constexpr int kLinear = 8;
+            while (hi - lo > kLinear) {
+                const int mid = lo + ((hi - lo) >> 1);
+                if (__ldg(table + mid) < u) lo = mid + 1; else hi = mid;
+            }
+            int id = lo;
+#pragma unroll
+            for (int t = 0; t < kLinear; ++t)
+                if (lo + t < hi) id += (__ldg(table + lo + t) < u) ? 1 : 0;
             if (out64) out64[li] = id;
             if (out32) out32[li] = id;
             if (logq) logq[li] = logf(__ldg(pop_prob + id));

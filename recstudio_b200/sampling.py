@@ -18,6 +18,7 @@ from ._lib import check, lib, ptr, stream_ptr
 def _generator(device: torch.device, generator: Optional[torch.Generator]):
     if generator is not None:
         return generator
+    torch.cuda.init()           # default_generators is empty until CUDA is initialised (lazy init)
     idx = device.index if device.index is not None else torch.cuda.current_device()
     return torch.cuda.default_generators[idx]
 
@@ -80,9 +81,11 @@ def build_guide(table: torch.Tensor, guide_bits: Optional[int] = None):
     """guide[k] = searchsorted(table, k / 2^bits): O(1)-expected replacement of the bisection."""
     n = table.numel()
     if guide_bits is None:
-        # ~N/4 guide entries, at most 2^22 (16 MB): guide + table + pop_prob (4 B/item each) then stay inside the
-        # 126 MB L2 at N = 10 M (a 2^24-entry guide pushed the random reads of the draw out to DRAM: 0.24 ms/step)
-        guide_bits = max(1, min(22, (max(n, 2) - 1).bit_length() - 2))
+        # about 8 table entries per guide bucket: the draw kernel then needs no bisection step at all (it counts the
+        # <= 8 entries of the bracket with independent loads), i.e. two dependent random accesses per draw instead
+        # of log2(N).  N = 10 M: 2^21 entries (8 MB, guide + table + pop_prob stay inside the 126 MB L2);
+        # N = 100 M: 2^24 entries (64 MB; nothing fits L2 at that size anyway).
+        guide_bits = max(1, min(24, ((max(n, 2) - 1) // 8).bit_length()))
     guide = torch.empty((1 << guide_bits) + 1, dtype=torch.int32, device=table.device)
     with torch.cuda.device(table.device):
         check(lib().rsb200_popular_build_guide(ptr(table), n, guide_bits, ptr(guide), stream_ptr()), "build_guide")
