@@ -89,14 +89,20 @@ struct BatchMeta {
     float lq;         // log Q(neg) (SSM)
 };
 
-template <int LOSS>
-__device__ __forceinline__ BatchMeta load_meta(const FwdParams& p, size_t rowbase, int jb, int j1, int lane) {
+template <int LOSS, bool HINT = false>
+__device__ __forceinline__ BatchMeta load_meta(const FwdParams& p, size_t rowbase, int jb, int j1, int lane, uint64_t pol = 0) {
     BatchMeta m;
     const int j = jb + lane;
     const bool valid = j < j1;
-    m.id = valid ? __ldg(p.neg + rowbase + j) : 0;
-    if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
-    m.slot = valid ? __ldg(p.slot_neg + rowbase + j) : kNoSlot;
+    if (HINT) {        // ids / slots are read exactly once: same eviction priority as the rows
+        m.id = valid ? (int)ldg32_hint(reinterpret_cast<const uint32_t*>(p.neg) + rowbase + j, pol) : 0;
+        if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
+        m.slot = valid ? ldg32_hint(p.slot_neg + rowbase + j, pol) : kNoSlot;
+    } else {
+        m.id = valid ? __ldg(p.neg + rowbase + j) : 0;
+        if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
+        m.slot = valid ? __ldg(p.slot_neg + rowbase + j) : kNoSlot;
+    }
     m.lq = 0.f;
     if (LOSS == RSB200_LOSS_SSM && p.logq_neg != nullptr && valid) m.lq = __ldg(p.logq_neg + rowbase + j);
     return m;
@@ -340,7 +346,7 @@ pair_fwd_kernel(const FwdParams p) {
     const size_t rowbase = (size_t)b * n;
 
     // start the stream before the (dependent) positive-score reduction
-    BatchMeta cur = load_meta<LOSS>(p, rowbase, j0, j1, lane);
+    BatchMeta cur = load_meta<LOSS, HINT>(p, rowbase, j0, j1, lane, pol_row);
     BatchMeta nxt = cur;
     RowBuf<VPL> bufA, bufB;
     if (PIPE) {
@@ -429,7 +435,7 @@ pair_fwd_kernel(const FwdParams p) {
                 }
             }
             if (p.prefetch) cur = nxt;
-            else if (jb + 32 < j1) cur = load_meta<LOSS>(p, rowbase, jb + 32, j1, lane);
+            else if (jb + 32 < j1) cur = load_meta<LOSS, HINT>(p, rowbase, jb + 32, j1, lane, pol_row);
         }
     }
 

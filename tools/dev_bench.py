@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--variants", type=str, default="", help="comma list: time each variant in this process")
+    ap.add_argument("--interleave", action="store_true", help="alternate the variants step by step (cancels drift between runs)")
     ap.add_argument("--sampler", default="uniform", choices=["uniform", "popular"])
     ap.add_argument("--mode", type=int, default=0, help="PopularSamplerModel mode (0 log, 2 count^0.75)")
     a = ap.parse_args()
@@ -42,9 +43,33 @@ def main():
         counts[0] = 0
         pop = plugins.FusedPopularSampler(counts, mode=a.mode).to(dev)
     names = ["sample", "count", "scan", "fwd", "scatter"]
-    for variant in ([int(v) for v in a.variants.split(",")] if a.variants else [a.variant]):
+    variants = [int(v) for v in a.variants.split(",")] if a.variants else [a.variant]
+    if a.interleave:
+        run_interleaved(a, dev, wi, wu, user, pos, ws, variants, names)
+        return
+    for variant in variants:
         a.variant = variant
         run_variant(a, dev, wi, wu, user, pos, ws, pop, names)
+
+
+def run_interleaved(a, dev, wi, wu, user, pos, ws, variants, names):
+    tot = {v: {k: 0.0 for k in names} for v in variants}
+    for it in range(a.steps + 3):
+        for v in variants:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record()
+            _, neg32 = sampling.uniform_draw(a.N, a.B, a.n, dev, want_i64=False, want_i32=True)
+            ev[1].record()
+            for i, ph in enumerate((_lib.PHASE_COUNT, _lib.PHASE_SCAN, _lib.PHASE_FWD, _lib.PHASE_SCATTER)):
+                fused.pair_step(ws, wi, wu, user, pos, neg32, a.loss, a.score, phases=ph, variant=v)
+                ev[i + 2].record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                for i, k in enumerate(names):
+                    tot[v][k] += ev[i].elapsed_time(ev[i + 1])
+    for v in variants:
+        ms = {k: x / a.steps for k, x in tot[v].items()}
+        print(json.dumps({"variant": v, "interleaved": True, "ms": ms, "step_ms": sum(ms.values())}))
 
 
 def run_variant(a, dev, wi, wu, user, pos, ws, pop, names):
