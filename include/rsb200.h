@@ -171,7 +171,7 @@ typedef struct rsb200_pair_args {
     uint32_t*      off_item;    /* [num_items + 1]  histogram -> CSR offsets          */
     uint32_t*      off_user;    /* [num_users + 1]                                    */
     int32_t*       neg32_buf;   /* [B * n] int32 copy of neg_i64 (unused when neg_i32 is given) */
-    uint32_t*      slot_neg;    /* [B * n]                                            */
+    uint32_t*      slot_neg;    /* [B * n]  COUNT: position inside the row's segment; SCAN turns it into the absolute entry position */
     uint32_t*      slot_pos;    /* [B]                                                */
     uint32_t*      slot_user;   /* [B]                                                */
     uint64_t*      ent_item;    /* [B * (n + 1)]  (query, coefficient) entries by row */
@@ -190,7 +190,13 @@ typedef struct rsb200_pair_args {
     int64_t scan_tmp_elems;
     float   grad_scale;              /* upstream gradient (loss.backward() => 1.0)     */
     int32_t loss_kind, score_kind, sink, accumulate;
-    int32_t variant;                 /* 0 = default kernel; other values select experimental variants */
+    int32_t variant;                 /* 0 = default kernels.  A/B switches kept for the measurements quoted in DESIGN.md 2
+                                      * (same results, different memory schedule): 1 software-pipelined forward, 2 TMA
+                                      * (cp.async.bulk) ring, 3 L2 prefetch, 4 forward compiled for 4 CTAs/SM, 6 CSR offsets
+                                      * looked up inside the forward kernel (no resolve pass), 16..31 L2 eviction-priority
+                                      * hints (bit 0 rows evict_first, bit 1 offsets, bit 2 entries evict_last, bit 3 scatter),
+                                      * 40..44 scatter occupancy / unroll.  32 = timing diagnostic WITHOUT the entry list:
+                                      * the gradients it produces are invalid. */
 } rsb200_pair_args;
 
 /* Fills the size fields a caller needs to allocate the workspace of a

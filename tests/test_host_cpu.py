@@ -181,3 +181,22 @@ def test_rank_metrics_mirror_matches_reference_golden():
     for name, fn in rank_metrics.get_rank_metrics(["ndcg", "recall", "precision", "map", "mrr", "hit"]):
         for k in (1, 3, 5):
             assert abs(fn(label, tgt, k).item() - g[f"m_{name}_{k}"].item()) < 1e-7, (name, k)
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/rsb200.h is a C header and librsb200.so a plain C-ABI library: a C99 program with no Python / torch in
+    the process links it and exercises the size queries, argument validation and error strings."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    from recstudio_b200 import build
+    lib = build.build()
+    exe = str(tmp_path / "abi_smoke")
+    src = os.path.join(REPO, "tests", "c_abi", "abi_smoke.c")
+    libdir = os.path.dirname(lib)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), src, "-o", exe,
+                    "-L", libdir, "-lrsb200", "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi ok" in out.stdout, out.stdout + out.stderr
