@@ -60,6 +60,7 @@ extern "C" {
 /* gradient sinks for PHASE_SCATTER */
 #define RSB200_SINK_COMPACT  0   /* rows[R] (int64, ascending, unique) + vals[R,d]: a coalesced sparse-COO gradient */
 #define RSB200_SINK_DENSE    1   /* vals is a dense [num_rows, d] buffer; touched rows are OVERWRITTEN (accumulate=0) or += (accumulate=1); rows[] still written */
+#define RSB200_SINK_APPLY    2   /* no gradient output: the optimizer update (opt_* fields) is applied to the touched rows of w_*_rw; rows[] still written */
 
 /* ------------------------------------------------------------------------- */
 int32_t     rsb200_version(void);
@@ -197,6 +198,18 @@ typedef struct rsb200_pair_args {
                                       * hints (bit 0 rows evict_first, bit 1 offsets, bit 2 entries evict_last, bit 3 scatter),
                                       * 40..44 scatter occupancy / unroll.  32 = timing diagnostic WITHOUT the entry list:
                                       * the gradients it produces are invalid. */
+    /* RSB200_SINK_APPLY ("fuse into the scatter epilogue"): PHASE_SCATTER applies the optimizer update of
+     * every touched row straight from the accumulated gradient, so the gradient rows are neither written nor re-read.
+     * w_*_rw normally alias w_item / w_user; state arrays have the tables' shapes. */
+    float*  w_item_rw;
+    float*  w_user_rw;
+    float*  item_state1;             /* Adagrad: sum of squares; SparseAdam: exp_avg        */
+    float*  item_state2;             /* SparseAdam: exp_avg_sq                              */
+    float*  user_state1;
+    float*  user_state2;
+    int32_t opt_kind;                /* 0 SGD, 1 Adagrad, 2 SparseAdam (semantics of rsb200_rows_update) */
+    float   opt_lr, opt_beta1, opt_beta2, opt_eps;
+    float   opt_step_size;           /* SparseAdam: lr * sqrt(1 - beta2^t) / (1 - beta1^t)   */
 } rsb200_pair_args;
 
 /* Fills the size fields a caller needs to allocate the workspace of a

@@ -20,7 +20,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "rsb200.h")
 LOSS_BPR, LOSS_SSM, LOSS_FULL = 0, 1, 2
 SCORE_IP, SCORE_EUCLID = 0, 1
 PHASE_COUNT, PHASE_SCAN, PHASE_FWD, PHASE_SCATTER, PHASE_ALL = 1, 2, 4, 8, 15
-SINK_COMPACT, SINK_DENSE = 0, 1
+SINK_COMPACT, SINK_DENSE, SINK_APPLY = 0, 1, 2
 SHARD_PREP, SHARD_FWD, SHARD_FINISH, SHARD_SCATTER = 1, 2, 4, 8
 
 

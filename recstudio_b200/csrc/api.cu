@@ -104,7 +104,16 @@ static int32_t check_pair(const rsb200_pair_args* a) {
                 aligned16(a->item_vals) && aligned16(a->user_vals), RSB200_EINVAL, "tables / row buffers must be 16-byte aligned");
     RSB_REQUIRE(a->loss_kind == RSB200_LOSS_BPR || a->loss_kind == RSB200_LOSS_SSM, RSB200_EINVAL, "bad loss_kind");
     RSB_REQUIRE(a->score_kind == RSB200_SCORE_IP || a->score_kind == RSB200_SCORE_EUCLID, RSB200_EINVAL, "bad score_kind");
-    RSB_REQUIRE(a->sink == RSB200_SINK_COMPACT || a->sink == RSB200_SINK_DENSE, RSB200_EINVAL, "bad sink");
+    RSB_REQUIRE(a->sink == RSB200_SINK_COMPACT || a->sink == RSB200_SINK_DENSE || a->sink == RSB200_SINK_APPLY, RSB200_EINVAL, "bad sink");
+    if (a->sink == RSB200_SINK_APPLY) {
+        RSB_REQUIRE(a->opt_kind >= 0 && a->opt_kind <= 2, RSB200_EINVAL, "opt_kind must be 0 (sgd), 1 (adagrad) or 2 (sparse_adam)");
+        RSB_REQUIRE(a->w_item_rw && a->w_user_rw && aligned16(a->w_item_rw) && aligned16(a->w_user_rw), RSB200_EINVAL,
+                    "SINK_APPLY needs writable tables (w_item_rw / w_user_rw)");
+        RSB_REQUIRE(a->opt_kind == 0 || (a->item_state1 && a->user_state1 && aligned16(a->item_state1) && aligned16(a->user_state1)),
+                    RSB200_EINVAL, "optimizer state1 missing");
+        RSB_REQUIRE(a->opt_kind != 2 || (a->item_state2 && a->user_state2 && aligned16(a->item_state2) && aligned16(a->user_state2)),
+                    RSB200_EINVAL, "optimizer state2 missing");
+    }
     RSB_REQUIRE(a->off_item && a->off_user && a->slot_neg && a->slot_pos && a->slot_user && a->ent_item && a->ent_user &&
                 a->urow_item && a->urow_user && a->q_buf && a->dq_buf && a->loss_part && a->lse && a->scan_tmp &&
                 a->err_flag && a->totals && a->loss, RSB200_EINVAL, "null workspace pointer");
@@ -171,12 +180,19 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = a->score_kind == RSB200_SCORE_EUCLID;
         s.hint = (a->variant >= 16 && a->variant < 32) ? ((a->variant >> 3) & 1) : 0;
         if (a->variant >= 40 && a->variant <= 44) s.hint = a->variant - 38;   // scatter occupancy / unroll experiments
+        s.opt = -1; s.w_rw = nullptr; s.s1 = nullptr; s.s2 = nullptr; s.lr = s.b1 = s.b2 = s.eps = s.step_size = 0.f;
+        if (a->sink == RSB200_SINK_APPLY) {
+            s.opt = a->opt_kind; s.w_rw = a->w_item_rw; s.s1 = a->item_state1; s.s2 = a->item_state2;
+            s.lr = a->opt_lr; s.b1 = a->opt_beta1; s.b2 = a->opt_beta2; s.eps = a->opt_eps; s.step_size = a->opt_step_size;
+            s.dense = 0; s.accumulate = 0;
+        }
         rc = launch_scatter(s, a->cap_item, st);
         if (rc) return rc;
         ScatterParams u = s;
         u.off = a->off_user; u.urow = a->urow_user; u.totals = a->totals + 2; u.ent = a->ent_user; u.src = a->dq_buf;
         u.lse = nullptr; u.w = a->w_user; u.rows_out = a->user_rows; u.vals = a->user_vals; u.cap = a->cap_user;
         u.euclid = 0;
+        if (a->sink == RSB200_SINK_APPLY) { u.w_rw = a->w_user_rw; u.s1 = a->user_state1; u.s2 = a->user_state2; }
         rc = launch_scatter(u, a->cap_user, st);
         if (rc) return rc;
     }

@@ -62,6 +62,6 @@ extern "C" int32_t rsb200_rows_coalesce(const int64_t* ids, const float* vals, i
     ScatterParams s;
     s.off = off; s.urow = urow; s.totals = totals; s.ent = ent; s.src = vals; s.lse = nullptr; s.w = nullptr; s.gscale = nullptr;
     s.rows_out = rows_out; s.vals = vals_out; s.cap = cap; s.D = (int)d; s.ssm_scale = 1.f;
-    s.dense = sink == RSB200_SINK_DENSE; s.accumulate = accumulate; s.euclid = 0; s.hint = 0;
+    s.dense = sink == RSB200_SINK_DENSE; s.accumulate = accumulate; s.euclid = 0; s.hint = 0; s.opt = -1;
     return launch_scatter(s, cap, st);
 }

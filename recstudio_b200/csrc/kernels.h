@@ -41,6 +41,10 @@ struct ScatterParams {
     float ssm_scale;
     int dense, accumulate, euclid;
     int hint;                 // L2 eviction hints (PLAIN kernel): entries / output rows evict_first, src evict_last
+    // optimizer fused into the epilogue (RSB200_SINK_APPLY): opt < 0 = off
+    int opt;                  // 0 SGD, 1 Adagrad, 2 SparseAdam
+    float* w_rw; float* s1; float* s2;
+    float lr, b1, b2, eps, step_size;
 };
 
 // group.cu

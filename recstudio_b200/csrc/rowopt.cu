@@ -11,6 +11,7 @@
 // Row 0 (padding) never appears in `rows`.  One warp per row, 16-byte accesses.
 #include "common.cuh"
 #include "kernels.h"
+#include "rowopt.cuh"
 
 namespace rsb {
 
@@ -22,36 +23,11 @@ rows_update_kernel(float* __restrict__ w, float* __restrict__ s1, float* __restr
     const int lane = threadIdx.x & 31;
     const int64_t R = min((int64_t)*count, cap);
     const int64_t warps = (int64_t)gridDim.x * 8;
+    const OptParams o = {lr, b1, b2, eps, step_size};
     for (int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); u < R; u += warps) {
         const int64_t r = rows[u];
-        for (int c = lane * 4; c < D; c += 128) {
-            const float4 g = ldg128_stream(vals + (size_t)u * D + c);
-            float* wp = w + (size_t)r * D + c;
-            float4 x = *reinterpret_cast<const float4*>(wp);
-            if (KIND == 0) {
-                x.x -= lr * g.x; x.y -= lr * g.y; x.z -= lr * g.z; x.w -= lr * g.w;
-            } else if (KIND == 1) {
-                float* sp = s1 + (size_t)r * D + c;
-                float4 s = *reinterpret_cast<const float4*>(sp);
-                s.x += g.x * g.x; s.y += g.y * g.y; s.z += g.z * g.z; s.w += g.w * g.w;
-                *reinterpret_cast<float4*>(sp) = s;
-                x.x -= lr * g.x / (sqrtf(s.x) + eps); x.y -= lr * g.y / (sqrtf(s.y) + eps);
-                x.z -= lr * g.z / (sqrtf(s.z) + eps); x.w -= lr * g.w / (sqrtf(s.w) + eps);
-            } else {
-                float* mp = s1 + (size_t)r * D + c;
-                float* vp = s2 + (size_t)r * D + c;
-                float4 m = *reinterpret_cast<const float4*>(mp), v = *reinterpret_cast<const float4*>(vp);
-                m.x = b1 * m.x + (1.f - b1) * g.x; m.y = b1 * m.y + (1.f - b1) * g.y;
-                m.z = b1 * m.z + (1.f - b1) * g.z; m.w = b1 * m.w + (1.f - b1) * g.w;
-                v.x = b2 * v.x + (1.f - b2) * g.x * g.x; v.y = b2 * v.y + (1.f - b2) * g.y * g.y;
-                v.z = b2 * v.z + (1.f - b2) * g.z * g.z; v.w = b2 * v.w + (1.f - b2) * g.w * g.w;
-                *reinterpret_cast<float4*>(mp) = m;
-                *reinterpret_cast<float4*>(vp) = v;
-                x.x -= step_size * m.x / (sqrtf(v.x) + eps); x.y -= step_size * m.y / (sqrtf(v.y) + eps);
-                x.z -= step_size * m.z / (sqrtf(v.z) + eps); x.w -= step_size * m.w / (sqrtf(v.w) + eps);
-            }
-            *reinterpret_cast<float4*>(wp) = x;
-        }
+        for (int c = lane * 4; c < D; c += 128)
+            opt_update4<KIND>(w, s1, s2, (size_t)r * D + c, ldg128_stream(vals + (size_t)u * D + c), o);   // rowopt.cuh
     }
 }
 

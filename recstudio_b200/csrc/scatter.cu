@@ -18,17 +18,26 @@
 // per-entry work is 2 shuffles + one 16-byte load + 4 FMA + a bit test.
 #include "common.cuh"
 #include "kernels.h"
+#include "rowopt.cuh"
 
 namespace rsb {
 
 constexpr int kScatWarps = 8;
+
+// optimizer update of 4 consecutive elements of one row: the very same code as rows_update_kernel (rowopt.cuh)
+template <int OPT>
+__device__ __forceinline__ void apply_update(const ScatterParams& p, size_t off, float4 g) {
+    const OptParams o = {p.lr, p.b1, p.b2, p.eps, p.step_size};
+    opt_update4<OPT>(p.w_rw, p.s1, p.s2, off, g, o);
+}
 
 // PLAIN = compact sink, overwrite, inner-product: the hot configuration with all options compiled out
 // HINT (PLAIN only) = L2 eviction priorities: the entry list and the gradient rows are touched once
 // (evict_first), the query matrix is re-read by every entry (evict_last).
 // OCC = CTAs per SM the kernel is compiled for (register cap), UNR = entries (query-row loads) in flight per warp.
 // FULL = every lane owns a live float4 of the row (D == 128 VPL): the column predicates compile out.
-template <int VPL, bool PLAIN, bool HINT = false, int OCC = 4, int UNR = 4, bool FULL = false>
+// OPT >= 0 = RSB200_SINK_APPLY: the row's optimizer update (rowopt.cu arithmetic) replaces the gradient store.
+template <int VPL, bool PLAIN, bool HINT = false, int OCC = 4, int UNR = 4, bool FULL = false, int OPT = -1>
 __global__ void __launch_bounds__(kScatWarps * 32, OCC)
 scatter_kernel(const ScatterParams p) {
     uint64_t pol_first = 0, pol_last = 0;
@@ -133,13 +142,17 @@ scatter_kernel(const ScatterParams p) {
                                     a.z = 2.f * (a.z - csum * wv.z); a.w = 2.f * (a.w - csum * wv.w);
                                 }
                                 if (!PLAIN) { a.x *= gs; a.y *= gs; a.z *= gs; a.w *= gs; }   // PLAIN: folded into c
-                                float* dst = p.vals + orow * D + col;
-                                if (accumulate) {
-                                    const float4 o = *reinterpret_cast<const float4*>(dst);
-                                    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                                if (OPT >= 0) {
+                                    apply_update<OPT>(p, (size_t)rr * D + col, a);
+                                } else {
+                                    float* dst = p.vals + orow * D + col;
+                                    if (accumulate) {
+                                        const float4 o = *reinterpret_cast<const float4*>(dst);
+                                        a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                                    }
+                                    if (HINT) stg128_stream_hint(dst, a, pol_first);
+                                    else stg128_stream(dst, a);
                                 }
-                                if (HINT) stg128_stream_hint(dst, a, pol_first);
-                                else stg128_stream(dst, a);
                             }
                             acc[x] = make_float4(0, 0, 0, 0);
                         }
@@ -168,6 +181,12 @@ loss_sum_kernel(const float* __restrict__ part, int B, float* __restrict__ loss)
 
 template <int VPL>
 static void launch_scatter_v(const ScatterParams& p, unsigned blocks, cudaStream_t st) {
+    if (p.opt >= 0) {               // RSB200_SINK_APPLY: generic (non-PLAIN) body with the update in the epilogue
+        if (p.opt == 0) scatter_kernel<VPL, false, false, 4, 4, false, 0><<<blocks, kScatWarps * 32, 0, st>>>(p);
+        else if (p.opt == 1) scatter_kernel<VPL, false, false, 4, 4, false, 1><<<blocks, kScatWarps * 32, 0, st>>>(p);
+        else scatter_kernel<VPL, false, false, 4, 4, false, 2><<<blocks, kScatWarps * 32, 0, st>>>(p);
+        return;
+    }
     const bool plain = !p.dense && !p.accumulate && !p.euclid;
     if (plain && VPL == 1 && p.hint >= 2) {          // occupancy / unroll experiments (rsb200_pair_args.variant 40..44)
         const unsigned chunks = blocks;              // caller passes the uncapped block count for these

@@ -301,7 +301,7 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         s.off = a->off; s.urow = a->urow; s.totals = a->totals; s.ent = a->ent; s.src = a->q_all; s.lse = a->lse;
         s.w = a->w_local; s.gscale = a->grad_scale_dev; s.rows_out = a->item_rows; s.vals = a->item_vals; s.cap = a->cap;
         s.D = (int)a->d; s.ssm_scale = coef_scale;
-        s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = eu; s.hint = 0;
+        s.dense = a->sink == RSB200_SINK_DENSE; s.accumulate = a->accumulate; s.euclid = eu; s.hint = 0; s.opt = -1;
         rc = launch_scatter(s, a->cap, st);
         if (rc) return rc;
     }

@@ -87,7 +87,8 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
               phases: int = PHASE_ALL, grad_scale: float = 1.0, accumulate: bool = False,
               dense_item_grad: Optional[torch.Tensor] = None, dense_user_grad: Optional[torch.Tensor] = None,
               variant: int = 0, grad_scale_dev: Optional[torch.Tensor] = None,
-              item_vals: Optional[torch.Tensor] = None, user_vals: Optional[torch.Tensor] = None):
+              item_vals: Optional[torch.Tensor] = None, user_vals: Optional[torch.Tensor] = None,
+              apply: Optional[dict] = None):
     """Enqueue the selected phases of the fused step on the current stream.
 
     Returns the 0-dim loss tensor (a view of ``ws.loss``).  Gradients are left in
@@ -119,8 +120,18 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
         logq_neg = logq_neg.to(torch.float32).contiguous()
     a.logq_pos, a.logq_neg = ptr(logq_pos), ptr(logq_neg)
     a.loss, a.pos_score, a.neg_score = ptr(ws.loss), ptr(ws.pos_score), ptr(ws.neg_score)
-    dense = ws.sink == "dense"
-    if dense:
+    dense = ws.sink == "dense" and apply is None
+    keep_states = ()
+    if apply is not None:
+        # RSB200_SINK_APPLY: PHASE_SCATTER applies the optimizer update in its epilogue (no gradient rows)
+        keep_states = tuple(apply.get(k) for k in ("item_state1", "item_state2", "user_state1", "user_state2"))
+        a.w_item_rw, a.w_user_rw = ptr(w_item), ptr(w_user)
+        a.item_state1, a.item_state2, a.user_state1, a.user_state2 = (ptr(t) for t in keep_states)
+        a.opt_kind = int(apply["kind"])
+        a.opt_lr, a.opt_beta1, a.opt_beta2 = float(apply["lr"]), float(apply["beta1"]), float(apply["beta2"])
+        a.opt_eps, a.opt_step_size = float(apply["eps"]), float(apply["step_size"])
+        a.item_vals, a.user_vals = 0, 0
+    elif dense:
         if dense_item_grad is None or dense_user_grad is None:
             raise _lib.Rsb200Error("dense sink needs dense_item_grad / dense_user_grad")
         if tuple(dense_item_grad.shape) != (num_items, d) or tuple(dense_user_grad.shape) != (num_users, d):
@@ -149,11 +160,12 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
     a.cap_item, a.cap_user, a.scan_tmp_elems = ws.cap_item, ws.cap_user, ws.scan_tmp.numel()
     a.grad_scale = float(grad_scale)
     a.loss_kind, a.score_kind = int(loss_kind), int(score_kind)
-    a.sink, a.accumulate, a.variant = (SINK_DENSE if dense else SINK_COMPACT), int(bool(accumulate)), int(variant)
+    a.sink = _lib.SINK_APPLY if apply is not None else (SINK_DENSE if dense else SINK_COMPACT)
+    a.accumulate, a.variant = int(bool(accumulate)), int(variant)
     with torch.cuda.device(w_item.device):
         check(lib().rsb200_pair_step(C.byref(a), int(phases), stream_ptr()), "pair_step")
     # keep temporaries referenced by the async launch alive until the stream catches up
-    ws._keepalive = (logq_pos, logq_neg, neg, user, pos, grad_scale_dev)
+    ws._keepalive = (logq_pos, logq_neg, neg, user, pos, grad_scale_dev) + keep_states
     return ws.loss[0]
 
 

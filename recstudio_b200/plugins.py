@@ -377,6 +377,9 @@ class _FusedStepFn(torch.autograd.Function):
             fused.pair_step(ws, w_item, w_user, user, pos, neg32, loss_kind, score_kind, dense_item_grad=gi,
                             dense_user_grad=gu, **common)
             return gi, gu, None, None, None, None, None, None, None, None, None
+        if mode == "apply":       # nothing is computed here: FusedRowOptimizer.step() runs PHASE_SCATTER with the update
+            ws.pending_apply = (w_item, w_user, user, pos, neg32, loss_kind, score_kind, common)   # fused into its epilogue
+            return None, None, None, None, None, None, None, None, None, None, None
         d = w_item.shape[1]
         iv = torch.empty(ws.cap_item, d, dtype=torch.float32, device=w_item.device)
         uv = torch.empty(ws.cap_user, d, dtype=torch.float32, device=w_item.device)
@@ -422,6 +425,9 @@ class _FusedHeadFn(torch.autograd.Function):
         g = g.reshape(1).to(torch.float32).contiguous()
         common = dict(logq_pos=lqp, logq_neg=lqn, phases=_lib.PHASE_SCATTER, grad_scale_dev=g)
         nones = (None,) * 8
+        if host.fused_grad == "apply":
+            raise _lib.Rsb200Error("fused_grad='apply' fuses the optimizer into the step of two embedding-table towers; "
+                                   "use 'rows' with an arbitrary query encoder")
         if host.fused_grad == "dense":
             gi, gq = torch.zeros_like(w_item), torch.zeros_like(wq)
             fused.pair_step(ws, w_item, wq, uid, pos, neg32, loss_kind, score_kind, dense_item_grad=gi, dense_user_grad=gq, **common)
@@ -469,7 +475,9 @@ class FusedRetrieverMixin:
 
     ``fused_grad``: 'dense'  -> dense ``weight.grad`` (what the reference's dense Adam expects),
                     'sparse' -> coalesced sparse-COO ``weight.grad`` (sgd / adagrad / sparse_adam),
-                    'rows'   -> gradients stay in the workspace for a row optimizer (no host sync).
+                    'rows'   -> gradients stay in the workspace for a row optimizer (no host sync),
+                    'apply'  -> no gradient rows at all: ``FusedRowOptimizer.step()`` runs the scatter with the
+                                optimizer update in its epilogue (RSB200_SINK_APPLY).
     """
     fused_grad = "dense"
 

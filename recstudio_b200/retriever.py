@@ -226,8 +226,8 @@ class FusedRetriever(plugins.FusedRetrieverMixin, _Base):
 
     def __init__(self, config: Dict = None, fused_grad: str = "dense", device_loader: bool = False, **kwargs):
         super().__init__(config, **kwargs)
-        if fused_grad not in ("dense", "sparse", "rows"):
-            raise ValueError("fused_grad must be 'dense', 'sparse' or 'rows'")
+        if fused_grad not in ("dense", "sparse", "rows", "apply"):
+            raise ValueError("fused_grad must be 'dense', 'sparse', 'rows' or 'apply'")
         self.fused_grad = fused_grad
         self.device_loader = device_loader
 
@@ -260,7 +260,7 @@ class FusedRetriever(plugins.FusedRetrieverMixin, _Base):
         """The reference's documented multi-learner hook (recommender.py:403-406).  With
         ``fused_grad='rows'`` the two embedding tables are stepped by ``FusedRowOptimizer`` straight from
         the fused step's workspace; every other parameter keeps the reference's optimizer."""
-        if self.fused_grad != "rows":
+        if self.fused_grad not in ("rows", "apply"):
             return super()._get_optimizers()
         from .rowopt import FusedRowOptimizer
         tr = self.config["train"]

@@ -1,10 +1,11 @@
-"""Row optimizer for ``fused_grad='rows'``.
+"""Row optimizer for ``fused_grad='rows'`` / ``'apply'``.
 
 The reference steps a dense optimizer over every table row each iteration
 (``optim.Adam(self.parameters())``, recommender.py:427-428,462-463,646).  Here the gradient rows
 stay in the fused step's workspace and ``FusedRowOptimizer.step()`` updates only those rows with
 rsb200_rows_update; the row count is read on the device, so a training iteration issues no host
-synchronisation at all.  The trainer only duck-types ``zero_grad()`` / ``step()``
+synchronisation at all.  With ``fused_grad='apply'`` the update is fused into the scatter epilogue
+(RSB200_SINK_APPLY): the gradient rows (2.9 GB at config 2) are neither written nor re-read.  The trainer only duck-types ``zero_grad()`` / ``step()``
 (recommender.py:598-600,645-646), and the documented hook for this is ``_get_optimizers``
 ("If you want to use multi learner, please override `_get_optimizers`", recommender.py:403-406).
 
@@ -48,6 +49,21 @@ class FusedRowOptimizer:
     def step(self):
         cache = self.model.__dict__.get("_fused_ws_cache", {})
         ws = next(iter(cache.values()), None)
+        pending = getattr(ws, "pending_apply", None) if ws is not None else None
+        if pending is not None:
+            # fused_grad='apply': PHASE_SCATTER with the update in its epilogue -- the gradient rows are never written
+            from . import fused
+            self.step_count += 1
+            w_item, w_user, user, pos, neg32, loss_kind, score_kind, common = pending
+            (i1, i2), (u1, u2) = self._state_for(w_item), self._state_for(w_user)
+            bc1 = 1.0 - self.betas[0] ** self.step_count
+            bc2 = 1.0 - self.betas[1] ** self.step_count
+            spec = {"kind": self.kind, "lr": self.lr, "beta1": self.betas[0], "beta2": self.betas[1], "eps": self.eps,
+                    "step_size": self.lr * (bc2 ** 0.5) / bc1, "item_state1": i1, "item_state2": i2,
+                    "user_state1": u1, "user_state2": u2}
+            fused.pair_step(ws, w_item, w_user, user, pos, neg32, loss_kind, score_kind, apply=spec, **common)
+            ws.pending_apply = None
+            return
         grads = getattr(ws, "row_grads", None) if ws is not None else None
         if grads is None:
             raise _lib.Rsb200Error("FusedRowOptimizer.step(): no row gradients; run training_step(...).backward() "

@@ -7,12 +7,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.mark.parametrize("mode", ["rows", "apply"])
 @pytest.mark.parametrize("learner,torch_cls,kw", [("sgd", torch.optim.SGD, {}), ("adagrad", torch.optim.Adagrad, {}),
                                                     ("sparse_adam", torch.optim.SparseAdam, {})])
-def test_row_optimizer_matches_torch(learner, torch_cls, kw):
+def test_row_optimizer_matches_torch(learner, torch_cls, kw, mode):
+    """'rows': gradient rows -> rsb200_rows_update; 'apply': the update fused into the scatter epilogue
+    (RSB200_SINK_APPLY, no gradient rows).  Both equal the torch optimizer fed with the same sparse gradient."""
     from recstudio_b200 import retriever, rowopt
     U, N, d, B, n = 200, 3000, 64, 64, 50
-    a = retriever.build_synthetic(U, N, d, n, fused_grad="rows", device=DEV, init_std=0.2, seed=1)
+    a = retriever.build_synthetic(U, N, d, n, fused_grad=mode, device=DEV, init_std=0.2, seed=1)
     b = retriever.build_synthetic(U, N, d, n, fused_grad="sparse", device=DEV, init_std=0.2, seed=1)
     assert torch.equal(a.item_encoder.weight, b.item_encoder.weight)
     opt_a = rowopt.FusedRowOptimizer(a, learner, lr=0.05)
@@ -30,11 +33,12 @@ def test_row_optimizer_matches_torch(learner, torch_cls, kw):
         for wa, wb in ((a.item_encoder.weight, b.item_encoder.weight), (a.query_encoder.weight, b.query_encoder.weight)):
             scale = wb.abs().max().item()
             diff = (wa - wb).abs()
-            if learner == "adagrad":
-                # g / sqrt(sum g^2) is scale-free: an element whose gradient is a near-cancelled sum (1e-9)
-                # amplifies the fused step's summation-order noise to O(lr).  Almost all elements must agree
-                # to fp32 noise; the rest stay within a fraction of one step.
-                assert (diff > 2e-6 * scale).float().mean().item() < 1e-3, (learner, it)
+            if learner == "adagrad" or (learner == "sparse_adam" and mode == "apply"):
+                # g / sqrt(sum g^2) (and Adam's m / sqrt(v)) is scale-free: an element whose gradient is a near-cancelled
+                # sum (1e-9) amplifies the fused step's summation-order noise (the order of a row's entries comes from
+                # atomics) to O(lr).  Almost all elements must agree to fp32 noise; the rest stay within a fraction of one
+                # step.  ('rows' + sparse_adam shares the gradient kernel with the torch arm and is compared strictly.)
+                assert (diff > 2e-6 * scale).float().mean().item() < 3e-3, (learner, it)
                 assert diff.max().item() <= 0.1 * 0.05, (learner, it)
             else:
                 assert diff.max().item() <= 2e-6 * scale, (learner, it)
@@ -48,3 +52,29 @@ def test_row_optimizer_needs_rows():
         rowopt.FusedRowOptimizer(m, "sgd").step()
     with pytest.raises(ValueError):
         rowopt.FusedRowOptimizer(m, "adam")
+
+
+@pytest.mark.parametrize("loss,scorer", [("bpr", "ip"), ("ssm", "eu"), ("bpr", "eu")])
+def test_apply_matches_rows(loss, scorer):
+    """The fused epilogue (RSB200_SINK_APPLY) runs the very same per-element arithmetic (csrc/rowopt.cuh) on the same
+    accumulated gradient as the two-kernel path; SGD is linear in the gradient, so the weights agree to fp32
+    summation-order noise (d = 128: full rows; Euclid reads W[row] before updating it)."""
+    from recstudio_b200 import retriever, rowopt
+    U, N, d, B, n = 100, 2000, 128, 48, 70
+    models = [retriever.build_synthetic(U, N, d, n, loss=loss, scorer=scorer, fused_grad=m, device=DEV, init_std=0.3, seed=3)
+              for m in ("rows", "apply")]
+    opts = [rowopt.FusedRowOptimizer(m, "sgd", lr=0.5) for m in models]
+    gen = torch.Generator().manual_seed(1)
+    for it in range(3):
+        batch = {"user_id": torch.randint(1, U, (B,), generator=gen).to(DEV), "item_id": torch.randint(1, N, (B,), generator=gen).to(DEV),
+                 "rating": torch.ones(B, device=DEV)}
+        losses = []
+        for m, opt in zip(models, opts):
+            torch.manual_seed(7 + it)
+            loss_t = m.training_step(dict(batch)); loss_t.backward(); opt.step()
+            losses.append(loss_t.item())
+        assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[0])
+        for name in ("item_encoder", "query_encoder"):
+            wa, wb = getattr(models[0], name).weight, getattr(models[1], name).weight
+            assert (wa - wb).abs().max().item() <= 1e-6 * wa.abs().max().item()
+    assert float(models[1].item_encoder.weight[0].abs().sum()) == 0.0
