@@ -281,3 +281,72 @@ def test_config2_shape_properties():
             sn = (wi[neg32[b].long()] * q[b]).sum(-1)
             want = want - torch.sigmoid(sn - sp[b]).sum() / (B * n) * q[b]
         assert (vi[k] - want).abs().max().item() <= 1e-5 * want.abs().max().item() + 1e-12
+
+
+@pytest.mark.parametrize("loss", [R.BPR, R.SSM])
+def test_config2_shape_popularity_skew(loss):
+    """SURVEY 8(d) C2 variants at full size: sigma = 0.1 tables (scores are not all ~ 0) and Zipf-skewed negatives from
+    the PopularSampler (heavy duplicates: a few rows collect thousands of touches, id 0 is drawable).  Size-independent
+    properties: every non-padding touch accounted for, rows = sorted unique touched ids, BPR/IP gradient column sums
+    vanish, spot rows recomputed directly (SSM: with the log Q correction)."""
+    from recstudio_b200 import fused, plugins
+    dev = torch.device("cuda:0")
+    N, U, d, B, n = 10_000_001, 1_000_001, 128, 8192, 1024
+    torch.manual_seed(11)
+    wi = torch.empty(N, d, device=dev).normal_(0, 0.1); wi[0] = 0
+    wu = torch.empty(U, d, device=dev).normal_(0, 0.1); wu[0] = 0
+    rng = np.random.RandomState(0)
+    counts = np.floor(rng.zipf(1.05, size=N)).clip(max=1e9); counts[0] = 0
+    smp = plugins.FusedPopularSampler(counts, mode=2).to(dev)          # count^0.75: strong skew
+    g = torch.Generator(device=dev).manual_seed(0)
+    user = torch.randint(1, U, (B,), device=dev, generator=g)
+    pos = torch.randint(1, N, (B,), device=dev, generator=g)
+    neg32, lqn = smp.fused_draw(B, n, dev)
+    lqp = smp.compute_item_p(None, pos)
+    ws = fused.PairWorkspace(N, U, B, n, d, dev)
+    loss_t = fused.pair_step(ws, wi, wu, user, pos, neg32, loss, R.IP, logq_pos=lqp if loss == R.SSM else None,
+                             logq_neg=lqn if loss == R.SSM else None)
+    torch.cuda.synchronize()
+    assert int(ws.err_flag.item()) == 0 and np.isfinite(loss_t.item())
+    tot = ws.totals.tolist()
+    assert tot[0] == int((neg32 > 0).sum()) + B and tot[2] == B
+    (ri, vi), (ru, vu) = fused.sparse_grads(ws)
+    uniq = torch.unique(torch.cat([neg32.flatten().long(), pos]))
+    uniq = uniq[uniq > 0]
+    assert torch.equal(ri, uniq) and ri.numel() < 0.7 * B * n            # heavy duplication
+    if loss == R.BPR:
+        colsum = vi.double().sum(0).abs().max().item()
+        # touches of the padding row are scored but receive no gradient, so the column sums vanish only up to them
+        q = wu[user]
+        sp = (q * wi[pos]).sum(-1)
+        pad_b, pad_j = torch.nonzero(neg32 == 0, as_tuple=True)
+        c_pad = torch.sigmoid(-sp[pad_b]) / (B * n)                      # s(q, w_0) = 0
+        missing = (c_pad[:, None] * q[pad_b]).double().sum(0)
+        assert (vi.double().sum(0) + missing).abs().max().item() <= 1e-5 * max(vi.double().abs().sum(0).max().item(), 1e-12), colsum
+    # spot-check the most touched row and a few others against a direct evaluation
+    q = wu[user]
+    sp = (q * wi[pos]).sum(-1)
+    cnt = torch.bincount(neg32.flatten().long(), minlength=1)
+    heavy = int(torch.argmax(cnt[1:]) + 1)
+    sel = [heavy] + ri[torch.arange(0, ri.numel(), max(1, ri.numel() // 12), device=dev)[:12]].tolist()
+    if loss == R.SSM:
+        z0 = sp - lqp
+        zn = torch.einsum("bd,bnd->bn", q[:64], wi[neg32[:64].long()]) - lqn[:64]      # lse check on the first 64 queries
+        lse64 = torch.logsumexp(torch.cat([z0[:64, None], zn], 1), 1)
+        assert (ws.lse[:64] - lse64).abs().max().item() <= 1e-4
+    for r in sel:
+        bb, jj = torch.nonzero(neg32 == r, as_tuple=True)
+        s = (q[bb] * wi[r]).sum(-1)
+        if loss == R.BPR:
+            c = torch.sigmoid(s - sp[bb]) / (B * n)
+        else:
+            c = torch.exp(s - lqn[bb, jj] - ws.lse[bb]) / B
+        want = (c[:, None] * q[bb]).double().sum(0)
+        for b in torch.nonzero(pos == r, as_tuple=True)[0].tolist():
+            if loss == R.BPR:
+                sn = (wi[neg32[b].long()] * q[b]).sum(-1)
+                want = want - (torch.sigmoid(sn - sp[b]).sum() / (B * n) * q[b]).double()
+            else:
+                want = want + ((torch.exp(sp[b] - lqp[b] - ws.lse[b]) - 1) / B * q[b]).double()
+        k = int(torch.searchsorted(ri, torch.tensor([r], device=dev)))
+        assert (vi[k].double() - want).abs().max().item() <= 2e-5 * want.abs().max().item() + 1e-12, (r, int(bb.numel()))
