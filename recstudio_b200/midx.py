@@ -210,45 +210,52 @@ class FusedMIDXSamplerUniform(_IndexedSampler):
         total = self._build(cd01, self.K ** 2, item_embs)
         self.wkk = total.view(self.K, self.K)          # = cd0m.T @ (cd1m * norm)   (:297,300,408)
 
+    def _draw_buckets(self, flat_query: Tensor, num_neg: int):
+        """Two-stage bucket draw (sampler.py:313-327): first-codebook code ~ softmax(q0.c0) weighted by the mass the second
+        codebook can reach from it (``wkk``), then the second code given the first.  Returns (bucket [Q, n], logit [Q, n]) where
+        the logit q0.c0[k0] + q1.c1[k1] is the un-normalised log-probability of the bucket.  RNG: one
+        ``multinomial(.., n, replacement=True)`` over [Q, K], then one ``multinomial(.., 1)`` over [Q*n, K] -- the
+        reference's calls in the reference's order."""
+        half0, half1 = flat_query.chunk(2, dim=-1)
+        logit1 = half1 @ self.c1.T                                  # [Q, K]
+        prob1 = torch.softmax(logit1, dim=-1)
+        logit0 = half0 @ self.c0.T
+        prob0 = torch.softmax(logit0, dim=-1)
+        first_w = (prob1 @ self.wkk.T) * prob0                      # mass reachable through each first code
+        code0 = torch.multinomial(first_w, num_neg, replacement=True)
+        second_w = self.wkk[code0, :] * prob1.unsqueeze(1)          # [Q, n, K]
+        code1 = torch.multinomial(second_w.view(-1, second_w.size(-1)), 1).squeeze(-1).view(*second_w.shape[:-1])
+        logit = torch.gather(logit0, -1, code0) + torch.gather(logit1, -1, code1)
+        return code0 * self.K + code1, logit
+
     def forward(self, query, num_neg, pos_items=None):
         with torch.no_grad():
             if self._is_cosine():
                 query = F.normalize(query, dim=-1)
-            q0, q1 = query.view(-1, query.size(-1)).chunk(2, dim=-1)
-            r1 = q1 @ self.c1.T
-            r1s = torch.softmax(r1, dim=-1)
-            r0 = q0 @ self.c0.T
-            r0s = torch.softmax(r0, dim=-1)
-            s0 = (r1s @ self.wkk.T) * r0s
-            k0 = torch.multinomial(s0, num_neg, replacement=True)
-            p0 = torch.gather(r0, -1, k0)
-            subwkk = self.wkk[k0, :]
-            s1 = subwkk * r1s.unsqueeze(1)
-            k1 = torch.multinomial(s1.view(-1, s1.size(-1)), 1).squeeze(-1).view(*s1.shape[:-1])
-            p1 = torch.gather(r1, -1, k1)
-            k01 = k0 * self.K + k1
-            p01 = p0 + p1
-            neg_items, neg_prob = self.sample_item(k01, p01)
-            if pos_items is not None:
-                pos_prob = self.compute_item_p(query, pos_items)
-                return pos_prob, neg_items.view(*query.shape[:-1], -1), neg_prob.view(*query.shape[:-1], -1)
-            return neg_items.view(*query.shape[:-1], -1), neg_prob.view(*query.shape[:-1], -1)
+            bucket, logit = self._draw_buckets(query.view(-1, query.size(-1)), num_neg)
+            neg_items, neg_prob = self.sample_item(bucket, logit)
+            lead = query.shape[:-1]
+            neg_items, neg_prob = neg_items.view(*lead, -1), neg_prob.view(*lead, -1)
+            if pos_items is None:
+                return neg_items, neg_prob
+            return self.compute_item_p(query, pos_items), neg_items, neg_prob
 
-    def compute_item_p(self, query, pos_items):                                  # :367-393
-        pos_items_ = pos_items.unsqueeze(1) if pos_items.dim() == 1 else pos_items
-        k0 = self.cd0[pos_items_]
-        k1 = self.cd1[pos_items_]
-        c0 = self.c0_[k0, :]
-        c1 = self.c1_[k1, :]
-        q0, q1 = query.chunk(2, dim=-1)
-        if query.dim() == pos_items_.dim():
-            r = (torch.bmm(c0, q0.unsqueeze(-1)) + torch.bmm(c1, q1.unsqueeze(-1))).squeeze(-1)
-        else:
-            r = torch.bmm(q0, c0.transpose(1, 2)) + torch.bmm(q1, c1.transpose(1, 2))
-            pos_items_ = pos_items_.unsqueeze(1)
-        if not hasattr(self, "p"):
-            return r.view_as(pos_items)
-        return (r + torch.log(self.p[pos_items_])).view_as(pos_items)
+    def compute_item_p(self, query, pos_items):
+        """Proposal log-probability (up to the per-query constant) of given items (sampler.py:367-393): the logit of the
+        item's bucket, plus log of its in-bucket weight when the final draw is weighted.  Index 0 (padding) maps to the
+        all-zero centre prepended in ``c0_`` / ``c1_``."""
+        ids = pos_items.unsqueeze(1) if pos_items.dim() == 1 else pos_items
+        cent0 = self.c0_[self.cd0[ids], :]                          # [B, L, d/2]
+        cent1 = self.c1_[self.cd1[ids], :]
+        half0, half1 = query.chunk(2, dim=-1)
+        if query.dim() == ids.dim():                                # one query per row, L candidate items
+            logit = (torch.bmm(cent0, half0.unsqueeze(-1)) + torch.bmm(cent1, half1.unsqueeze(-1))).squeeze(-1)
+        else:                                                       # [B, Lq, d] queries against [B, L] items
+            logit = torch.bmm(half0, cent0.transpose(1, 2)) + torch.bmm(half1, cent1.transpose(1, 2))
+            ids = ids.unsqueeze(1)
+        if hasattr(self, "p"):
+            logit = logit + torch.log(self.p[ids])
+        return logit.view_as(pos_items)
 
 
 class FusedMIDXSamplerPop(FusedMIDXSamplerUniform):
@@ -286,32 +293,30 @@ class FusedClusterSamplerUniform(_IndexedSampler):
         with torch.no_grad():
             if self._is_cosine():
                 query = F.normalize(query, dim=-1)
-            q = query.view(-1, query.size(-1))
-            r = q @ self.c.T
-            rs = torch.softmax(r, dim=-1)
-            k = torch.multinomial(rs, num_neg, replacement=True)
-            p = torch.gather(r, -1, k)
-            neg_items, neg_prob = self.sample_item(k, p, pos_items)
-            if pos_items is not None:
-                pos_prob = self.compute_item_p(query, pos_items)
-                return pos_prob, neg_items.view(*query.shape[:-1], -1), neg_prob.view(*query.shape[:-1], -1)
-            return neg_items.view(*query.shape[:-1], -1), neg_prob.view(*query.shape[:-1], -1)
+            logit_all = query.view(-1, query.size(-1)) @ self.c.T                      # [Q, K]   (sampler.py:462-466)
+            bucket = torch.multinomial(torch.softmax(logit_all, dim=-1), num_neg, replacement=True)
+            neg_items, neg_prob = self.sample_item(bucket, torch.gather(logit_all, -1, bucket), pos_items)
+            lead = query.shape[:-1]
+            neg_items, neg_prob = neg_items.view(*lead, -1), neg_prob.view(*lead, -1)
+            if pos_items is None:
+                return neg_items, neg_prob
+            return self.compute_item_p(query, pos_items), neg_items, neg_prob
 
-    def compute_item_p(self, query, pos_items):                                  # :473-490
+    def compute_item_p(self, query, pos_items):
+        """sampler.py:473-490: logit of the item's cluster (+ log of its in-cluster weight).  Unlike the reference, the
+        weight term is reshaped to the items' shape, so 1-D positives work with a popularity table (the reference adds
+        [B] + [B, 1] there and then fails in ``view_as``)."""
         shape = pos_items.shape
-        if pos_items.dim() == 1:
-            pos_items = pos_items.view(-1, 1)
-        k = self.cd[pos_items]
-        c = self.c_[k, :]
-        if query.dim() == pos_items.dim():
-            r = torch.bmm(c, query.unsqueeze(-1)).squeeze(-1)
+        ids = pos_items.view(-1, 1) if pos_items.dim() == 1 else pos_items
+        cent = self.c_[self.cd[ids], :]
+        if query.dim() == ids.dim():
+            logit = torch.bmm(cent, query.unsqueeze(-1)).squeeze(-1)
         else:
-            r = torch.bmm(query, c.transpose(1, 2))
-            pos_items = pos_items.unsqueeze(1)
-        r = r.reshape(*shape)
-        if not hasattr(self, "p"):
-            return r
-        return r + torch.log(self.p[pos_items]).reshape(*shape)
+            logit = torch.bmm(query, cent.transpose(1, 2))
+        logit = logit.reshape(*shape)
+        if hasattr(self, "p"):
+            logit = logit + torch.log(self.p[pos_items])
+        return logit
 
 
 class FusedClusterSamplerPop(FusedClusterSamplerUniform):
