@@ -195,7 +195,8 @@ typedef struct rsb200_pair_args {
                                       * (same results, different memory schedule): 1 software-pipelined forward, 2 TMA
                                       * (cp.async.bulk) ring, 3 L2 prefetch, 4 forward compiled for 4 CTAs/SM, 6 CSR offsets
                                       * looked up inside the forward kernel (no resolve pass), 16..31 L2 eviction-priority
-                                      * hints (bit 0 rows evict_first, bit 1 offsets, bit 2 entries evict_last, bit 3 scatter),
+                                      * hints (bit 0 rows evict_first, bit 1 offsets, bit 2 entries evict_last, bit 3 scatter), 7 staged
+                                      * entries + permute pass (needs cstage),
                                       * 40..44 scatter occupancy / unroll.  32 = timing diagnostic WITHOUT the entry list:
                                       * the gradients it produces are invalid. */
     /* RSB200_SINK_APPLY ("fuse into the scatter epilogue"): PHASE_SCATTER applies the optimizer update of
@@ -210,6 +211,12 @@ typedef struct rsb200_pair_args {
     int32_t opt_kind;                /* 0 SGD, 1 Adagrad, 2 SparseAdam (semantics of rsb200_rows_update) */
     float   opt_lr, opt_beta1, opt_beta2, opt_eps;
     float   opt_step_size;           /* SparseAdam: lr * sqrt(1 - beta2^t) / (1 - beta1^t)   */
+    float*  cstage;                  /* [B * n] or NULL; used by variant 7 only (A/B): PHASE_FWD writes each negative's
+                                      * coefficient / logit here in touch order (coalesced) and PHASE_SCATTER starts with a
+                                      * permute pass that moves them to their row-grouped entry positions -- instead of one
+                                      * random 8-byte write per touch inside the row stream.  Measured at config 2: forward
+                                      * 0.786 -> 0.703 ms, permute pass +0.097 ms: the random writes cost the same wherever
+                                      * they run, so the direct write stays the default. */
 } rsb200_pair_args;
 
 /* Fills the size fields a caller needs to allocate the workspace of a

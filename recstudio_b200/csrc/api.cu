@@ -162,6 +162,8 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         p.loss_scale = (float)(1.0 / (denom > 0 ? denom : 1.0));
         p.prefetch = (a->variant == 3) ? 1 : 0;
         p.slot_abs = (a->variant != 6) ? 1 : 0;
+        // variant 7: staged entries + permute pass (measured: forward -0.08 ms, permute +0.10 ms -- not the default)
+        p.cstage = (a->cstage && a->variant == 7) ? a->cstage : nullptr;
         p.hint = (a->variant >= 16 && a->variant < 32) ? (a->variant & 7) : 0;   // variants 16..31: L2 eviction hints
         if (a->variant == 32) p.hint = 8;    // timing diagnostic: skip the offset lookups / entry writes (gradients invalid)
         p.ncount = nullptr; p.sp_in = nullptr; p.stats_part = nullptr;
@@ -172,6 +174,11 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         if (rc) return rc;
     }
     if (phases & RSB200_PHASE_SCATTER) {
+        if (a->cstage && a->variant == 7) {
+            rc = launch_permute_entries(a->slot_neg, a->cstage, B * n, n, a->loss_kind == RSB200_LOSS_BPR ? kDirect : 0u,
+                                        a->ent_item, st);
+            if (rc) return rc;
+        }
         ScatterParams s;
         s.off = a->off_item; s.urow = a->urow_item; s.totals = a->totals; s.ent = a->ent_item; s.src = a->q_buf;
         s.lse = a->lse; s.w = a->w_item; s.gscale = a->grad_scale_dev; s.rows_out = a->item_rows; s.vals = a->item_vals; s.D = (int)a->d;

@@ -76,6 +76,38 @@ int32_t launch_resolve(const int32_t* ids, uint32_t* slot, const uint32_t* off, 
     return 0;
 }
 
+// ent[epos[i]] = (query of touch i | flag, staged value): the forward kernel leaves the per-touch coefficient / logit
+// in touch order (a coalesced store inside its row stream); this pass moves them to their row-grouped positions.  Run on
+// its own, the 67 MB entry list stays L2-resident, so the 8-byte random writes merge in L2 and reach DRAM as full lines --
+// inside the forward kernel every one of them was a read-modify-write of a 32-byte sector.
+__global__ void __launch_bounds__(256)
+permute_entries_kernel(const uint32_t* __restrict__ epos, const float* __restrict__ cstage, int64_t M, int64_t n, uint32_t flag,
+                       uint64_t* __restrict__ ent) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s[kCountPer]; float v[kCountPer];
+#pragma unroll
+    for (int k = 0; k < kCountPer; ++k) {
+        const int64_t i = i0 + k * stride;
+        s[k] = i < M ? __ldg(epos + i) : kNoSlot;
+        v[k] = i < M ? __ldg(cstage + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kCountPer; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (s[k] != kNoSlot)
+            ent[s[k]] = (uint64_t)((uint32_t)(i / n) | flag) | ((uint64_t)__float_as_uint(v[k]) << 32);
+    }
+}
+
+int32_t launch_permute_entries(const uint32_t* epos, const float* cstage, int64_t M, int64_t n, uint32_t flag, uint64_t* ent,
+                               cudaStream_t st) {
+    if (M == 0) return 0;
+    permute_entries_kernel<<<(unsigned)cdiv(M, 256 * kCountPer), 256, 0, st>>>(epos, cstage, M, n, flag, ent);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------- scan
 // 3-phase scan over u32 counts.  Each block owns a tile of kTile elements; the packed
 // u64 carries (sum of counts) in the low and (number of non-empty rows) in the high word.

@@ -18,6 +18,7 @@ struct FwdParams {
     float loss_scale;   // 1 / (B n)              for BPR, 1 / B              for SSM
     int prefetch;       // variant 3: L2-prefetch the next batch's rows
     int slot_abs;       // slot_neg already holds absolute entry positions (group.cu resolve_kernel)
+    float* cstage;      // [B, n] staged coefficients / logits in touch order (entries are permuted later), or null
     int hint;           // L2 eviction hints: bit 0 rows evict_first, bit 1 offsets evict_last, bit 2 entries evict_last
     // owner-compute (PARTIAL) mode of the row-sharded step, see shard.cu
     const int32_t* ncount;   // [B] length of each query's compacted negative list (stride n)
@@ -53,6 +54,8 @@ template <typename IdT>
 int32_t launch_count(const IdT* ids, int64_t M, int64_t num_rows, uint32_t* cnt, uint32_t* slot,
                      int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st);
 int32_t launch_resolve(const int32_t* ids, uint32_t* slot, const uint32_t* off, int64_t M, cudaStream_t st);
+int32_t launch_permute_entries(const uint32_t* epos, const float* cstage, int64_t M, int64_t n, uint32_t flag, uint64_t* ent,
+                               cudaStream_t st);
 int32_t launch_scan(uint32_t* cnt_off, int64_t num_rows, uint32_t* urow, int64_t cap, uint32_t* totals,
                     uint64_t* tmp, int64_t tmp_elems, cudaStream_t st);
 // pair_fwd.cu

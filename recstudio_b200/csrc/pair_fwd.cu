@@ -428,7 +428,9 @@ pair_fwd_kernel(const FwdParams p) {
             }
             if (valid) {
                 if (p.neg_score) p.neg_score[rowbase + jb + lane] = st.sc_out;
-                if (cur.slot != kNoSlot) {
+                if (p.cstage) {
+                    p.cstage[rowbase + jb + lane] = st.val_out;          // touch order: coalesced; permuted into ent later
+                } else if (cur.slot != kNoSlot) {
                     const uint64_t en = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
                     if (HINT) stg64_hint(p.ent_item + epos, en, pol_ent);
                     else p.ent_item[epos] = en;

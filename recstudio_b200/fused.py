@@ -31,7 +31,7 @@ class PairWorkspace:
     """
 
     def __init__(self, num_items: int, num_users: int, B: int, n: int, d: int, device,
-                 sink: str = "compact", want_scores: bool = False, cap_item: Optional[int] = None,
+                 sink: str = "compact", want_scores: bool = False, stage_entries: bool = False, cap_item: Optional[int] = None,
                  alloc_vals: bool = True):
         _lib.require_cuda()
         self.device = torch.device(device)
@@ -76,6 +76,7 @@ class PairWorkspace:
             self.user_vals = None
         self.pos_score = torch.empty(max(B, 1), dtype=f32, device=dev) if want_scores else None
         self.neg_score = torch.empty(max(B, 1), max(n, 1), dtype=f32, device=dev) if want_scores else None
+        self.cstage = torch.empty(max(B * n, 1), dtype=f32, device=dev) if stage_entries else None   # variant 7 only
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
@@ -120,6 +121,7 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
         logq_neg = logq_neg.to(torch.float32).contiguous()
     a.logq_pos, a.logq_neg = ptr(logq_pos), ptr(logq_neg)
     a.loss, a.pos_score, a.neg_score = ptr(ws.loss), ptr(ws.pos_score), ptr(ws.neg_score)
+    a.cstage = ptr(ws.cstage) if variant == 7 else 0          # variant 7 (A/B): staged entries + permute pass, see rsb200.h
     dense = ws.sink == "dense" and apply is None
     keep_states = ()
     if apply is not None:

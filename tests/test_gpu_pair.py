@@ -33,7 +33,8 @@ def _run(w_item, w_user, user, pos, neg, loss, scorer, lqp=None, lqn=None, sink=
     p = torch.as_tensor(pos, dtype=torch.int64).to(dev)
     ng = torch.as_tensor(neg).to(dev).to(neg_dtype).contiguous()
     B, n = ng.shape
-    ws = fused.PairWorkspace(wi.shape[0], wu.shape[0], B, n, wi.shape[1], dev, sink=sink, want_scores=want_scores)
+    ws = fused.PairWorkspace(wi.shape[0], wu.shape[0], B, n, wi.shape[1], dev, sink=sink, want_scores=want_scores,
+                             stage_entries=(variant == 7))
     kw = {}
     if lqp is not None:
         kw["logq_pos"] = torch.as_tensor(lqp).to(dev)
@@ -97,7 +98,7 @@ def test_dense_sink_and_int32_ids(name):
     _check_grads(out, g["d_item"], g["d_user"])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 17, 19, 22, 23, 31])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 7, 17, 19, 22, 23, 31])
 @pytest.mark.parametrize("name", ["step_d128_bpr_ip", "step_d128_ssm_eu", "step_d64dup_ssm_ip"])
 def test_kernel_variants_match_golden(name, variant):
     """The experimental forward variants (rsb200_pair_args.variant: 1 pipelined, 2 TMA ring, 3 L2 prefetch,

@@ -33,7 +33,7 @@ def main():
     wu = torch.empty(a.U, a.d, device=dev).normal_(0, 0.1); wu[0] = 0
     user = torch.randint(1, a.U, (a.B,), device=dev)
     pos = torch.randint(1, a.N, (a.B,), device=dev)
-    ws = fused.PairWorkspace(a.N, a.U, a.B, a.n, a.d, dev)
+    ws = fused.PairWorkspace(a.N, a.U, a.B, a.n, a.d, dev, stage_entries=True)
     pop = None
     if a.sampler == "popular":
         import numpy as np
