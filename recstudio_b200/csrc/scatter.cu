@@ -119,13 +119,23 @@ scatter_kernel(const ScatterParams p) {
                     csum += cc[k];
                     if (PLAIN && FULL) {
                         if ((lastmask >> (t0 + k)) & 1u) {             // warp-uniform: the current row is complete
+                            if (OPT >= 0) {                            // RSB200_SINK_APPLY: update W[row] in place
+                                const uint32_t rr = __shfl_sync(kFull, r, cur);
 #pragma unroll
-                            for (int x = 0; x < VPL; ++x) {
-                                if (HINT) stg128_stream_hint(dst_run + x * 128, acc[x], pol_first);
-                                else stg128_stream(dst_run + x * 128, acc[x]);
-                                acc[x] = make_float4(0, 0, 0, 0);
+                                for (int x = 0; x < VPL; ++x) {
+                                    apply_update<OPT>(p, (size_t)rr * D + lane * 4 + x * 128, acc[x]);
+                                    acc[x] = make_float4(0, 0, 0, 0);
+                                }
+                                ++cur;
+                            } else {
+#pragma unroll
+                                for (int x = 0; x < VPL; ++x) {
+                                    if (HINT) stg128_stream_hint(dst_run + x * 128, acc[x], pol_first);
+                                    else stg128_stream(dst_run + x * 128, acc[x]);
+                                    acc[x] = make_float4(0, 0, 0, 0);
+                                }
+                                dst_run += D;                          // compact sink: rows of the chunk are consecutive
                             }
-                            dst_run += D;                              // compact sink: rows of the chunk are consecutive
                         }
                     } else if ((lastmask >> (t0 + k)) & 1u) {          // warp-uniform: row `cur` is complete
                         uint32_t rr = 0;
@@ -181,6 +191,12 @@ loss_sum_kernel(const float* __restrict__ part, int B, float* __restrict__ loss)
 
 template <int VPL>
 static void launch_scatter_v(const ScatterParams& p, unsigned blocks, cudaStream_t st) {
+    if (p.opt >= 0 && !p.euclid && p.D == 128 * VPL) {      // RSB200_SINK_APPLY on full rows: the specialised body
+        if (p.opt == 0) scatter_kernel<VPL, true, false, 4, 4, true, 0><<<blocks, kScatWarps * 32, 0, st>>>(p);
+        else if (p.opt == 1) scatter_kernel<VPL, true, false, 4, 4, true, 1><<<blocks, kScatWarps * 32, 0, st>>>(p);
+        else scatter_kernel<VPL, true, false, 4, 4, true, 2><<<blocks, kScatWarps * 32, 0, st>>>(p);
+        return;
+    }
     if (p.opt >= 0) {               // RSB200_SINK_APPLY: generic (non-PLAIN) body with the update in the epilogue
         if (p.opt == 0) scatter_kernel<VPL, false, false, 4, 4, false, 0><<<blocks, kScatWarps * 32, 0, st>>>(p);
         else if (p.opt == 1) scatter_kernel<VPL, false, false, 4, 4, false, 1><<<blocks, kScatWarps * 32, 0, st>>>(p);
