@@ -19,6 +19,8 @@ reference's own ``nn.TransformerEncoder`` path runs instead (exact semantics are
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 import torch.nn.functional as F
 from torch import Tensor
@@ -126,7 +128,33 @@ class FusedSASRecQueryEncoder(torch.nn.Module):
         if not need_pooling:
             return out
         ptype = self.training_pooling_type if self.training else self.eval_pooling_type
-        if ptype != "last":
-            raise _lib.Rsb200Error("FusedSASRecQueryEncoder implements 'last' pooling (SASRec); got %r" % ptype)
-        idx = (batch["seqlen"] - 1).clamp(min=0).view(-1, 1, 1).expand(-1, 1, out.size(-1))     # layers.py:307-311
-        return out.gather(1, idx).squeeze(1)
+        return pool_sequence(out, batch["seqlen"], ptype, batch.get("mask_token") if ptype == "mask" else None)
+
+
+POOLING_TYPES = ("origin", "mask", "concat", "sum", "mean", "max", "last")
+
+
+def pool_sequence(seq_out: Tensor, seqlen: Tensor, pooling_type: str = "last", mask_token: Optional[Tensor] = None):
+    """``SeqPoolingLayer.forward`` (recstudio/model/module/layers.py:256-314, keepdim=False, 3-D input) on the encoder
+    output [B, L, D]: 'last' = position seqlen-1 (SASRec), 'mask' = the rows selected by the boolean [B, L] ``mask_token``
+    (BERT4Rec training: one row per masked position, bert4rec.py:46-58), 'origin' / 'concat' / 'sum' / 'mean' / 'max' =
+    the reference's reductions over the first ``seqlen`` positions with padded positions zeroed first."""
+    if pooling_type not in POOLING_TYPES:
+        raise ValueError("pooling_type can only be one of %s but %s is given." % (list(POOLING_TYPES), pooling_type))
+    B, L, D = seq_out.shape
+    if pooling_type == "mask":
+        assert mask_token is not None, "mask_token can be None when pooling_type is 'mask'."
+        return seq_out[mask_token]
+    if pooling_type == "last":
+        idx = (seqlen - 1).view(-1, 1, 1).expand(-1, -1, D)
+        return seq_out.gather(dim=1, index=idx).squeeze(1)
+    valid = torch.arange(L, device=seq_out.device).view(1, L, 1) < seqlen.view(-1, 1, 1)
+    kept = seq_out.masked_fill(~valid, 0.0)
+    if pooling_type == "origin":
+        return kept
+    if pooling_type == "concat":
+        return kept.reshape(B, -1)
+    if pooling_type == "max":
+        return kept.max(dim=1)                      # the reference returns torch's (values, indices) pair here
+    total = kept.sum(dim=1)
+    return total if pooling_type == "sum" else total / seqlen.view(-1, 1)

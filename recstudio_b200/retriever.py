@@ -321,18 +321,21 @@ def build_synthetic(num_users: int, num_items: int, d: int, n, loss: str = "bpr"
 
 def build_sasrec_synthetic(num_items: int, d: int, n: int, max_seq_len: int = 200, n_head: int = 2, hidden_size: int = 128,
                            n_layer: int = 2, dropout: float = 0.0, loss: str = "ssm", fused_grad: str = "dense",
-                           device="cuda:0", init_std: float = 0.02, seed: int = 2022) -> FusedRetriever:
+                           device="cuda:0", init_std: float = 0.02, seed: int = 2022, bidirectional: bool = False,
+                           training_pooling_type: str = "last") -> FusedRetriever:
     """SASRec (recstudio/model/seq/sasrec.py:70-123) on the fused path without a dataset object: the item
     tower is a FusedEmbedding shared with the FusedSASRecQueryEncoder (sasrec.py:107), the head is the fused
     sampled-softmax / BPR step (BASELINE config 3).  Batches: {'in_item_id' [B, L], 'seqlen' [B], 'item_id' [B]}."""
     from . import attention
-    loss_m = plugins.FusedBPRLoss() if loss == "bpr" else plugins.FusedSampledSoftmaxLoss()
+    loss_m = {"bpr": plugins.FusedBPRLoss, "ssm": plugins.FusedSampledSoftmaxLoss, "softmax": plugins.FusedSoftmaxLoss}[loss]()
     item = plugins.FusedEmbedding(num_items, d, padding_idx=0)
     enc = attention.FusedSASRecQueryEncoder(fiid="item_id", embed_dim=d, max_seq_len=max_seq_len, n_head=n_head,
                                             hidden_size=hidden_size, dropout=dropout, activation="gelu", layer_norm_eps=1e-12,
-                                            n_layer=n_layer, item_encoder=item)
-    kwargs = dict(item_encoder=item, query_encoder=enc, scorer=plugins.FusedInnerProductScorer(),
-                  sampler=plugins.FusedUniformSampler(num_items), loss=loss_m)
+                                            n_layer=n_layer, item_encoder=item, bidirectional=bidirectional,
+                                            training_pooling_type=training_pooling_type)
+    kwargs = dict(item_encoder=item, query_encoder=enc, scorer=plugins.FusedInnerProductScorer(), loss=loss_m)
+    if loss != "softmax":                      # full-softmax models (BERT4Rec) have no sampler (bert4rec.py:43-44)
+        kwargs["sampler"] = plugins.FusedUniformSampler(num_items)
     if iface.HAVE_RECSTUDIO:
         from recstudio.utils import get_model
         conf = get_model("SASRec")[1]
@@ -343,7 +346,9 @@ def build_sasrec_synthetic(num_items: int, d: int, n: int, max_seq_len: int = 20
         m.item_fields, m.neg_count = {"item_id"}, n
     else:
         m = FusedRetriever({"model": {"embed_dim": d}, "train": {"negative_count": n, "seed": seed}}, fused_grad=fused_grad, **kwargs)
-    m.query_fields = {"in_item_id", "seqlen"}
+    m.query_fields = {"in_item_id", "seqlen"} | ({"mask_token"} if training_pooling_type == "mask" else set())
+    if loss == "softmax":
+        m.sampler = None
     m = m.to(device)
     with torch.no_grad():      # init_method: normal (seq/config/sasrec.yaml:11, init.py:18-27), padding row re-zeroed
         g = torch.Generator(device=device).manual_seed(seed)
@@ -352,3 +357,11 @@ def build_sasrec_synthetic(num_items: int, d: int, n: int, max_seq_len: int = 20
                 p.normal_(0, init_std, generator=g)
         m.item_encoder.weight[0] = 0
     return m
+
+
+def build_bert4rec_synthetic(num_items: int, d: int, **kw) -> FusedRetriever:
+    """BERT4Rec (recstudio/model/seq/bert4rec.py:8-58) on the fused kernels: the SASRec encoder with bidirectional attention and
+    'mask' pooling, the item table extended by the mask-token row (id ``num_items``), full-catalog SoftmaxLoss, no sampler.
+    Batches: {'in_item_id' [B, L] (masked positions hold the mask token), 'seqlen' [B], 'mask_token' bool [B, L],
+    'item_id' [number of masked positions]} -- what ``_reconstruct_train_data`` produces."""
+    return build_sasrec_synthetic(num_items + 1, d, 0, loss="softmax", bidirectional=True, training_pooling_type="mask", **kw)

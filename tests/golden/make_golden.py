@@ -436,10 +436,30 @@ def golden_midx():
     save("midx", **out)
 
 
+def golden_pooling():
+    """SeqPoolingLayer (recstudio/model/module/layers.py:247-314) for every pooling type the SASRec / BERT4Rec query
+    encoder can be configured with."""
+    from recstudio.model import module as rs_module
+    g = torch.Generator().manual_seed(77)
+    B, L, D = 7, 9, 12
+    x = torch.randn(B, L, D, generator=g)
+    seqlen = torch.randint(1, L + 1, (B,), generator=g)
+    mask_token = torch.rand(B, L, generator=g) < 0.3
+    out = dict(x=x, seqlen=seqlen, mask_token=mask_token)
+    for ptype in ("origin", "mask", "concat", "sum", "mean", "max", "last"):
+        layer = rs_module.SeqPoolingLayer(pooling_type=ptype)
+        r = layer(x, seqlen, mask_token=mask_token if ptype == "mask" else None)
+        if ptype == "max":
+            out["max_values"], out["max_indices"] = r.values, r.indices
+        else:
+            out[ptype] = r
+    save("pooling", **out)
+
+
 if __name__ == "__main__":
     ALL = [golden_appendix_a, golden_training_steps, golden_popular, golden_uniform_cpu, golden_topk_eval,
            golden_full_softmax, golden_masked_uniform, golden_sampling_methods,
-           golden_midx]
+           golden_midx, golden_pooling]
     want = sys.argv[1:]                       # optional: names of the generators to (re)run
     for fn in ALL:
         if not want or fn.__name__ in want:

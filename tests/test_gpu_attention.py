@@ -184,3 +184,47 @@ def test_sasrec_fused_head_training_step(mode):
     want = ref["d_item"]
     sel = head_only & (want.abs().sum(-1) > 0)
     assert (gi.cpu()[sel] - want[sel]).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
+def test_bert4rec_masked_training_step():
+    """BERT4Rec on the fused kernels (bert4rec.py:8-58): bidirectional tcgen05 attention, 'mask' pooling (one query per
+    masked position), the item table extended by the mask-token row, full-catalog SoftmaxLoss through
+    rsb200_fullsoftmax_fwd_bwd.  The loss must equal torch's logsumexp loss on the SAME pooled queries (1e-5), the rows of
+    the table that no input sequence touches must receive exactly the softmax head's gradient, and the encoder must
+    get its gradient through d loss / d query."""
+    from recstudio_b200 import retriever
+    N, d, Lq, B = 5_000, 128, 64, 24
+    m = retriever.build_bert4rec_synthetic(N, d, max_seq_len=Lq, device=DEV, init_std=0.1)
+    assert m.item_encoder.weight.shape[0] == N + 1 and m.sampler is None and m.query_encoder.bidirectional
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    seqlen = torch.randint(2, Lq + 1, (B,), device=DEV, generator=gen)
+    real = torch.arange(Lq, device=DEV)[None, :] < seqlen[:, None]
+    ids = torch.randint(1, N, (B, Lq), device=DEV, generator=gen) * real
+    # _reconstruct_train_data (bert4rec.py:46-58): mask a fifth of the real positions, targets = the original tokens
+    masked = (torch.rand(B, Lq, device=DEV, generator=gen) < 0.2) & real
+    masked[:, 0] |= ~masked.any(1)                                   # at least one masked position per sequence
+    target = ids[masked]
+    ids = ids.masked_fill(masked, N)                                 # the mask token is id N (the extra table row)
+    batch = {"in_item_id": ids, "seqlen": seqlen, "mask_token": masked, "item_id": target,
+             "rating": torch.ones(target.numel(), device=DEV)}
+    m.train()
+    loss = m.training_step(batch)
+    assert type(loss.grad_fn).__name__.startswith("_FullSoftmaxFn")
+    loss.backward()
+    with torch.no_grad():
+        query = m.query_encoder(batch)                               # [number of masked positions, d]
+    assert query.shape == (int(masked.sum()), d)
+    w = m.item_encoder.weight.detach()
+    scores = query.double() @ w[1:].double().T
+    want = (torch.logsumexp(scores, -1) - (query.double() * w[target].double()).sum(-1)).mean()
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item())
+    gi = m.item_encoder.weight.grad
+    assert torch.isfinite(gi).all() and float(gi[0].abs().sum()) == 0.0
+    p = torch.softmax(scores, -1)
+    p[torch.arange(target.numel(), device=DEV), target - 1] -= 1.0
+    head = torch.zeros(N + 1, d, dtype=torch.float64, device=DEV)
+    head[1:] = p.T @ query.double() / target.numel()
+    untouched = torch.ones(N + 1, dtype=torch.bool, device=DEV); untouched[ids.unique()] = False; untouched[0] = False
+    assert (gi[untouched].double() - head[untouched]).abs().max().item() <= 1e-5 * head.abs().max().item()
+    g_in = m.query_encoder.transformer_layer.layers[0].self_attn.in_proj_weight.grad
+    assert g_in is not None and torch.isfinite(g_in).all() and g_in.abs().max().item() > 0

@@ -200,3 +200,21 @@ def test_c_abi_from_plain_c(tmp_path):
                     "-L", libdir, "-lrsb200", "-Wl,-rpath," + libdir], check=True, capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "abi ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_sequence_pooling_matches_reference_golden():
+    """attention.pool_sequence == the reference's SeqPoolingLayer for all seven pooling types (tests/golden/pooling.npz);
+    device-agnostic torch plumbing around the attention kernels, so it is checked here on the CPU."""
+    import numpy as np
+    from conftest import load_golden
+    from recstudio_b200 import attention
+    g = load_golden("pooling")
+    x, seqlen, mask = torch.from_numpy(g["x"]), torch.from_numpy(g["seqlen"]), torch.from_numpy(g["mask_token"])
+    for ptype in ("origin", "mask", "concat", "sum", "mean", "last"):
+        got = attention.pool_sequence(x, seqlen, ptype, mask if ptype == "mask" else None)
+        np.testing.assert_array_equal(got.numpy(), g[ptype])
+    mx = attention.pool_sequence(x, seqlen, "max")
+    np.testing.assert_array_equal(mx.values.numpy(), g["max_values"])
+    np.testing.assert_array_equal(mx.indices.numpy(), g["max_indices"])
+    with pytest.raises(ValueError):
+        attention.pool_sequence(x, seqlen, "first")
