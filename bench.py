@@ -316,10 +316,15 @@ def run_sharded(args):
 
     def step(u, p_, ev=None):
         """one pass of the hot path over one batch; ev brackets the owner-compute forward kernel"""
-        neg = draw()
         q = sharded.CudaOps.gather_rows(wu, u)
-        q_all, pos_all, neg_all = (sharded._all_gather_cat(t) for t in (q, p_, neg))
-        eng.bind(q_all, pos_all, neg_all, _lib.LOSS_BPR, _lib.SCORE_IP)
+        if args.c5_sampler == "uniform":     # owners regenerate every rank's UniformSampler draw: no id exchange
+            state = sharded.uniform_regen_state(dev, BATCH, NEG)
+            q_all, pos_all = (sharded._all_gather_cat(t) for t in (q, p_))
+            eng.bind(q_all, pos_all, None, _lib.LOSS_BPR, _lib.SCORE_IP, regen_state=state)
+        else:
+            neg = draw()
+            q_all, pos_all, neg_all = (sharded._all_gather_cat(t) for t in (q, p_, neg))
+            eng.bind(q_all, pos_all, neg_all, _lib.LOSS_BPR, _lib.SCORE_IP)
         sp = eng.prep()
         dist.all_reduce(sp)
         if ev: ev[0].record()

@@ -425,6 +425,13 @@ typedef struct rsb200_shard_args {
     float   grad_scale;         /* upstream gradient (loss.backward() => 1.0)                  */
     int32_t world, rank;        /* number of owners, index of this owner in stats_all          */
     int32_t loss_kind, score_kind, sink, accumulate;
+    /* Owner-side regeneration of the UniformSampler draw (optional; neg may then be NULL): instead of all-gathering the
+     * 4-byte negative ids of every rank, every owner recomputes them from the ranks' generator states -- rank r's ids are
+     * exactly what rsb200_sample_uniform(seed[r], offset[r], num_items, regen_B, n) would write, i.e. what
+     * torch.randint(1, num_items, (regen_B, n), device='cuda') returns on rank r.  Query g belongs to rank g / regen_B. */
+    const uint64_t* regen_state;   /* DEVICE [world, 2] = (seed, philox offset) of every rank, or NULL (ids given in neg) */
+    int64_t regen_B;               /* queries per rank (G == world * regen_B)                   */
+    int32_t regen_sm_count, regen_max_threads_per_sm;   /* ATen draw policy, as for rsb200_sample_uniform */
 } rsb200_shard_args;
 
 int32_t rsb200_shard_step(const rsb200_shard_args* args, int32_t phases, void* stream);

@@ -48,7 +48,21 @@ struct PrepParams {
     uint32_t* err;
     int64_t num_items, row0, local_rows;
     int G, n, D, euclid;
+    // owner-side regeneration of the uniform draw (regen_state != null): ids are recomputed, `neg` is not read
+    const uint64_t* regen_state;   // [world, 2] (seed, philox offset)
+    int64_t regen_T;               // 256 * grid of the ATen kernel for numel = regen_B * n
+    int regen_B;
 };
+
+// id of element li of the draw torch.randint(1, num_items, (B, n)) for generator state (seed, offset): ATen thread
+// idx = li mod T draws curand4 in round (li / T) / 4 and hands word (li / T) % 4 to this element (sampler.cu).
+__device__ __forceinline__ int32_t regen_uniform_id(uint64_t seed, uint64_t offset, int64_t li, int64_t T, uint32_t range) {
+    const int64_t q = li / T, idx = li - q * T;
+    const uint4 w = Philox::gen(seed, (uint64_t)idx, offset / 4 + (uint64_t)(q >> 2));
+    const int ii = (int)(q & 3);
+    const uint32_t word = ii == 0 ? w.x : (ii == 1 ? w.y : (ii == 2 ? w.z : w.w));
+    return (int32_t)(word % range + 1u);
+}
 
 // one warp per query
 __global__ void __launch_bounds__(kPrepWarps * 32)
@@ -83,6 +97,14 @@ shard_prep_kernel(const PrepParams p) {
     const size_t base = (size_t)b * p.n;
     int kept = 0;
     bool bad = false;
+    uint64_t rg_seed = 0, rg_off = 0;
+    int64_t rg_base = 0;
+    if (p.regen_state) {
+        const int r = b / p.regen_B;
+        rg_seed = __ldg(p.regen_state + 2 * r);
+        rg_off = __ldg(p.regen_state + 2 * r + 1);
+        rg_base = (int64_t)(b - r * p.regen_B) * p.n;        // first element of this query inside rank r's draw
+    }
     // kU batches of 32 ids per iteration: the loads, then the atomics, of kU batches are independent and in
     // flight together (the one-batch loop was latency-bound: 0.37 ms for 67 M ids at 8 owners)
     constexpr int kU = 4;
@@ -91,7 +113,8 @@ shard_prep_kernel(const PrepParams p) {
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const int j = jb + u * 32 + lane;
-            raw[u] = (j < p.n) ? __ldg(p.neg + base + j) : -1;
+            if (p.regen_state) raw[u] = (j < p.n) ? regen_uniform_id(rg_seed, rg_off, rg_base + j, p.regen_T, (uint32_t)(p.num_items - 1)) : -1;
+            else raw[u] = (j < p.n) ? __ldg(p.neg + base + j) : -1;
         }
         int kpos[kU]; int64_t lids[kU]; bool mines[kU]; bool zero[kU];
 #pragma unroll
@@ -235,8 +258,15 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
     RSB_REQUIRE(a->loss_kind == RSB200_LOSS_BPR || a->loss_kind == RSB200_LOSS_SSM, RSB200_EINVAL, "bad loss_kind");
     RSB_REQUIRE(a->score_kind == RSB200_SCORE_IP || a->score_kind == RSB200_SCORE_EUCLID, RSB200_EINVAL, "bad score_kind");
     RSB_REQUIRE(a->sink == RSB200_SINK_COMPACT || a->sink == RSB200_SINK_DENSE, RSB200_EINVAL, "bad sink");
-    RSB_REQUIRE(a->w_local && a->q_all && a->pos && (a->n == 0 || a->neg) && a->sp && a->stats_all && a->dq && a->loss,
+    RSB_REQUIRE(a->w_local && a->q_all && a->pos && (a->n == 0 || a->neg || a->regen_state) && a->sp && a->stats_all && a->dq && a->loss,
                 RSB200_EINVAL, "null table / batch / exchange pointer");
+    if (a->regen_state) {
+        RSB_REQUIRE(a->regen_B >= 1 && a->regen_B * a->world == a->G, RSB200_EINVAL, "regen_B * world must equal G");
+        RSB_REQUIRE(a->regen_sm_count > 0 && a->regen_max_threads_per_sm >= 256, RSB200_EINVAL, "bad draw policy");
+        RSB_REQUIRE(a->logq_neg == nullptr, RSB200_EUNSUPPORTED, "owner-side regeneration implements the uniform sampler (log Q = 0)");
+        RSB_REQUIRE(a->num_items - 1 < ((int64_t)1 << 28) && a->regen_B * a->n * 8 < ((int64_t)1 << 31), RSB200_EUNSUPPORTED,
+                    "draw outside ATen's 32-bit path (see rsb200_sample_uniform)");
+    }
     RSB_REQUIRE(a->neg_c && a->slot_neg && a->ncount && a->pos_local && a->slot_pos && a->off && a->urow && a->ent &&
                 a->loss_part && a->lse && a->scan_tmp && a->totals && a->err_flag, RSB200_EINVAL, "null workspace pointer");
     RSB_REQUIRE(a->logq_neg == nullptr || a->lq_c != nullptr, RSB200_EINVAL, "logq_neg needs the lq_c workspace");
@@ -259,6 +289,13 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
             p.ncount = a->ncount; p.pos_local = a->pos_local; p.slot_pos = a->slot_pos; p.sp = a->sp; p.err = a->err_flag;
             p.num_items = a->num_items; p.row0 = a->row0; p.local_rows = a->local_rows;
             p.G = (int)G; p.n = (int)n; p.D = (int)a->d; p.euclid = eu;
+            p.regen_state = a->regen_state; p.regen_B = (int)a->regen_B; p.regen_T = 0;
+            if (a->regen_state) {        // ATen policy: grid = min(sm * (max_threads / 256), ceil(numel / 256)), T = 256 grid
+                const int64_t numel = a->regen_B * n;
+                int64_t grid = (int64_t)a->regen_sm_count * (a->regen_max_threads_per_sm / 256);
+                if (cdiv(numel, 256) < grid) grid = cdiv(numel, 256);
+                p.regen_T = 256 * (grid > 0 ? grid : 1);
+            }
             shard_prep_kernel<<<qblocks, kPrepWarps * 32, 0, st>>>(p);
             RSB_LAUNCH_CHECK();
         }

@@ -238,17 +238,29 @@ class OwnerComputeCuda:
         self.item_rows, self.item_vals = E(self.cap, dtype=i64), E(self.cap, d)
         self._args = None
 
-    def bind(self, q_all, pos_all, neg_all, loss_kind, score_kind, logq_pos=None, logq_neg=None, grad_scale: float = 1.0):
+    def bind(self, q_all, pos_all, neg_all, loss_kind, score_kind, logq_pos=None, logq_neg=None, grad_scale: float = 1.0,
+             regen_state: Optional[torch.Tensor] = None):
+        """``neg_all`` [G, n] int32 GLOBAL ids -- or ``None`` with ``regen_state`` [world, 2] int64 (seed, philox offset of
+        every rank's CUDA generator): the owner then recomputes every rank's ``torch.randint(1, N, (B, n))`` draw itself
+        (UniformSampler; nothing id-sized crosses NVLink)."""
         G, n, d = self.G, self.n, self.d
         assert q_all.shape == (G, d) and q_all.dtype == torch.float32 and pos_all.shape == (G,) and pos_all.dtype == torch.int64
-        assert neg_all.shape == (G, n) and neg_all.dtype == torch.int32
+        if regen_state is None:
+            assert neg_all.shape == (G, n) and neg_all.dtype == torch.int32
+        else:
+            assert neg_all is None and regen_state.shape == (self.world, 2) and regen_state.dtype == torch.int64 \
+                and regen_state.is_cuda and logq_neg is None and G % self.world == 0
         if logq_neg is not None and self.lq_c is None:
             raise _lib.Rsb200Error("OwnerComputeCuda was built without the logq workspace (with_logq=True)")
-        self._keep = [t.contiguous() if t is not None else None for t in (q_all, pos_all, neg_all, logq_pos, logq_neg)]
-        q_all, pos_all, neg_all, logq_pos, logq_neg = self._keep
+        self._keep = [t.contiguous() if t is not None else None for t in (q_all, pos_all, neg_all, logq_pos, logq_neg, regen_state)]
+        q_all, pos_all, neg_all, logq_pos, logq_neg, regen_state = self._keep
         a = _lib.ShardArgs()
         P = _lib.ptr
-        a.w_local, a.q_all, a.pos, a.neg = P(self.weight), P(q_all), P(pos_all), P(neg_all)
+        a.w_local, a.q_all, a.pos, a.neg = P(self.weight), P(q_all), P(pos_all), (P(neg_all) if neg_all is not None else None)
+        if regen_state is not None:
+            dev = self.weight.device
+            sm, mt, _, _ = _lib.device_info(dev.index if dev.index is not None else torch.cuda.current_device())
+            a.regen_state, a.regen_B, a.regen_sm_count, a.regen_max_threads_per_sm = P(regen_state), G // self.world, sm, mt
         a.logq_pos = P(logq_pos) if logq_pos is not None else None
         a.logq_neg = P(logq_neg) if logq_neg is not None else None
         a.grad_scale_dev = None
@@ -290,9 +302,22 @@ class OwnerComputeCuda:
             raise _lib.Rsb200Error("shard_step: item id outside [0, num_items)")
 
 
-def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, loss_kind: int, score_kind: int,
+def uniform_regen_state(device, B: int, n: int, group=None, generator=None) -> torch.Tensor:
+    """[world, 2] int64 (seed, philox offset) of every rank's CUDA generator, all-gathered (16 bytes per rank), and this
+    rank's generator advanced by exactly what ``torch.randint(1, N, (B, n), device=cuda)`` would have consumed: the
+    owners regenerate the UniformSampler draws from these states instead of receiving the ids."""
+    from . import sampling
+    device = torch.device(device)
+    gen = sampling._generator(device, generator)
+    seed, off = gen.initial_seed(), gen.get_offset()
+    mine = torch.tensor([[seed - (1 << 64) if seed >= (1 << 63) else seed, off]], dtype=torch.int64).pin_memory()
+    gen.set_offset(off + sampling.counter_offset(B * n, device))
+    return _all_gather_cat(mine.to(device, non_blocking=True), group)
+
+
+def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: Optional[torch.Tensor], loss_kind: int, score_kind: int,
                        logq_pos: Optional[torch.Tensor] = None, logq_neg: Optional[torch.Tensor] = None, group=None,
-                       gathered=None):
+                       gathered=None, regen_state: Optional[torch.Tensor] = None):
     """One data-parallel step over the row-sharded item table WITHOUT moving rows.
 
     Every rank passes its own B queries (vectors ``q`` [B, d], GLOBAL ids ``pos`` [B], ``neg`` [B, n] int32);
@@ -300,13 +325,18 @@ def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: torch.Te
     ``(loss, (rows, vals, totals), dq_all)``: the global mean loss (identical on every rank), the gradient rows
     of the rows THIS rank owns (LOCAL ids, ``R = totals[1]`` valid rows) and ``d loss / d query`` of all
     ``G = world x B`` queries (rank r's queries are ``dq_all[r*B:(r+1)*B]``).  No host synchronisation."""
-    if gathered is None:
+    if gathered is None and regen_state is not None:          # uniform negatives regenerated by the owners: no id exchange
+        q_all, pos_all, neg_all, lqp, lqn = _all_gather_cat(q, group), _all_gather_cat(pos, group), None, None, None
+    elif gathered is None:
         q_all, pos_all, neg_all = _all_gather_cat(q, group), _all_gather_cat(pos, group), _all_gather_cat(neg, group)
         lqp = _all_gather_cat(logq_pos, group) if logq_pos is not None else None
         lqn = _all_gather_cat(logq_neg, group) if logq_neg is not None else None
     else:
         q_all, pos_all, neg_all, lqp, lqn = gathered
-    engine.bind(q_all, pos_all, neg_all, loss_kind, score_kind, lqp, lqn)
+    if regen_state is not None:
+        engine.bind(q_all, pos_all, None, loss_kind, score_kind, lqp, lqn, regen_state=regen_state)
+    else:
+        engine.bind(q_all, pos_all, neg_all, loss_kind, score_kind, lqp, lqn)
     sp = engine.prep()
     dist.all_reduce(sp, group=group)                                   # every positive has exactly one owner
     mine = engine.fwd()
@@ -329,12 +359,15 @@ def exchange_stats(engine, mine: torch.Tensor, group=None):
 
 
 def owner_compute_training_step(items: ShardedRows, engine, w_user: torch.Tensor, user: torch.Tensor, pos: torch.Tensor,
-                                neg: torch.Tensor, loss_kind: int, score_kind: int, logq_pos=None, logq_neg=None):
-    """Same contract as ``sharded_training_step`` (replicated user table), on the owner-compute path."""
+                                neg: Optional[torch.Tensor], loss_kind: int, score_kind: int, logq_pos=None, logq_neg=None,
+                                regen_state: Optional[torch.Tensor] = None):
+    """Same contract as ``sharded_training_step`` (replicated user table), on the owner-compute path.  ``neg=None`` with
+    ``regen_state=uniform_regen_state(...)``: UniformSampler negatives regenerated by the owners (no id exchange)."""
     q = items.ops.gather_rows(w_user, user)
     user_all = _all_gather_cat(user, items.group)
-    loss, (rows, vals, totals), dq_all = owner_compute_step(engine, q, pos, neg.to(torch.int32), loss_kind, score_kind,
-                                                            logq_pos, logq_neg, group=items.group)
+    loss, (rows, vals, totals), dq_all = owner_compute_step(engine, q, pos, neg.to(torch.int32) if neg is not None else None,
+                                                            loss_kind, score_kind, logq_pos, logq_neg, group=items.group,
+                                                            regen_state=regen_state)
     r = int(totals[1].item())
     ur, uv = items.ops.coalesce_rows(user_all, dq_all, w_user.shape[0], skip_row0=True)
     return loss, (rows[:r], vals[:r]), (ur, uv)

@@ -128,3 +128,70 @@ def test_matches_the_single_table_fused_step(loss_kind):
     assert abs(loss - loss_ref) <= 2e-6 * abs(loss_ref)
     assert (d_item - ref_item).abs().max().item() <= 1e-5 * ref_item.abs().max().item()
     assert (dq - ref_dq).abs().max().item() <= 1e-5 * ref_dq.abs().max().item()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("loss_kind", [R.BPR, R.SSM])
+def test_owner_side_regeneration_of_the_uniform_draw(world, loss_kind):
+    """Instead of receiving every rank's negative ids, the owners recompute them from the ranks' generator states
+    (rsb200_shard_args.regen_state): rank r's ids are exactly torch.randint(1, N, (B, n), device=cuda) for its
+    (seed, offset).  The step must be bit-identical to the one fed with the explicitly drawn, gathered ids."""
+    from recstudio_b200 import sampling, sharded
+    N, U, d, B, n = 40_001, 301, 64, 24, 300           # numel = B * n above one ATen grid row for some lanes of T
+    G = world * B
+    g = torch.Generator().manual_seed(world)
+    w_item = (torch.randn(N, d, generator=g) * 0.3).to(DEV); w_item[0] = 0
+    q_all = (torch.randn(G, d, generator=g) * 0.3).to(DEV)
+    pos = torch.randint(1, N, (G,), generator=g).to(DEV)
+    states, negs = [], []
+    for r in range(world):                                 # what every rank would draw on its own generator
+        torch.manual_seed(1000 + r)
+        torch.rand(17 * (r + 1), device=DEV)                # ranks sit at different offsets
+        gen = torch.cuda.default_generators[0]
+        states.append([gen.initial_seed(), gen.get_offset()])
+        want = torch.randint(1, N, (B, n), device=DEV)
+        negs.append(want.int())
+    neg_all = torch.cat(negs, 0)
+    state = torch.tensor(states, dtype=torch.int64, device=DEV)
+    per = sharded.rows_per_rank(N, world)
+    outs = []
+    for regen in (False, True):
+        engines = []
+        for r in range(world):
+            row0 = r * per; local = max(0, min(per, N - row0))
+            e = sharded.OwnerComputeCuda(N, row0, local, w_item[row0:row0 + local].contiguous(), world, r, G, n)
+            if regen:
+                e.bind(q_all, pos, None, loss_kind, R.IP, regen_state=state)
+            else:
+                e.bind(q_all, pos, neg_all, loss_kind, R.IP)
+            engines.append(e)
+        sp = torch.stack([e.prep().clone() for e in engines]).sum(0)
+        for e in engines:
+            e.sp[:G] = sp
+        stats = torch.stack([e.fwd().clone() for e in engines])
+        res = []
+        for e in engines:
+            e.stats_all[:, :G] = stats
+        for e in engines:
+            loss, dq = e.finish()
+            rows, vals, totals = e.scatter()
+            R_ = int(totals[1].item())
+            res.append((loss.clone(), dq.clone(), rows[:R_].clone(), vals[:R_].clone(), e.ncount[:G].clone(), int(totals[0].item())))
+            e.check()
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert torch.equal(a[4], b[4]) and a[5] == b[5]              # same owned negatives per query, same touch count
+        assert torch.equal(a[2], b[2])                               # same gradient rows
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])   # loss and dq bit-identical (same compaction order)
+        assert (a[3] - b[3]).abs().max().item() <= 1e-6 * max(a[3].abs().max().item(), 1e-30)   # entry order inside a row may differ
+    # uniform_regen_state advances the generator exactly like the draw it replaces
+    torch.manual_seed(5)
+    ref_after = (torch.randint(1, N, (B, n), device=DEV), torch.rand(2, device=DEV))[1]
+    torch.manual_seed(5)
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        import os
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29571")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
+    st = sharded.uniform_regen_state(DEV, B, n)
+    assert st.shape == (1, 2) and torch.equal(torch.rand(2, device=DEV), ref_after)

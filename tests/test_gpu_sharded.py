@@ -81,7 +81,7 @@ def test_sharded_step_on_two_gpus(loss_kind):
     assert np.abs(d_item - ref["d_item"].numpy()).max() <= 1e-5 * np.abs(ref["d_item"].numpy()).max()
 
 
-def _oc_worker(rank, port, loss_kind, q):
+def _oc_worker(rank, port, loss_kind, q, regen=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -94,8 +94,18 @@ def _oc_worker(rank, port, loss_kind, q):
         torch.manual_seed(100 + rank)
         _, neg32 = sampling.uniform_draw(N, B, NNEG, dev, want_i64=False, want_i32=True)
         eng = sharded.OwnerComputeCuda(N, items.row0, items.local_rows, items.weight, WORLD, rank, WORLD * B, NNEG)
-        loss, (orow, oval), (urow, uval) = sharded.owner_compute_training_step(
-            items, eng, w_user.to(dev), user[rank].to(dev), pos[rank].to(dev), neg32, loss_kind, R.IP)
+        if regen:       # the owners recompute every rank's draw from the all-gathered (seed, offset) pairs: no id exchange
+            torch.manual_seed(100 + rank)
+            torch.randint(1, N, (B, NNEG), device=dev)
+            after = torch.rand(3, device=dev)                       # what follows the draw on this rank's stream
+            torch.manual_seed(100 + rank)
+            state = sharded.uniform_regen_state(dev, B, NNEG, group=items.group)
+            assert torch.equal(torch.rand(3, device=dev), after)    # generator advanced exactly like the draw it replaces
+            loss, (orow, oval), (urow, uval) = sharded.owner_compute_training_step(
+                items, eng, w_user.to(dev), user[rank].to(dev), pos[rank].to(dev), None, loss_kind, R.IP, regen_state=state)
+        else:
+            loss, (orow, oval), (urow, uval) = sharded.owner_compute_training_step(
+                items, eng, w_user.to(dev), user[rank].to(dev), pos[rank].to(dev), neg32, loss_kind, R.IP)
         eng.check()
         torch.cuda.synchronize()
         q.put((rank, loss.item(), neg32.cpu().numpy(), (orow + items.row0).cpu().numpy(), oval.cpu().numpy(),
@@ -104,16 +114,18 @@ def _oc_worker(rank, port, loss_kind, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("regen", [False, True])
 @pytest.mark.parametrize("loss_kind", [R.BPR, R.SSM])
-def test_owner_compute_step_on_two_gpus(loss_kind):
-    """The query-shipping formulation (rsb200_shard_step + three small NCCL exchanges): same contract, same answer."""
+def test_owner_compute_step_on_two_gpus(loss_kind, regen):
+    """The query-shipping formulation (rsb200_shard_step + three small NCCL exchanges): same contract, same answer;
+    regen=True: the negative ids are not exchanged at all, every owner regenerates both ranks' UniformSampler draws."""
     if torch.cuda.device_count() < WORLD:
         pytest.skip("needs %d GPUs" % WORLD)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_oc_worker, args=(r, port, loss_kind, q)) for r in range(WORLD)]
+    procs = [ctx.Process(target=_oc_worker, args=(r, port, loss_kind, q, regen)) for r in range(WORLD)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=600) for _ in range(WORLD))
