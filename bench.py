@@ -191,21 +191,32 @@ def run_b200(args):
 
     for i in range(W):
         step(i)
+    # the timed loop replays ONE CUDA graph per step (draw + COUNT + SCAN + FWD + SCATTER, fused.GraphedPairStep): the
+    # kernels around the two big streams are a few microseconds each, so launch gaps cost ~5 % when issued one by one
+    graphed = None if args.no_graph else fused.GraphedPairStep(ws, wi, wu, _lib.LOSS_BPR, _lib.SCORE_IP)
+    if graphed is not None:
+        for i in range(W):
+            graphed(users[i], poss[i])
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     launches0 = L.rsb200_launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record()
     for i in range(K):
-        loss = step(W + i, evs[i])
+        loss = graphed(users[W + i], poss[W + i]) if graphed is not None else step(W + i)
     t1.record()
     barrier()
-    launches = L.rsb200_launch_count() - launches0
+    launches = graphed.launches_per_step * K if graphed is not None else L.rsb200_launch_count() - launches0
     total_ms = t0.elapsed_time(t1)
-    fwd_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    # dominant-kernel timing for the roofline: CUDA events around the PHASE_FWD launch, un-graphed, after the timed region
+    KF = min(K, 50)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KF)]
+    for i in range(KF):
+        step(W + i, evs[i])
+    barrier()
+    fwd_ms = sum(a.elapsed_time(b) for a, b in evs) / KF
     loss_val = float(loss.item())
     unique_rows = int(ws.totals[1].item())
 
@@ -244,7 +255,8 @@ def run_b200(args):
                 "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "BASELINE configs[1]: BPR + InnerProduct + in-kernel UniformSampler, items 10,000,001 x 128, "
-                                       "users 1,000,001 x 128, B=8192, n=1024, sparse-row gradient sink",
+                                       "users 1,000,001 x 128, B=8192, n=1024, sparse-row gradient sink"
+                                       + ("" if args.no_graph else ", one CUDA graph replay per step"),
                            "global_batch": BATCH * world, "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
                            "l2": "inputs (5.12 GB table, random rows) exceed the 126 MB L2; no flush needed"},
                 "e2e": {"value": e2e, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -403,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development only)")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores)")
     ap.add_argument("--c5-sampler", default="popular", choices=["popular", "uniform"],
                     help="negative sampler of the c5-sharded workload (configs[4] names the PopularitySampler)")

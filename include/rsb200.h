@@ -95,6 +95,13 @@ int32_t rsb200_sample_uniform(uint64_t seed, uint64_t philox_offset,
                               int32_t* neg_out_i32 /* [num_queries, num_neg] or NULL */,
                               void* stream);
 
+/* Same draw with the generator state in DEVICE memory (state_dev[0] = seed, state_dev[1] = philox offset, a multiple of
+ * 4): the launch can be captured in a CUDA graph and draws fresh ids on every replay; state_dev[1] is advanced on the
+ * device by rsb200_philox_counter_offset(...) after the draw (the host advances torch's generator by the same amount). */
+int32_t rsb200_sample_uniform_dev(uint64_t* state_dev, int64_t num_items, int64_t num_queries, int64_t num_neg,
+                                  int32_t sm_count, int32_t max_threads_per_sm,
+                                  int64_t* neg_out_i64, int32_t* neg_out_i32, void* stream);
+
 /* guide table: guide[k] = searchsorted(table, k / 2^guide_bits), k in [0, 2^guide_bits],
  * turns the reference's log2(N)-step bisection into an O(1)-expected search with
  * identical results.  guide has 2^guide_bits + 1 int32 entries. */

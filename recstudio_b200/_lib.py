@@ -113,6 +113,7 @@ def lib():
         sigs = {
             "rsb200_device_info": [v, v, v, v],
             "rsb200_sample_uniform": [u64, u64, i64, i64, i64, i32, i32, v, v, v],
+            "rsb200_sample_uniform_dev": [v, i64, i64, i64, i32, i32, v, v, v],
             "rsb200_popular_build_guide": [v, i64, i32, v, v],
             "rsb200_sample_popular": [u64, u64, v, v, i64, i64, i64, i32, i32, v, i32, v, v, v, v],
             "rsb200_popular_logq": [v, i64, v, i64, v, v],

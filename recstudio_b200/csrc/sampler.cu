@@ -46,6 +46,30 @@ uniform_kernel(uint64_t seed, uint64_t ctr_base, int64_t T, int64_t rounds, int6
     }
 }
 
+// CUDA-graph-capturable form: (seed, philox offset) live in DEVICE memory, so a captured launch draws fresh ids on every
+// replay; advance_state_kernel moves the offset on by what the draw consumed (the host does the same to torch's generator).
+__global__ void __launch_bounds__(256)
+uniform_dev_state_kernel(const uint64_t* __restrict__ state, int64_t T, int64_t rounds, int64_t numel, uint32_t range,
+                         int64_t* __restrict__ out64, int32_t* __restrict__ out32) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T * rounds) return;
+    const uint64_t seed = state[0], ctr_base = state[1] / 4;
+    int64_t r = t / T, idx = t - r * T;
+    uint4 w = Philox::gen(seed, (uint64_t)idx, ctr_base + (uint64_t)r);
+    uint32_t words[4] = {w.x, w.y, w.z, w.w};
+    int64_t li = r * 4 * T + idx;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii, li += T) {
+        if (li < numel) {
+            uint32_t v = words[ii] % range + 1u;
+            if (out64) out64[li] = (int64_t)v;
+            if (out32) out32[li] = (int32_t)v;
+        }
+    }
+}
+
+__global__ void advance_state_kernel(uint64_t* state, uint64_t inc) { state[1] += inc; }
+
 // first i in [lo, hi] with table[i] >= u  (hi is returned if none)
 __device__ __forceinline__ int lower_bound(const float* __restrict__ table, int lo, int hi, float u) {
     while (lo < hi) {
@@ -305,6 +329,26 @@ extern "C" int32_t rsb200_sample_uniform_masked(uint64_t seed, uint64_t philox_o
     int64_t threads = p.T * p.rounds;
     masked_draw_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(seed, philox_offset / 4, p.T, p.rounds, numel, per_user,
                                                                      num_items - 1, adj_ws, cnt_ws, (int)hist_len, neg64, neg32);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t rsb200_sample_uniform_dev(uint64_t* state_dev, int64_t num_items, int64_t num_queries, int64_t num_neg,
+                                             int32_t sm_cnt, int32_t max_tpsm, int64_t* neg64, int32_t* neg32, void* stream) {
+    RSB_REQUIRE(state_dev != nullptr, RSB200_EINVAL, "null generator state");
+    int32_t rc = check_draw(0, num_items, num_queries, num_neg, sm_cnt, max_tpsm);
+    if (rc) return rc;
+    RSB_REQUIRE(num_items - 1 < ((int64_t)1 << 28), RSB200_EUNSUPPORTED,
+                "range >= 2^28 takes ATen's 64-bit draw path (DistributionTemplates.h:319); not implemented");
+    int64_t numel = num_queries * num_neg;
+    if (numel == 0) return 0;
+    DrawPolicy p = make_policy(numel, sm_cnt, max_tpsm);
+    int64_t threads = p.T * p.rounds;
+    cudaStream_t st = (cudaStream_t)stream;
+    uniform_dev_state_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(state_dev, p.T, p.rounds, numel,
+                                                                           (uint32_t)(num_items - 1), neg64, neg32);
+    RSB_LAUNCH_CHECK();
+    advance_state_kernel<<<1, 1, 0, st>>>(state_dev, (uint64_t)(p.rounds * 4));
     RSB_LAUNCH_CHECK();
     return 0;
 }

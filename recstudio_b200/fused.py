@@ -177,3 +177,57 @@ def sparse_grads(ws: PairWorkspace):
     tot = ws.totals.tolist()
     ri, ru = tot[1], tot[3]
     return (ws.item_rows[:ri], ws.item_vals[:ri]), (ws.user_rows[:ru], ws.user_vals[:ru])
+
+
+class GraphedPairStep:
+    """The whole fused step -- UniformSampler draw, COUNT, SCAN, FWD, SCATTER (17 launches) -- captured once in a CUDA
+    graph and replayed: the kernels between the two big streams are a few microseconds each, so launch gaps are ~5 % of
+    the step when they are issued one by one.  The draw reads the generator state from device memory
+    (rsb200_sample_uniform_dev), so every replay draws exactly what ``torch.randint(1, N, (B, n), device=cuda)`` would
+    return for the torch generator's current state, and the generator is advanced accordingly; if anything else consumed
+    the generator in between, the state is re-uploaded before the replay.  Gradients are left in ``ws`` as for
+    ``pair_step`` (compact sink)."""
+
+    def __init__(self, ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, loss_kind: int, score_kind: int,
+                 generator: Optional[torch.Generator] = None):
+        from . import sampling
+        num_items, num_users, B, n, d = ws.shape
+        dev = ws.device
+        self.ws, self.dev, self.shape = ws, dev, (num_items, B, n)
+        self.gen = sampling._generator(dev, generator)
+        self.inc = sampling.counter_offset(B * n, dev)
+        self.user = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.neg32 = torch.empty(B, n, dtype=torch.int32, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._tracked = None
+        sm, mt = sampling._policy(dev)
+
+        def body():
+            with torch.cuda.device(dev):
+                check(lib().rsb200_sample_uniform_dev(ptr(self.state), num_items, B, n, sm, mt, 0, ptr(self.neg32), stream_ptr()),
+                      "sample_uniform_dev")
+            pair_step(ws, w_item, w_user, self.user, self.pos, self.neg32, loss_kind, score_kind)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                 # warm-up outside the capture (lazy module loading, attributes)
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        l0 = lib().rsb200_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        self.launches_per_step = int(lib().rsb200_launch_count() - l0)
+
+    def __call__(self, user: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+        self.user.copy_(user, non_blocking=True)
+        self.pos.copy_(pos, non_blocking=True)
+        seed, off = self.gen.initial_seed(), self.gen.get_offset()
+        if self._tracked != (seed, off):              # first call, or someone else used the generator: upload its state
+            self.state.copy_(torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, off], dtype=torch.int64))
+        self.graph.replay()
+        self.gen.set_offset(off + self.inc)
+        self._tracked = (seed, off + self.inc)
+        return self.ws.loss[0]

@@ -351,3 +351,38 @@ def test_config2_shape_popularity_skew(loss):
                 want = want + ((torch.exp(sp[b] - lqp[b] - ws.lse[b]) - 1) / B * q[b]).double()
         k = int(torch.searchsorted(ri, torch.tensor([r], device=dev)))
         assert (vi[k].double() - want).abs().max().item() <= 2e-5 * want.abs().max().item() + 1e-12, (r, int(bb.numel()))
+
+
+def test_graphed_step_matches_plain_step():
+    """fused.GraphedPairStep: the whole step (draw with the generator state in device memory, COUNT, SCAN, FWD, SCATTER)
+    captured in one CUDA graph.  Every replay must draw exactly torch.randint's ids for the generator's current state,
+    leave the generator where torch would, and produce the plain step's loss and gradients."""
+    from recstudio_b200 import fused, sampling
+    dev = torch.device("cuda:0")
+    N, U, d, B, n = 5001, 301, 128, 96, 300
+    g = torch.Generator().manual_seed(4)
+    wi = (torch.randn(N, d, generator=g) * 0.3).to(dev); wi[0] = 0
+    wu = (torch.randn(U, d, generator=g) * 0.3).to(dev); wu[0] = 0
+    batches = [(torch.randint(1, U, (B,), generator=g).to(dev), torch.randint(1, N, (B,), generator=g).to(dev)) for _ in range(3)]
+    ws_g = fused.PairWorkspace(N, U, B, n, d, dev)
+    step = fused.GraphedPairStep(ws_g, wi, wu, R.SSM, R.IP)
+    assert step.launches_per_step >= 15
+    ws_p = fused.PairWorkspace(N, U, B, n, d, dev)
+    for it, (user, pos) in enumerate(batches):
+        torch.manual_seed(50 + it)
+        if it == 2:
+            torch.rand(999, device=dev)                      # someone else consumed the generator: state is re-uploaded
+        st = torch.cuda.get_rng_state(dev)
+        want_neg = torch.randint(1, N, (B, n), device=dev)
+        after = torch.rand(5, device=dev)
+        loss_p = fused.pair_step(ws_p, wi, wu, user, pos, want_neg.int(), R.SSM, R.IP).item()
+        (ri, vi), (ru, vu) = fused.sparse_grads(ws_p)
+        torch.cuda.set_rng_state(st, dev)
+        loss_g = step(user, pos).item()
+        assert torch.equal(step.neg32.long(), want_neg)
+        assert torch.equal(torch.rand(5, device=dev), after)
+        (gi, gv), (gu, guv) = fused.sparse_grads(ws_g)
+        assert abs(loss_g - loss_p) <= 1e-6 * abs(loss_p)
+        assert torch.equal(gi, ri) and torch.equal(gu, ru)
+        assert (gv - vi).abs().max().item() <= 1e-5 * vi.abs().max().item()
+        assert (guv - vu).abs().max().item() <= 1e-5 * vu.abs().max().item()
