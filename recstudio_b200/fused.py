@@ -217,7 +217,8 @@ class GraphedPairStep:
         torch.cuda.synchronize(dev)
         l0 = lib().rsb200_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads (e.g. NCCL's watchdog polling events) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             body()
         self.launches_per_step = int(lib().rsb200_launch_count() - l0)
 
