@@ -218,3 +218,20 @@ def test_sequence_pooling_matches_reference_golden():
     np.testing.assert_array_equal(mx.indices.numpy(), g["max_indices"])
     with pytest.raises(ValueError):
         attention.pool_sequence(x, seqlen, "first")
+
+
+def test_every_declared_function_has_a_typed_binding(L):
+    """The ctypes layer declares argument types for every entry point of include/rsb200.h, and the number of arguments in
+    each binding equals the number of parameters in the C declaration (a drifted binding would corrupt the call frame)."""
+    import re
+    from recstudio_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER).read(), flags=re.S)
+    decls = dict((m.group(1), m.group(2)) for m in re.finditer(r"\b(rsb200_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(decls) == set(_lib.declared_symbols())
+    for name, params in sorted(decls.items()):
+        fn = getattr(L, name)
+        params = params.strip()
+        n_params = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert fn.argtypes is not None or n_params == 0, "no argtypes for %s" % name
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n_params, "%s: binding has %d arguments, header declares %d" % (name, len(fn.argtypes), n_params)
