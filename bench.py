@@ -40,6 +40,8 @@ sys.path.insert(0, REPO)
 N_ITEMS, N_USERS, DIM, BATCH, NEG = 10_000_001, 1_000_001, 128, 8192, 1024
 INIT_STD = 0.05
 CPU_SAMPLE_B = 512          # bounded CPU sample: same tables, B = 512 interactions per step
+WORKLOAD_C2 = ("BASELINE configs[1]: BPR + InnerProduct + UniformSampler, items 10,000,001 x 128, "
+               "users 1,000,001 x 128, B=8192, n=1024")
 
 
 def peaks():
@@ -140,8 +142,8 @@ def run_reference(args):
             "value": cb["value"], "unit": "interactions/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: BPR, InnerProduct, UniformSampler, 10,000,001 x 128 items, "
-                                   "B=8192 x n=1024 (CPU arm times a bounded B=%d sample per step)" % CPU_SAMPLE_B},
+            "config": {"workload": WORKLOAD_C2, "global_batch": BATCH, "parallelism": "host CPU (torch, %d threads)" % cb["cores"],
+                       "sample": "each step is a bounded B=%d sample of the B=%d batch (same tables, same n)" % (CPU_SAMPLE_B, BATCH)},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -261,9 +263,8 @@ def run_b200(args):
         line = {"metric": "interactions/sec (BPR 10M x d128 fused gather-score-loss-scatter)", "value": value,
                 "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: BPR + InnerProduct + in-kernel UniformSampler, items 10,000,001 x 128, "
-                                       "users 1,000,001 x 128, B=8192, n=1024, sparse-row gradient sink"
-                                       + ("" if graphed is None else ", one CUDA graph replay per step"),
+                "config": {"workload": WORKLOAD_C2, "gradient_sink": "sparse rows (compact COO)", "sampler": "in-kernel Philox draw",
+                           "cuda_graph": graphed is not None,
                            "global_batch": BATCH * world, "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
                            "l2": "inputs (5.12 GB table, random rows) exceed the 126 MB L2; no flush needed"},
                 "e2e": {"value": e2e, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
