@@ -283,3 +283,35 @@ def test_midx_oracle_matches_reference():
     b2 = M.midx_build(torch.from_numpy(g["mu_ip2_emb"]), K, b["c0"], b["c1"], 3, None)
     np.testing.assert_array_equal(b2["indices"], g["mu_ip2_indices"])
     np.testing.assert_allclose(b2["wkk"], g["mu_ip2_wkk"])
+
+
+# ---------------------------------------------------------------- size-independent properties of the new oracle pieces
+def test_masked_uniform_oracle_is_the_order_preserving_map_onto_the_complement():
+    """For a duplicate-free history the reference's arithmetic maps the k-th raw draw value (k = floor(u (N - c)) + 1) to
+    the k-th smallest item that is NOT in the history: checked exhaustively over every k for random histories."""
+    rng = np.random.RandomState(0)
+    for _ in range(25):
+        N = int(rng.randint(5, 60)); H = int(rng.randint(1, 12))
+        c = int(rng.randint(0, min(H, N - 1) + 1))
+        hist = np.zeros((1, H), dtype=np.int64)
+        hist[0, rng.permutation(H)[:c]] = rng.permutation(N)[:c] + 1          # padding zeros anywhere in the row
+        complement = np.array([i for i in range(1, N + 1) if i not in set(hist[0].tolist())])
+        m = N - c
+        seeds = ((np.arange(m) + 0.5) / m).astype(np.float32)[None, :]        # hits every k = 1 .. N - c exactly once
+        got = S.masked_uniform_from_seeds(N, hist, seeds)[0]
+        np.testing.assert_array_equal(got, complement)
+
+
+def test_construct_index_oracle_properties():
+    from oracle import midx as M
+    rng = np.random.RandomState(1)
+    for nb in (1, 7, 300):
+        codes = rng.randint(0, nb, size=2000)
+        ind, ptr_ = M.construct_index(codes, nb)
+        assert sorted(ind.tolist()) == list(range(2000)) and ptr_[0] == 0 and ptr_[-1] == 2000
+        for c in range(nb):
+            seg = ind[ptr_[c]:ptr_[c + 1]]
+            assert np.all(codes[seg] == c) and np.all(np.diff(seg) > 0)        # grouped by bucket, stable (ascending ids)
+        cp, tot = M.bucket_cdf(np.ones(2000, np.float32), ind, ptr_)
+        np.testing.assert_allclose(tot, np.diff(ptr_))
+        assert all(abs(cp[ptr_[c + 1] - 1] - 1.0) < 1e-6 for c in range(nb) if ptr_[c + 1] > ptr_[c])
