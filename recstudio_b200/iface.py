@@ -1,97 +1,66 @@
-"""The reference's plugin interfaces for the retriever hot path.
+"""The reference's plugin interfaces for the retriever hot path: the REAL ``recstudio`` classes.
 
-If ``recstudio`` (ustcml/RecStudio) is importable, the REAL base classes are used so
-that every replacement passes the reference's own ``isinstance`` gates
-(``baseretriever.py:17-46``, ``recommender.py:48-54``, ``init.py:6,24,37``).  When it
-is not (the GPU box: the Python reference cannot travel), local mirrors with the
-same names, signatures and semantics are defined -- interface declarations only
-(no arithmetic), so that the plugin layer and its tests read the same either way.
+Every replacement in this package subclasses the reference class it replaces so that it passes the
+reference's own ``isinstance`` gates (``baseretriever.py:17-46``, ``recommender.py:48-54``,
+``init.py:6,24,37``).  There are no local mirrors: ``recstudio`` (ustcml/RecStudio, unmodified) must be
+importable.  It is resolved in this order:
 
-NB (import-order hazard in the reference): ``recstudio.model`` must be imported
-before ``recstudio.ann.sampler`` -- sampler.py:6 imports ``recstudio.model.scorer``
-whose package ``__init__`` reaches baseretriever.py:9 (``from recstudio.ann.sampler
-import *``) while sampler.py is half-initialised.
+  1. whatever ``import recstudio`` finds (a user's own installation);
+  2. ``<repo>/baseline/_ref`` -- the ``pip install --target`` copy that ``__graft_entry__.build()`` makes
+     from ``/root/reference`` (git-ignored, travels to the GPU box with the snapshot).
+
+The reference hard-imports two packages this image lacks and never calls on this path, ``nni``
+(``recommender.py:10``, ``utils.py:8``) and ``torchmetrics`` (``eval/__init__.py:6``); when they are
+missing, the import-only stand-ins under ``<repo>/baseline/shim`` are appended to ``sys.path``.
+
+NB (import-order hazard in the reference): ``recstudio.model`` must be imported before
+``recstudio.ann.sampler`` -- sampler.py:6 imports ``recstudio.model.scorer`` whose package
+``__init__`` reaches baseretriever.py:9 (``from recstudio.ann.sampler import *``) while sampler.py is
+half-initialised.  Importing ``recstudio.utils`` creates ``./log`` and ``./.recstudio`` in the CWD
+(``utils.py:27-31``).
 """
 from __future__ import annotations
 
-import torch
+import importlib.util
+import os
+import sys
 
-HAVE_RECSTUDIO = False
-try:  # pragma: no cover - depends on the environment
-    import recstudio.model  # noqa: F401  (must come first, see above)
-    from recstudio.ann.sampler import MaskedUniformSampler as RefMaskedUniformSampler
-    from recstudio.ann.sampler import PopularSamplerModel as RefPopularSamplerModel
-    from recstudio.ann.sampler import Sampler
-    from recstudio.ann.sampler import UniformSampler as RefUniformSampler
-    from recstudio.model.basemodel import BaseRetriever
-    from recstudio.model.loss_func import BPRLoss as RefBPRLoss
-    from recstudio.model.loss_func import FullScoreLoss, PairwiseLoss, PointwiseLoss
-    from recstudio.model.loss_func import SampledSoftmaxLoss as RefSampledSoftmaxLoss
-    from recstudio.model.loss_func import SoftmaxLoss as RefSoftmaxLoss
-    from recstudio.model.scorer import CosineScorer, EuclideanScorer, InnerProductScorer
-    HAVE_RECSTUDIO = True
-except Exception:  # recstudio (or one of its hard deps: nni, torchmetrics) is absent
-    class Sampler(torch.nn.Module):
-        """recstudio/ann/sampler.py:48-58"""
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(_REPO, "baseline", "_ref")
+SHIM_DIR = os.path.join(_REPO, "baseline", "shim")
 
-        def __init__(self, num_items, scorer_fn=None):
-            super().__init__()
-            self.num_items = num_items - 1      # remove padding (sampler.py:51)
-            self.scorer = scorer_fn
 
-        def update(self, item_embs, max_iter=30):
-            pass
+def _have(mod: str) -> bool:
+    try:
+        return importlib.util.find_spec(mod) is not None
+    except (ImportError, ValueError):
+        return False
 
-        def compute_item_p(self, query, pos_items):
-            pass
 
-    class FullScoreLoss(torch.nn.Module):
-        """recstudio/model/loss_func.py:6-17"""
+def _resolve():
+    if not _have("recstudio") and os.path.isdir(os.path.join(REF_DIR, "recstudio")):
+        sys.path.append(REF_DIR)
+    if not _have("recstudio"):
+        raise ImportError(
+            "recstudio_b200 plugs into ustcml/RecStudio, which is not importable.  Install the unmodified reference "
+            "(`python -c 'import __graft_entry__ as g; g.build()'` puts it under %s) or add your own checkout to "
+            "sys.path.  The low-level ops (recstudio_b200.fused / sampling / topk / sharded) do not need it." % REF_DIR)
+    if not (_have("nni") and _have("torchmetrics")):
+        sys.path.append(SHIM_DIR)           # appended: a real installation always wins
 
-        def forward(self, label, pos_score, all_score):
-            pass
 
-    class PairwiseLoss(torch.nn.Module):
-        """recstudio/model/loss_func.py:20-22"""
+_resolve()
 
-        def forward(self, label, pos_score, log_pos_prob, neg_score, log_neg_prob):
-            pass
+import recstudio.model  # noqa: E402,F401  (must come first, see above)
+from recstudio.ann.sampler import MaskedUniformSampler as RefMaskedUniformSampler  # noqa: E402,F401
+from recstudio.ann.sampler import PopularSamplerModel as RefPopularSamplerModel  # noqa: E402,F401
+from recstudio.ann.sampler import Sampler  # noqa: E402,F401
+from recstudio.ann.sampler import UniformSampler as RefUniformSampler  # noqa: E402,F401
+from recstudio.model.basemodel import BaseRetriever  # noqa: E402,F401
+from recstudio.model.loss_func import BPRLoss as RefBPRLoss  # noqa: E402,F401
+from recstudio.model.loss_func import FullScoreLoss, PairwiseLoss, PointwiseLoss  # noqa: E402,F401
+from recstudio.model.loss_func import SampledSoftmaxLoss as RefSampledSoftmaxLoss  # noqa: E402,F401
+from recstudio.model.loss_func import SoftmaxLoss as RefSoftmaxLoss  # noqa: E402,F401
+from recstudio.model.scorer import CosineScorer, EuclideanScorer, InnerProductScorer  # noqa: E402,F401
 
-    class PointwiseLoss(torch.nn.Module):
-        """recstudio/model/loss_func.py:25-28"""
-
-        def forward(self, label, pos_score):
-            raise NotImplementedError
-
-    class InnerProductScorer(torch.nn.Module):
-        """recstudio/model/scorer.py:5-17 (interface only; arithmetic lives in plugins.py)"""
-
-        def forward(self, query, items):
-            raise NotImplementedError
-
-    class EuclideanScorer(InnerProductScorer):
-        """recstudio/model/scorer.py:28-34"""
-
-    class CosineScorer(InnerProductScorer):
-        """recstudio/model/scorer.py:19-25 (marker: the samplers only test isinstance to normalise their inputs)"""
-
-    # marker types so that `type(x) in (...)` checks read the same in both environments
-    class RefUniformSampler(Sampler):
-        pass
-
-    class RefPopularSamplerModel(Sampler):
-        pass
-
-    class RefMaskedUniformSampler(Sampler):
-        pass
-
-    class RefBPRLoss(PairwiseLoss):
-        pass
-
-    class RefSampledSoftmaxLoss(PairwiseLoss):
-        pass
-
-    class RefSoftmaxLoss(FullScoreLoss):
-        pass
-
-    BaseRetriever = None
+HAVE_RECSTUDIO = True      # kept for callers that used to branch on it; always true now

@@ -1,7 +1,7 @@
 """Drop-in replacements for the reference's plugin surfaces on the retriever hot path.
 
-Every class subclasses the reference class it replaces (``iface.py`` resolves those to
-the real ``recstudio`` classes when importable) so that ``BaseRetriever(config,
+Every class subclasses the reference class it replaces (``iface.py`` binds the real
+``recstudio`` classes) so that ``BaseRetriever(config,
 item_encoder=, query_encoder=, scorer=, sampler=, loss=)`` accepts them unchanged
 (recstudio/model/basemodel/baseretriever.py:14-46, recommender.py:48-54):
 
@@ -467,7 +467,7 @@ _SCORE_KIND = {FusedInnerProductScorer: SCORE_IP, FusedEuclideanScorer: SCORE_EU
 
 
 class FusedRetrieverMixin:
-    """Mix in FRONT of ``BaseRetriever`` (or ``MiniRetriever``): ``training_step`` takes the
+    """Mix in FRONT of ``BaseRetriever``: ``training_step`` takes the
     single fused CUDA path when the plugin combination is one the kernels implement
     (Embedding x {Uniform, Popular} x {IP, Euclid} x {BPR, SampledSoftmax},
     ``sampling_method == 'none'``, 1-D ``item_id``, no history exclusion); anything else
@@ -493,17 +493,16 @@ class FusedRetrieverMixin:
             return self.score_func(query.detach(), self.item_encoder(self._get_item_feat(pool)))
 
     def sampling(self, batch, num_neg, method="none", excluding_hist=False, t=1, return_query=False, query=None):
-        """All six sampling methods of the reference with identical semantics and RNG call order
-        (baseretriever.py:248-369): 'none' draws from the sampler; 'dns' / 'sir' draw a pool of num_neg[0] ids,
-        score it (rsb200_score_ids: no [B, n0, d] tensor) and keep the top num_neg[1] / resample with
-        softmax(score) weights; 'toprand' / 'top&rand' take candidates from the fused full-catalog top-k
-        (rsb200_topk_full); 'brute' samples from softmax(all scores / t)."""
+        """BaseRetriever.sampling (baseretriever.py:248-369).  'none', 'toprand' and 'brute' ARE the reference's code
+        (``super().sampling``; its ``self.topk`` resolves to the fused full-catalog top-k below).  Only the arms whose
+        work the kernels replace are restated, with the reference's semantics and RNG call order:
+        'dns' / 'sir' score the pool of num_neg[0] sampled ids with rsb200_score_ids (no [B, n0, d] tensor, :331-355);
+        'top&rand' draws its random half with the fused Philox kernel (same ids as the reference's torch.randint, :289-299)."""
+        if method not in ("dns", "sir", "top&rand"):
+            return super().sampling(batch, num_neg, method, excluding_hist, t, return_query, query)
         pos_items = batch.get(self.fiid, None)
         if pos_items is not None and pos_items.dim() == 1:
             pos_items = pos_items.view(-1, 1)                                     # :255-258
-        user_hist = batch.get("user_hist", None)
-        if user_hist is None:
-            user_hist = batch.get(self.fiid, None)                                # :260-262
         if isinstance(num_neg, int):
             num_neg = [num_neg, num_neg]
         elif isinstance(num_neg, (list, tuple)):
@@ -511,43 +510,19 @@ class FusedRetrieverMixin:
             assert num_neg[0] >= num_neg[1], "the first element of negative_count must be larger than the second element."
         else:
             raise TypeError("num_neg only support int and List/Tuple type.")
-        if method not in _FUSABLE_METHODS:
-            raise NotImplementedError("sampling method only support one of none/brute/is/dns/top/toprand/top&rand")
 
-        if method == "none":
-            assert self.sampler is not None, "excepted sampler of retriever to be Sampler, but get None."
-            log_pos_prob, neg_id, log_neg_prob, query = self._sample(batch, num_neg[1], excluding_hist, True)
-        elif method == "toprand":                                                 # :281-287
-            _, topk_items, query = self.topk(batch, k=num_neg[0], user_h=user_hist, return_query=True)
-            rand_idx = torch.randint(0, num_neg[0], (topk_items.size(0), num_neg[1]), device=topk_items.device)
-            neg_id = torch.gather(topk_items, -1, rand_idx)
-            log_neg_prob = torch.zeros_like(neg_id)
-            log_pos_prob = None if pos_items is None else torch.zeros_like(pos_items)
-        elif method == "top&rand":                                                # :289-299
+        if method == "top&rand":
+            user_hist = batch.get("user_hist", None)
+            if user_hist is None:
+                user_hist = batch.get(self.fiid, None)                            # :260-262
             num_neg_0 = num_neg[1] // 2
             _, neg_id, query = self.topk(batch, k=num_neg_0, user_h=user_hist, return_query=True)
             num_queries = int(np.prod(query.shape[:-1]))
-            n_items = self._get_item_vector().size(0) + 1
-            rand_id, _ = sampling.uniform_draw(n_items, num_queries, num_neg[1] - num_neg_0, query.device)
+            rand_id, _ = sampling.uniform_draw(self.item_vector.size(0) + 1, num_queries, num_neg[1] - num_neg_0, query.device)
             neg_id = torch.cat((neg_id, rand_id), dim=-1)
             log_neg_prob = torch.zeros_like(neg_id)
             log_pos_prob = None if pos_items is None else torch.zeros_like(pos_items)
-        elif method == "brute":                                                   # :301-329
-            query = self.query_encoder(self._get_query_feat(batch)) if query is None else query
-            item_vector = self._get_item_vector()
-            with torch.no_grad():
-                all_prob = torch.softmax(self.score_func(query.detach(), item_vector.detach()) / t, dim=-1)
-                all_prob = torch.nn.functional.pad(all_prob, pad=(1, 0))
-                sampling_prob = all_prob
-                num_pos = 1
-                if pos_items is not None:
-                    log_pos_prob = torch.log(torch.gather(all_prob, dim=-1, index=pos_items))
-                    num_pos = pos_items.size(-1)
-                if excluding_hist:
-                    sampling_prob = torch.scatter(all_prob, -1, user_hist, 0.0)   # mask_with_hist(prob, hist, 0), utils.py:474-499
-                neg_id = torch.multinomial(sampling_prob, num_neg[1] * num_pos, replacement=True)
-                log_neg_prob = torch.log(torch.gather(sampling_prob, dim=-1, index=neg_id))
-        else:                                                                     # 'sir' / 'dns'  :331-355
+        else:
             if pos_items is not None:
                 log_pos_prob, neg_id_pool, _, query = self._sample(batch, num_neg[0], excluding_hist, True)
             else:

@@ -6,7 +6,7 @@ Run in the authoring container only (needs /root/reference):
     python tests/golden/make_golden.py
 
 The reference (ustcml/RecStudio @ 6f628ddd) is pure Python and imports with two
-stub packages (`nni`, `torchmetrics`, see oracle/refshim/).  It cannot travel to
+stub packages (`nni`, `torchmetrics`, see baseline/shim/).  It cannot travel to
 the GPU box, so the vectors it produces are committed as small fixtures next
 to this script.  Everything is computed on the CPU with torch
 {torch.__version__ recorded in each file}.  Nothing here is imported by the
@@ -18,7 +18,7 @@ import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, os.path.join(REPO, "oracle", "refshim"))
+sys.path.insert(0, os.path.join(REPO, "baseline", "shim"))
 sys.path.insert(0, "/root/reference")
 os.chdir(tempfile.mkdtemp(prefix="rs_golden_"))     # recstudio.utils creates ./log, ./.recstudio
 

@@ -3,14 +3,14 @@
 (TripletDataset -> fit -> evaluate, recstudio/quickstart/run.py:6-61), once with the reference's BPR
 and once with FusedBPR (same seed, same CUDA generator stream => the same negatives), both on cuda:0.
 Needs the unmodified reference importable from baseline/_ref (pip --target install, git-ignored) and the
-two stub packages of oracle/refshim.  Prints one JSON line."""
+two import-only stand-ins under baseline/shim.  Prints one JSON line."""
 import json
 import os
 import sys
 import tempfile
 
 REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path[:0] = [os.path.join(REPO, "oracle", "refshim"), os.path.join(REPO, "baseline", "_ref"), REPO]
+sys.path.insert(0, REPO)     # recstudio_b200.iface resolves the reference (baseline/_ref) and the nni / torchmetrics stand-ins
 os.chdir(tempfile.mkdtemp(prefix="rs_ml100k_"))
 
 import warnings  # noqa: E402
@@ -20,7 +20,7 @@ import logging  # noqa: E402
 
 import torch  # noqa: E402
 
-import recstudio.model  # noqa: E402,F401  (before recstudio.ann.sampler: import cycle in the reference)
+from recstudio_b200 import iface  # noqa: E402,F401  (puts baseline/_ref on sys.path and imports recstudio.model first)
 from recstudio.data.dataset import TripletDataset  # noqa: E402
 from recstudio.model.mf.bpr import BPR  # noqa: E402
 from recstudio.utils import get_model  # noqa: E402
