@@ -86,6 +86,15 @@ extern "C" int32_t rsb200_pair_workspace_sizes(int64_t num_items, int64_t num_us
     o->lse = B;
     int64_t a = scan_tmp_elems(num_items), b = scan_tmp_elems(num_users);
     o->scan_tmp = a > b ? a : b;
+    // binned grouping of the item side (bins.cu)
+    const int shift = bin_shift_for(num_items, B * (n + 1), B);
+    o->bin_shift = shift >= kMinBinShift ? shift : 0;
+    o->nbins = o->bin_shift ? cdiv(num_items, (int64_t)1 << shift) : 0;
+    o->bin_cnt = o->nbins;
+    o->bin_off = o->nbins + 1;
+    o->bin_cursor = o->nbins * kCursorStride;
+    o->bin_status = o->nbins;
+    o->bin_heavy = o->bin_shift ? bin_scatter_grid() * ((int64_t)1 << kMaxBinShift) : 0;
     return 0;
 }
 
@@ -114,9 +123,20 @@ static int32_t check_pair(const rsb200_pair_args* a) {
         RSB_REQUIRE(a->opt_kind != 2 || (a->item_state2 && a->user_state2 && aligned16(a->item_state2) && aligned16(a->user_state2)),
                     RSB200_EINVAL, "optimizer state2 missing");
     }
-    RSB_REQUIRE(a->off_item && a->off_user && a->slot_neg && a->slot_pos && a->slot_user && a->ent_item && a->ent_user &&
-                a->urow_item && a->urow_user && a->q_buf && a->dq_buf && a->loss_part && a->lse && a->scan_tmp &&
-                a->err_flag && a->totals && a->loss, RSB200_EINVAL, "null workspace pointer");
+    RSB_REQUIRE(a->grouping == 0 || a->grouping == 1, RSB200_EINVAL, "grouping must be 0 (counting sort) or 1 (bins)");
+    RSB_REQUIRE(a->off_user && a->slot_user && a->ent_item && a->ent_user && a->urow_user && a->q_buf && a->dq_buf &&
+                a->loss_part && a->lse && a->scan_tmp && a->err_flag && a->totals && a->loss, RSB200_EINVAL, "null workspace pointer");
+    if (a->grouping == 0) {
+        RSB_REQUIRE(a->off_item && a->slot_neg && a->slot_pos && a->urow_item, RSB200_EINVAL, "null workspace pointer (grouping 0)");
+    } else {
+        RSB_REQUIRE(a->bin_shift >= kMinBinShift && a->bin_shift <= kMaxBinShift, RSB200_EINVAL,
+                    "bin_shift must be in [%d, %d]", kMinBinShift, kMaxBinShift);
+        RSB_REQUIRE(a->B <= ((int64_t)1 << (31 - a->bin_shift)), RSB200_EUNSUPPORTED,
+                    "B = %lld does not fit the %d query bits of a binned entry", (long long)a->B, 31 - a->bin_shift);
+        RSB_REQUIRE(a->bin_cnt && a->bin_off && a->bin_cursor && a->bin_status && a->bin_ticket && a->bin_heavy, RSB200_EINVAL,
+                    "null bin workspace pointer (grouping 1)");
+        RSB_REQUIRE(a->variant != 7 && a->variant != 6, RSB200_EUNSUPPORTED, "variants 6 / 7 belong to grouping 0");
+    }
     return 0;
 }
 
@@ -127,23 +147,34 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
     const int64_t B = a->B, n = a->n;
     const int32_t* neg32 = a->neg_i32 ? a->neg_i32 : a->neg32_buf;
 
+    const bool bins = a->grouping == 1;
+    const int nbins = bins ? (int)cdiv(a->num_items, (int64_t)1 << a->bin_shift) : 0;
     if (phases & RSB200_PHASE_COUNT) {
-        RSB_CUDA(cudaMemsetAsync(a->off_item, 0, sizeof(uint32_t) * (size_t)(a->num_items + 1), st));
         RSB_CUDA(cudaMemsetAsync(a->off_user, 0, sizeof(uint32_t) * (size_t)(a->num_users + 1), st));
-        if (a->neg_i32) rc = launch_count<int32_t>(a->neg_i32, B * n, a->num_items, a->off_item, a->slot_neg, nullptr, a->err_flag, st);
-        else            rc = launch_count<int64_t>(a->neg_i64, B * n, a->num_items, a->off_item, a->slot_neg, a->neg32_buf, a->err_flag, st);
-        if (rc) return rc;
-        rc = launch_count<int64_t>(a->pos, B, a->num_items, a->off_item, a->slot_pos, nullptr, a->err_flag, st);
-        if (rc) return rc;
+        if (bins) {
+            if (a->neg_i32) rc = launch_bin_count<int32_t>(a->neg_i32, B * n, a->pos, B, a->num_items, a->bin_shift, nbins, a->bin_cnt,
+                                                           nullptr, a->err_flag, st);
+            else            rc = launch_bin_count<int64_t>(a->neg_i64, B * n, a->pos, B, a->num_items, a->bin_shift, nbins, a->bin_cnt,
+                                                           a->neg32_buf, a->err_flag, st);
+            if (rc) return rc;
+        } else {
+            RSB_CUDA(cudaMemsetAsync(a->off_item, 0, sizeof(uint32_t) * (size_t)(a->num_items + 1), st));
+            if (a->neg_i32) rc = launch_count<int32_t>(a->neg_i32, B * n, a->num_items, a->off_item, a->slot_neg, nullptr, a->err_flag, st);
+            else            rc = launch_count<int64_t>(a->neg_i64, B * n, a->num_items, a->off_item, a->slot_neg, a->neg32_buf, a->err_flag, st);
+            if (rc) return rc;
+            rc = launch_count<int64_t>(a->pos, B, a->num_items, a->off_item, a->slot_pos, nullptr, a->err_flag, st);
+            if (rc) return rc;
+        }
         rc = launch_count<int64_t>(a->user, B, a->num_users, a->off_user, a->slot_user, nullptr, a->err_flag, st);
         if (rc) return rc;
     }
     if (phases & RSB200_PHASE_SCAN) {
-        rc = launch_scan(a->off_item, a->num_items, a->urow_item, a->cap_item, a->totals, a->scan_tmp, a->scan_tmp_elems, st);
+        if (bins) rc = launch_bin_scan(a->bin_cnt, nbins, a->bin_off, a->bin_cursor, kCursorStride, a->bin_status, a->bin_ticket, a->totals, st);
+        else rc = launch_scan(a->off_item, a->num_items, a->urow_item, a->cap_item, a->totals, a->scan_tmp, a->scan_tmp_elems, st);
         if (rc) return rc;
         rc = launch_scan(a->off_user, a->num_users, a->urow_user, a->cap_user, a->totals + 2, a->scan_tmp, a->scan_tmp_elems, st);
         if (rc) return rc;
-        if (a->variant != 6) {       // slot -> absolute entry position while the offsets are L2-resident (variant 6: legacy lookup in FWD)
+        if (!bins && a->variant != 6) {       // slot -> absolute entry position while the offsets are L2-resident (variant 6: legacy lookup in FWD)
             rc = launch_resolve(neg32, a->slot_neg, a->off_item, B * n, st);
             if (rc) return rc;
         }
@@ -167,6 +198,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         p.hint = (a->variant >= 16 && a->variant < 32) ? (a->variant & 7) : 0;   // variants 16..31: L2 eviction hints
         if (a->variant == 32) p.hint = 8;    // timing diagnostic: skip the offset lookups / entry writes (gradients invalid)
         p.ncount = nullptr; p.sp_in = nullptr; p.stats_part = nullptr;
+        p.bin_cursor = bins ? a->bin_cursor : nullptr; p.bin_shift = a->bin_shift; p.bin_bbits = 31 - a->bin_shift;
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
         if (rc) return rc;
@@ -193,7 +225,19 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
             s.lr = a->opt_lr; s.b1 = a->opt_beta1; s.b2 = a->opt_beta2; s.eps = a->opt_eps; s.step_size = a->opt_step_size;
             s.dense = 0; s.accumulate = 0;
         }
-        rc = launch_scatter(s, a->cap_item, st);
+        if (bins) {
+            BinScatterParams b;
+            b.ent = a->ent_item; b.bin_off = a->bin_off; b.status = a->bin_status; b.ticket = a->bin_ticket; b.totals = a->totals;
+            b.heavy_counts = a->bin_heavy; b.src = a->q_buf; b.lse = a->lse; b.w = a->w_item; b.gscale = a->grad_scale_dev;
+            b.rows_out = a->item_rows; b.vals = a->item_vals; b.cap = a->cap_item;
+            b.nbins = nbins; b.shift = a->bin_shift; b.bbits = 31 - a->bin_shift; b.D = (int)a->d;
+            b.ssm_scale = s.ssm_scale; b.dense = s.dense; b.accumulate = s.accumulate; b.euclid = s.euclid;
+            b.opt = s.opt; b.w_rw = s.w_rw; b.s1 = s.s1; b.s2 = s.s2;
+            b.lr = s.lr; b.b1 = s.b1; b.b2 = s.b2; b.eps = s.eps; b.step_size = s.step_size;
+            rc = launch_bin_scatter(b, st);
+        } else {
+            rc = launch_scatter(s, a->cap_item, st);
+        }
         if (rc) return rc;
         ScatterParams u = s;
         u.off = a->off_user; u.urow = a->urow_user; u.totals = a->totals + 2; u.ent = a->ent_user; u.src = a->dq_buf;

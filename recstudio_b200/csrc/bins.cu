@@ -1,0 +1,629 @@
+// bins.cu -- two-level ("binned") grouping of gradient touches and the per-bin gradient scatter.
+//
+// Replaces, for the item table, the N-bucket counting sort of group.cu + scatter.cu (the sparse-row
+// form of embedding_dense_backward, autograd of nn.Embedding at recommender.py:638):
+//
+//   level 1  a table of num_rows rows is cut into bins of 2^shift consecutive rows.  BIN_COUNT builds the
+//            histogram of touches per bin (shared-memory aggregated: one global atomic per CTA and bin),
+//            BIN_SCAN turns it into entry offsets and per-bin append cursors.  The forward kernel
+//            (pair_fwd.cu) appends one 8-byte entry per touch to its bin's list with a cursor atomic:
+//            the tail sector of a list is completed within microseconds, so entries leave L2 as
+//            full sectors (the row-sorted layout of group.cu cost one 32-byte read-modify-write per entry),
+//            and the 10M-counter histogram, its scan, the slot / resolve arrays are gone.
+//   level 2  bin_scatter_kernel: one CTA per bin loads the bin's entries into shared memory, groups them
+//            by row there (counting sort over the 2^shift local rows), and forms every touched row's
+//            gradient  g[row] = sum_e c_e * src[b_e]  exactly once: no fp atomics, no [N,d] zero-fill.
+//            Entries of one row are summed in ascending (query, value) order, so the result does not
+//            depend on the order in which the forward kernel's atomics landed: same inputs => same bits.
+//            The compact sink needs the rank of a bin's first unique row among all unique rows: bins are
+//            taken in ticket order and chained with a decoupled look-back over per-bin status words.
+//
+// Entry: low word = kDirect flag (bit 31) | local row (shift bits) | query index (bbits = 31 - shift bits),
+//        high word = coefficient (flag set) or logit (SampledSoftmax negatives), as in scatter.cu.
+#include "common.cuh"
+#include "kernels.h"
+#include "rowopt.cuh"
+
+namespace rsb {
+
+constexpr int kBsThreads = 256;
+constexpr int kBsWarps = kBsThreads / 32;
+constexpr int kEcap = 4096;                      // entries of one chunk held in shared memory
+constexpr int kMaxBinRows = 1 << kMaxBinShift;   // 4096
+constexpr uint64_t kStAgg = 1ull << 62;          // status word: own unique-row count published
+constexpr uint64_t kStPre = 2ull << 62;          // status word: inclusive prefix published
+constexpr uint32_t kLast = 0x8000u;              // idx flag: last entry of its row
+
+// ------------------------------------------------------------------------------------------ policy
+// bins of 2^shift rows, sized so that a bin receives ~kBinTarget touches on average (one chunk), limited by the
+// bits left for the query index in the entry's low word.  shift < kMinBinShift => the caller uses group.cu.
+int bin_shift_for(int64_t num_rows, int64_t touches, int64_t num_queries) {
+    constexpr double kBinTarget = 3400.0;
+    int qbits = 1;
+    while (((int64_t)1 << qbits) < num_queries) ++qbits;
+    int shift = kMinBinShift;
+    const double want = kBinTarget * (double)num_rows / (double)(touches > 0 ? touches : 1);
+    while (shift < kMaxBinShift && (double)((int64_t)1 << (shift + 1)) <= want) ++shift;
+    if (shift > 31 - qbits) shift = 31 - qbits;
+    return shift;
+}
+
+// ------------------------------------------------------------------------------------------ BIN_COUNT
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+bin_count_kernel(const IdT* __restrict__ ids, int64_t M, const int64_t* __restrict__ pos, int64_t B, int64_t num_rows,
+                 int shift, int nbins, int use_smem, uint32_t* __restrict__ bin_cnt, int32_t* __restrict__ ids32_out,
+                 uint32_t* __restrict__ err_flag) {
+    extern __shared__ uint32_t s_hist[];
+    if (use_smem) {
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    uint32_t* hist = use_smem ? s_hist : bin_cnt;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    constexpr int kPer = 4;
+    for (int64_t base = i0; base < M; base += stride * kPer) {
+        int64_t id[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int64_t i = base + k * stride;
+            id[k] = i < M ? (int64_t)ids[i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int64_t i = base + k * stride;
+            if (id[k] > 0 && id[k] < num_rows) atomicAdd(hist + (id[k] >> shift), 1u);
+            else if (id[k] != 0) bad = true;
+            if (ids32_out && i < M) ids32_out[i] = (id[k] >= 0 && id[k] < num_rows) ? (int32_t)id[k] : 0;
+        }
+    }
+    for (int64_t i = i0; i < B; i += stride) {
+        const int64_t id = pos[i];
+        if (id > 0 && id < num_rows) atomicAdd(hist + (id >> shift), 1u);
+        else if (id != 0) bad = true;
+    }
+    if (bad) *err_flag = 1u;
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(bin_cnt + i, c);
+        }
+    }
+}
+
+template <typename IdT>
+int32_t launch_bin_count(const IdT* ids, int64_t M, const int64_t* pos, int64_t B, int64_t num_rows, int shift, int nbins,
+                         uint32_t* bin_cnt, int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st) {
+    RSB_CUDA(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)nbins, st));
+    if (M + B == 0) return 0;
+    const int use_smem = nbins <= 8192;
+    int64_t blocks = cdiv(M + B, 256 * 16);
+    const int64_t cap = (int64_t)sm_count() * 2;           // few CTAs: one flush of the shared histogram per CTA
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const size_t smem = use_smem ? sizeof(uint32_t) * (size_t)nbins : 0;
+    bin_count_kernel<IdT><<<(unsigned)blocks, 256, smem, st>>>(ids, M, pos, B, num_rows, shift, nbins, use_smem, bin_cnt,
+                                                               ids32_out, err_flag);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+template int32_t launch_bin_count<int32_t>(const int32_t*, int64_t, const int64_t*, int64_t, int64_t, int, int, uint32_t*, int32_t*,
+                                           uint32_t*, cudaStream_t);
+template int32_t launch_bin_count<int64_t>(const int64_t*, int64_t, const int64_t*, int64_t, int64_t, int, int, uint32_t*, int32_t*,
+                                           uint32_t*, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------ BIN_SCAN
+// one CTA: exclusive scan of the bin counts -> bin_off[nbins + 1]; arms the append cursors (cursor[b * stride] =
+// bin_off[b]) and clears the look-back status words and the bin ticket for bin_scatter_kernel.
+__global__ void __launch_bounds__(1024)
+bin_scan_kernel(const uint32_t* __restrict__ bin_cnt, int nbins, uint32_t* __restrict__ bin_off, uint32_t* __restrict__ cursor,
+                int cursor_stride, uint64_t* __restrict__ status, uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0u;
+    __syncthreads();
+    for (int base = 0; base < nbins; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nbins ? bin_cnt[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, tot = 0;
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t x = warp_tot[k];
+            if (k < w) wbase += x;
+            tot += x;
+        }
+        const uint32_t ex = s_carry + wbase + inc - v;
+        if (i < nbins) {
+            bin_off[i] = ex;
+            cursor[(size_t)i * cursor_stride] = ex;
+            status[i] = 0ull;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bin_off[nbins] = s_carry;
+        totals[0] = s_carry;
+        ticket[0] = 0u;
+    }
+}
+
+int32_t launch_bin_scan(const uint32_t* bin_cnt, int nbins, uint32_t* bin_off, uint32_t* cursor, int cursor_stride,
+                        uint64_t* status, uint32_t* ticket, uint32_t* totals, cudaStream_t st) {
+    bin_scan_kernel<<<1, 1024, 0, st>>>(bin_cnt, nbins, bin_off, cursor, cursor_stride, status, ticket, totals);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ BIN_SCATTER
+struct BinSmem {
+    unsigned long long stash[kEcap];   // 32 KB  entries of the current row range, arrival order
+    uint32_t cur[kMaxBinRows];         // 16 KB  row histogram -> exclusive starts -> (after placement) row ends
+    uint16_t urank[kMaxBinRows];       //  8 KB  rank of a row among the bin's touched rows
+    uint16_t idx[kEcap];               //  8 KB  row-sorted position -> stash index | kLast
+    uint16_t scratch[kEcap];           //  8 KB  permutation buffer of the long-segment sort
+    uint32_t warp_tot[kBsWarps];
+    uint32_t bounds[kBsWarps + 1];
+    uint32_t long_rows[192];           // rows with more than kShortSeg entries in the current range (<= kEcap / kShortSeg)
+    uint32_t bin, base, uniq, nst, nlong, ra, rb, giant;
+};
+constexpr uint32_t kShortSeg = 24;
+
+// exclusive scan over the R rows of sm.cur, packed as (count | touched << 16): cur[r] <- start offset of row r,
+// urank[r] <- number of touched rows before r (RANK).  Returns the packed total.  Counts must sum to < 65536.
+template <bool RANK>
+__device__ __forceinline__ uint32_t scan_rows(BinSmem& sm, int R) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int rpt = R >= kBsThreads ? R / kBsThreads : 1;      // rows per thread: 1, 2, 4, 8 or 16 (R is a power of two)
+    const int r0 = t * rpt;
+    uint32_t c[16];                                            // fully unrolled below: stays in registers
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (rpt >= 4) {
+            if (k < rpt) v = *reinterpret_cast<const uint4*>(&sm.cur[r0 + k]);
+        } else if (k == 0) {
+            v.x = (r0 < R) ? sm.cur[r0] : 0u;
+            v.y = (rpt == 2) ? sm.cur[r0 + 1] : 0u;
+        }
+        c[k] = v.x; c[k + 1] = v.y; c[k + 2] = v.z; c[k + 3] = v.w;
+    }
+    uint32_t local = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) local += c[k] + ((c[k] != 0u) ? 0x10000u : 0u);
+    uint32_t inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) sm.warp_tot[w] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kBsWarps; ++k) {
+        const uint32_t x = sm.warp_tot[k];
+        if (k < w) wbase += x;
+        total += x;
+    }
+    uint32_t ex = wbase + inc - local;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < rpt && r0 + k < R) {
+            sm.cur[r0 + k] = ex & 0xFFFFu;
+            if (RANK) sm.urank[r0 + k] = (uint16_t)(ex >> 16);
+        }
+        ex += c[k] + ((c[k] != 0u) ? 0x10000u : 0u);
+    }
+    __syncthreads();
+    return total;
+}
+
+// ascending sort of sm.idx[lo, hi) by the 64-bit entry it points to: one thread, short segments
+__device__ __forceinline__ void sort_segment_small(BinSmem& sm, uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo + 1; i < hi; ++i) {
+        const uint16_t xi = sm.idx[i];
+        const unsigned long long key = sm.stash[xi];
+        uint32_t j = i;
+        while (j > lo && sm.stash[sm.idx[j - 1]] > key) { sm.idx[j] = sm.idx[j - 1]; --j; }
+        sm.idx[j] = xi;
+    }
+}
+
+// the same for a long segment (a hot row), by one warp: final position = number of smaller keys (ties by stash index;
+// equal keys are equal entries, so their order cannot change the sum)
+__device__ __forceinline__ void sort_segment_warp(BinSmem& sm, uint32_t lo, uint32_t hi, int lane) {
+    const uint32_t n = hi - lo;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint16_t xi = sm.idx[lo + i];
+        const unsigned long long key = sm.stash[xi];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint16_t xj = sm.idx[lo + j];
+            const unsigned long long kj = sm.stash[xj];
+            rank += (kj < key || (kj == key && xj < xi)) ? 1u : 0u;
+        }
+        sm.scratch[lo + rank] = xi;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) sm.idx[lo + i] = sm.scratch[lo + i];
+    __syncwarp();
+}
+
+// Decoupled look-back (one thread): sm.base <- number of touched rows in all bins before `bin`; publishes this bin's
+// inclusive prefix.  Bins are taken in ticket order, so every predecessor is resident and publishes its own count
+// without waiting for anybody: the spin cannot deadlock.
+__device__ __forceinline__ void resolve_base(const BinScatterParams& p, BinSmem& sm, uint32_t bin) {
+    uint32_t prefix = 0;
+    for (int64_t j = (int64_t)bin - 1; j >= 0; --j) {
+        unsigned long long v;
+        do { v = *reinterpret_cast<volatile unsigned long long*>(p.status + j); } while ((v >> 62) == 0ull);
+        prefix += (uint32_t)v;
+        if ((v >> 62) == 2ull) break;
+    }
+    if (bin != 0) *reinterpret_cast<volatile unsigned long long*>(p.status + bin) = kStPre | (unsigned long long)(prefix + sm.uniq);
+    if (bin == (uint32_t)p.nbins - 1) p.totals[1] = prefix + sm.uniq;
+    sm.base = prefix;
+}
+
+// write (or apply) the finished gradient of local row lr
+template <int VPL, bool FULL, int OPT>
+__device__ __forceinline__ void flush_row(const BinScatterParams& p, const BinSmem& sm, float4 (&acc)[VPL], float& csum, uint32_t lr,
+                                          uint32_t row0, int lane, const bool (&act)[VPL]) {
+    const int D = p.D;
+    const uint32_t row = row0 + lr;
+    const size_t orow = p.dense ? (size_t)row : (size_t)sm.base + sm.urank[lr];
+#pragma unroll
+    for (int x = 0; x < VPL; ++x) {
+        if (FULL || act[x]) {
+            const int col = lane * 4 + x * 128;
+            float4 a = acc[x];
+            if (p.euclid) {
+                const float4 wv = ldg128(p.w + (size_t)row * D + col);
+                a.x = 2.f * (a.x - csum * wv.x); a.y = 2.f * (a.y - csum * wv.y);
+                a.z = 2.f * (a.z - csum * wv.z); a.w = 2.f * (a.w - csum * wv.w);
+            }
+            if (OPT >= 0) {
+                const OptParams o = {p.lr, p.b1, p.b2, p.eps, p.step_size};
+                opt_update4<(OPT >= 0 ? OPT : 0)>(p.w_rw, p.s1, p.s2, (size_t)row * D + col, a, o);
+            } else {
+                float* dst = p.vals + orow * D + col;
+                if (p.accumulate) {
+                    const float4 o = *reinterpret_cast<const float4*>(dst);
+                    a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                }
+                stg128_stream(dst, a);
+            }
+        }
+        acc[x] = make_float4(0, 0, 0, 0);
+    }
+    csum = 0.f;
+}
+
+// stash[0, m) holds the entries of rows [ra, rb) and cur[] their per-row counts: group, order and sum them
+// (WHOLE: the range is the whole bin, cur already holds the row starts, and the touched rows are reported here)
+template <int VPL, bool FULL, int OPT, bool WHOLE>
+__device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem& sm, uint32_t m, uint32_t row0, float gs,
+                                              const bool (&act)[VPL]) {
+    constexpr int UNR = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);          // query rows in flight per warp
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int D = p.D;
+    const int R = 1 << p.shift;
+    const uint32_t rmask = (uint32_t)R - 1u, bmask = (1u << p.bbits) - 1u;
+    if (!WHOLE) scan_rows<false>(sm, R);                            // counts -> starts
+    for (uint32_t i = t; i < m; i += kBsThreads) {                  // placement: sorted position -> stash index
+        const uint32_t lr = ((uint32_t)sm.stash[i] >> p.bbits) & rmask;
+        sm.idx[atomicAdd(&sm.cur[lr], 1u)] = (uint16_t)i;
+    }
+    if (t == 0) sm.nlong = 0u;
+    __syncthreads();
+    // per row: order its entries by (query, value) -- the arrival order of the forward kernel's atomics must not reach the
+    // floating-point sums -- and flag its last entry
+    for (int r = t; r < R; r += kBsThreads) {
+        const uint32_t e1 = sm.cur[r], e0 = r ? sm.cur[r - 1] : 0u;
+        if (e1 != e0) {
+            if (e1 - e0 > kShortSeg) sm.long_rows[atomicAdd(&sm.nlong, 1u)] = (uint32_t)r;
+            else if (e1 - e0 > 1) sort_segment_small(sm, e0, e1);
+        }
+    }
+    if (WHOLE && t == 0) resolve_base(p, sm, sm.bin);               // as late as possible: predecessors have published by now
+    __syncthreads();
+    for (uint32_t k = warp; k < sm.nlong; k += kBsWarps) {
+        const uint32_t r = sm.long_rows[k];
+        sort_segment_warp(sm, r ? sm.cur[r - 1] : 0u, sm.cur[r], lane);
+    }
+    __syncthreads();
+    for (int r = t; r < R; r += kBsThreads) {
+        const uint32_t e1 = sm.cur[r], e0 = r ? sm.cur[r - 1] : 0u;
+        if (e1 != e0) {
+            sm.idx[e1 - 1] |= kLast;
+            if (WHOLE && p.rows_out && (int64_t)sm.base + sm.urank[r] < p.cap)
+                p.rows_out[(size_t)sm.base + sm.urank[r]] = (int64_t)(row0 + r);
+        }
+    }
+    if (t <= kBsWarps) {        // warp w sums sorted positions [bounds[w], bounds[w + 1]): equal shares snapped to row ends
+        uint32_t b = (uint32_t)(((uint64_t)m * t) / kBsWarps);
+        if (t == kBsWarps) b = m;
+        else if (b > 0) b = sm.cur[((uint32_t)sm.stash[sm.idx[b - 1] & 0x7FFFu] >> p.bbits) & rmask];
+        sm.bounds[t] = b;
+    }
+    __syncthreads();
+    const uint32_t p0 = sm.bounds[warp], p1 = sm.bounds[warp + 1];
+    const float* src_lane = p.src + lane * 4;
+    float4 acc[VPL];
+#pragma unroll
+    for (int x = 0; x < VPL; ++x) acc[x] = make_float4(0, 0, 0, 0);
+    float csum = 0.f;
+    for (uint32_t q0 = p0; q0 < p1; q0 += UNR) {
+        float4 v[UNR][VPL];
+        float cc[UNR];
+        uint32_t lrk[UNR];
+        bool last[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            cc[k] = 0.f; lrk[k] = 0u; last[k] = false;
+#pragma unroll
+            for (int x = 0; x < VPL; ++x) v[k][x] = make_float4(0, 0, 0, 0);
+            if (q0 + k < p1) {
+                const uint32_t ix = sm.idx[q0 + k];
+                const unsigned long long e = sm.stash[ix & 0x7FFFu];
+                const uint32_t lo = (uint32_t)e;
+                const float val = __uint_as_float((uint32_t)(e >> 32));
+                const uint32_t bq = lo & bmask;
+                last[k] = (ix & kLast) != 0u;
+                lrk[k] = (lo >> p.bbits) & rmask;
+                cc[k] = ((lo & kDirect) ? val : expf(val - __ldg(p.lse + bq)) * p.ssm_scale) * gs;
+                const float* srow = src_lane + (size_t)bq * D;
+#pragma unroll
+                for (int x = 0; x < VPL; ++x)
+                    if (FULL || act[x]) v[k][x] = ldg128(srow + x * 128);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+#pragma unroll
+            for (int x = 0; x < VPL; ++x) fma4(acc[x], cc[k], v[k][x]);
+            csum += cc[k];
+            if (last[k]) flush_row<VPL, FULL, OPT>(p, sm, acc, csum, lrk[k], row0, lane, act);   // warp-uniform
+        }
+    }
+    __syncthreads();
+}
+
+// a single row with more than kEcap entries: all warps stream the bin, sum the entries of row `lr` (arrival order),
+// the eight partial sums are added in warp order
+template <int VPL, bool FULL, int OPT>
+__device__ __forceinline__ void process_giant_row(const BinScatterParams& p, BinSmem& sm, uint32_t beg, uint32_t cnt, uint32_t lr,
+                                                  uint32_t row0, float gs, const bool (&act)[VPL]) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int D = p.D;
+    const uint32_t rmask = (1u << p.shift) - 1u, bmask = (1u << p.bbits) - 1u;
+    const float* src_lane = p.src + lane * 4;
+    float4 acc[VPL];
+#pragma unroll
+    for (int x = 0; x < VPL; ++x) acc[x] = make_float4(0, 0, 0, 0);
+    float csum = 0.f;
+    for (uint32_t i0 = warp * 32; i0 < cnt; i0 += kBsThreads) {
+        const uint32_t i = i0 + lane;
+        unsigned long long e = 0ull;
+        bool mine = false;
+        if (i < cnt) {
+            e = __ldg(reinterpret_cast<const unsigned long long*>(p.ent) + beg + i);
+            mine = (((uint32_t)e >> p.bbits) & rmask) == lr;
+        }
+        const uint32_t lo = (uint32_t)e;
+        const uint32_t bq = lo & bmask;
+        float c = 0.f;
+        if (mine) c = ((lo & kDirect) ? __uint_as_float((uint32_t)(e >> 32))
+                                      : expf(__uint_as_float((uint32_t)(e >> 32)) - __ldg(p.lse + bq)) * p.ssm_scale) * gs;
+        uint32_t mask = __ballot_sync(kFull, mine);
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const uint32_t bb = __shfl_sync(kFull, bq, l);
+            const float cl = __shfl_sync(kFull, c, l);
+            const float* srow = src_lane + (size_t)bb * D;
+#pragma unroll
+            for (int x = 0; x < VPL; ++x)
+                if (FULL || act[x]) fma4(acc[x], cl, ldg128(srow + x * 128));
+            csum += cl;
+        }
+    }
+    float* part = reinterpret_cast<float*>(sm.stash);                 // [kBsWarps][D + 1]
+#pragma unroll
+    for (int x = 0; x < VPL; ++x)
+        if (FULL || act[x]) *reinterpret_cast<float4*>(part + (size_t)warp * 516 + lane * 4 + x * 128) = acc[x];
+    if (lane == 0) part[(size_t)warp * 516 + 512] = csum;
+    __syncthreads();
+    if (warp == 0) {
+        csum = 0.f;
+#pragma unroll
+        for (int x = 0; x < VPL; ++x) acc[x] = make_float4(0, 0, 0, 0);
+        for (int w = 0; w < kBsWarps; ++w) {
+#pragma unroll
+            for (int x = 0; x < VPL; ++x)
+                if (FULL || act[x]) {
+                    const float4 a = *reinterpret_cast<const float4*>(part + (size_t)w * 516 + lane * 4 + x * 128);
+                    acc[x].x += a.x; acc[x].y += a.y; acc[x].z += a.z; acc[x].w += a.w;
+                }
+            csum += part[(size_t)w * 516 + 512];
+        }
+        flush_row<VPL, FULL, OPT>(p, sm, acc, csum, lr, row0, lane, act);
+    }
+    __syncthreads();
+}
+
+template <int VPL, bool FULL, int OPT>
+__global__ void __launch_bounds__(kBsThreads, 3)
+bin_scatter_kernel(const BinScatterParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BinSmem& sm = *reinterpret_cast<BinSmem*>(smem_raw);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int R = 1 << p.shift;
+    const uint32_t rmask = (uint32_t)R - 1u;
+    const float gs = p.gscale ? __ldg(p.gscale) : 1.0f;
+    bool act[VPL];
+#pragma unroll
+    for (int x = 0; x < VPL; ++x) act[x] = FULL || (lane * 4 + x * 128) < p.D;
+    constexpr int UNR = 4;
+    uint32_t* gcount = p.heavy_counts + (size_t)blockIdx.x * kMaxBinRows;   // whole-bin row counts of a heavy bin
+
+    for (;;) {
+        __syncthreads();                                              // sm.bin of the previous bin is no longer read
+        if (t == 0) sm.bin = atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const uint32_t bin = sm.bin;
+        if (bin >= (uint32_t)p.nbins) break;
+        const uint32_t beg = __ldg(p.bin_off + bin), end = __ldg(p.bin_off + bin + 1);
+        const uint32_t cnt = end - beg;
+        const uint32_t row0 = bin << p.shift;
+        const bool heavy = cnt > (uint32_t)kEcap;
+
+        // ---- whole-bin pass: per-row touch counts (and, for bins that fit one chunk, the entries themselves)
+        for (int r = t * 4; r < R; r += kBsThreads * 4) *reinterpret_cast<uint4*>(&sm.cur[r]) = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        for (uint32_t i0 = t; i0 < cnt; i0 += kBsThreads * UNR) {
+            unsigned long long e[UNR];
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                const uint32_t i = i0 + k * kBsThreads;
+                e[k] = i < cnt ? __ldcs(reinterpret_cast<const unsigned long long*>(p.ent) + beg + i) : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                const uint32_t i = i0 + k * kBsThreads;
+                if (i < cnt) {
+                    if (!heavy) sm.stash[i] = e[k];
+                    atomicAdd(&sm.cur[((uint32_t)e[k] >> p.bbits) & rmask], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (heavy) {                                                  // keep the counts, scan the presence flags
+            for (int r = t; r < R; r += kBsThreads) {
+                const uint32_t c = sm.cur[r];
+                gcount[r] = c;
+                sm.cur[r] = c ? 1u : 0u;
+            }
+            __syncthreads();
+        }
+        // ---- rank of every touched row inside the bin; publish the bin's unique-row count, then look back for the
+        //      rank of its first row among all touched rows of the table (decoupled look-back over bins in ticket order)
+        const uint32_t tot = scan_rows<true>(sm, R);                  // heavy: cur is scratch after this
+        if (t == 0) {
+            sm.uniq = tot >> 16;
+            *reinterpret_cast<volatile unsigned long long*>(p.status + bin) = (bin == 0 ? kStPre : kStAgg) | (unsigned long long)sm.uniq;
+            if (cnt == 0 || heavy) resolve_base(p, sm, bin);          // else: resolved late, inside process_range
+        }
+        if (cnt == 0) continue;
+        if (!heavy) {                                                 // cur already holds the row starts
+            process_range<VPL, FULL, OPT, true>(p, sm, cnt, row0, gs, act);
+            continue;
+        }
+        __syncthreads();                                              // sm.base
+        // ---- heavy bin: consecutive row ranges of <= kEcap entries, each gathered from the bin's list by its own pass
+        if (p.rows_out) {
+            for (int r = t; r < R; r += kBsThreads)
+                if (gcount[r] && (int64_t)sm.base + sm.urank[r] < p.cap) p.rows_out[(size_t)sm.base + sm.urank[r]] = (int64_t)(row0 + r);
+        }
+        uint32_t ra = 0;
+        while (ra < (uint32_t)R) {
+            if (warp == 0) {                                          // longest range [ra, rb) with <= kEcap entries
+                uint32_t run = 0, rb = ra;
+                bool done = false;
+                while (!done && rb < (uint32_t)R) {
+                    const uint32_t r = rb + lane;
+                    const uint32_t c = r < (uint32_t)R ? gcount[r] : 0u;
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(kFull, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    const uint32_t over = __ballot_sync(kFull, run + inc > (uint32_t)kEcap);
+                    if (over) {
+                        const int l = __ffs(over) - 1;                // first row that does not fit
+                        rb += l;
+                        run += l ? __shfl_sync(kFull, inc, l - 1) : 0u;
+                        done = true;
+                    } else {
+                        run += __shfl_sync(kFull, inc, 31);
+                        rb += 32;
+                    }
+                }
+                if (rb > (uint32_t)R) rb = R;
+                if (lane == 0) {
+                    sm.giant = (rb == ra) ? 1u : 0u;                  // row ra alone exceeds a chunk
+                    sm.ra = ra; sm.rb = (rb == ra) ? ra + 1 : rb; sm.nst = 0u;
+                }
+            }
+            for (int r = t * 4; r < R; r += kBsThreads * 4) *reinterpret_cast<uint4*>(&sm.cur[r]) = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            const uint32_t rb = sm.rb;
+            if (sm.giant) {
+                process_giant_row<VPL, FULL, OPT>(p, sm, beg, cnt, ra, row0, gs, act);
+            } else {
+                for (uint32_t i = t; i < cnt; i += kBsThreads) {
+                    const unsigned long long e = __ldg(reinterpret_cast<const unsigned long long*>(p.ent) + beg + i);
+                    const uint32_t lr = ((uint32_t)e >> p.bbits) & rmask;
+                    if (lr >= ra && lr < rb) {
+                        sm.stash[atomicAdd(&sm.nst, 1u)] = e;
+                        atomicAdd(&sm.cur[lr], 1u);
+                    }
+                }
+                __syncthreads();
+                const uint32_t m = sm.nst;
+                if (m) process_range<VPL, FULL, OPT, false>(p, sm, m, row0, gs, act);
+            }
+            __syncthreads();
+            ra = rb;
+        }
+    }
+}
+
+int64_t bin_scatter_grid() { return (int64_t)sm_count() * 3; }
+
+template <int VPL>
+static int32_t launch_bin_scatter_v(const BinScatterParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(BinSmem);
+    int64_t blocks = bin_scatter_grid();
+    if (blocks > p.nbins) blocks = p.nbins;
+    if (blocks < 1) blocks = 1;
+    const bool full = p.D == 128 * VPL;
+#define RSB_BS(FULLV, OPTV)                                                                                          \
+    do {                                                                                                             \
+        RSB_CUDA(cudaFuncSetAttribute(bin_scatter_kernel<VPL, FULLV, OPTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                                   \
+        bin_scatter_kernel<VPL, FULLV, OPTV><<<(unsigned)blocks, kBsThreads, smem, st>>>(p);                         \
+    } while (0)
+    if (p.opt == 0) { if (full) RSB_BS(true, 0); else RSB_BS(false, 0); }
+    else if (p.opt == 1) { if (full) RSB_BS(true, 1); else RSB_BS(false, 1); }
+    else if (p.opt == 2) { if (full) RSB_BS(true, 2); else RSB_BS(false, 2); }
+    else { if (full) RSB_BS(true, -1); else RSB_BS(false, -1); }
+#undef RSB_BS
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int32_t launch_bin_scatter(const BinScatterParams& p, cudaStream_t st) {
+    if (p.nbins <= 0) return 0;
+    if (p.D <= 128) return launch_bin_scatter_v<1>(p, st);
+    if (p.D <= 256) return launch_bin_scatter_v<2>(p, st);
+    if (p.D <= 512) return launch_bin_scatter_v<4>(p, st);
+    set_error("embedding dim %d > 512 is not supported", p.D);
+    return RSB200_EUNSUPPORTED;
+}
+
+}  // namespace rsb

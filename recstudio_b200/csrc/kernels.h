@@ -21,6 +21,9 @@ struct FwdParams {
     float* cstage;      // [B, n] staged coefficients / logits in touch order (entries are permuted later), or null
     int hint;           // L2 eviction hints: bit 0 rows evict_first, bit 1 offsets evict_last, bit 2 entries evict_last
     // owner-compute (PARTIAL) mode of the row-sharded step, see shard.cu
+    // binned grouping (bins.cu): entries are appended to the list of their row's bin with a cursor atomic
+    uint32_t* bin_cursor;    // [nbins * kCursorStride] or null (= row-sorted positions from slot_neg / off_item)
+    int bin_shift, bin_bbits;
     const int32_t* ncount;   // [B] length of each query's compacted negative list (stride n)
     const float* sp_in;      // [B] positive score (computed by the positive's owner)
     float* stats_part;       // [B, 2] {csum, loss} (BPR) | {m, l} (SSM)
@@ -48,6 +51,38 @@ struct ScatterParams {
     float lr, b1, b2, eps, step_size;
 };
 
+// bins.cu: two-level grouping (bins of 2^shift rows, entries appended per bin, grouped by row in shared memory)
+constexpr int kMinBinShift = 4, kMaxBinShift = 12;
+constexpr int kCursorStride = 8;      // u32 words between two bins' append cursors: one 32-byte sector each
+struct BinScatterParams {
+    const uint64_t* ent;      // entries grouped by bin (arbitrary order inside a bin)
+    const uint32_t* bin_off;  // [nbins + 1]
+    uint64_t* status;         // [nbins] look-back words (cleared by bin_scan)
+    uint32_t* ticket;         // [1]
+    uint32_t* totals;         // totals[1] <- number of touched rows
+    uint32_t* heavy_counts;   // [grid, 4096] per-CTA scratch for bins that exceed one chunk
+    const float* src;         // [B, D]
+    const float* lse;         // [B] or null
+    const float* w;           // table (Euclid only)
+    const float* gscale;      // [1] device upstream gradient or null
+    int64_t* rows_out;        // [cap] or null
+    float* vals;              // compact [cap, D] or dense [num_rows, D]
+    int64_t cap;
+    int nbins, shift, bbits, D;
+    float ssm_scale;
+    int dense, accumulate, euclid;
+    int opt;                  // < 0: gradient sink; 0 SGD, 1 Adagrad, 2 SparseAdam applied in the epilogue
+    float* w_rw; float* s1; float* s2;
+    float lr, b1, b2, eps, step_size;
+};
+int bin_shift_for(int64_t num_rows, int64_t touches, int64_t num_queries);
+int64_t bin_scatter_grid();
+template <typename IdT>
+int32_t launch_bin_count(const IdT* ids, int64_t M, const int64_t* pos, int64_t B, int64_t num_rows, int shift, int nbins,
+                         uint32_t* bin_cnt, int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st);
+int32_t launch_bin_scan(const uint32_t* bin_cnt, int nbins, uint32_t* bin_off, uint32_t* cursor, int cursor_stride,
+                        uint64_t* status, uint32_t* ticket, uint32_t* totals, cudaStream_t st);
+int32_t launch_bin_scatter(const BinScatterParams& p, cudaStream_t st);
 // group.cu
 int64_t scan_tmp_elems(int64_t num_rows);
 template <typename IdT>

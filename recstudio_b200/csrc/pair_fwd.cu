@@ -39,6 +39,14 @@ __device__ __forceinline__ uint64_t pack_entry(uint32_t b_flag, float v) {
     return (uint64_t)b_flag | ((uint64_t)__float_as_uint(v) << 32);
 }
 
+// binned grouping (bins.cu): reserve the next position of the row's bin list; the entry's low word carries the local row
+__device__ __forceinline__ uint32_t bin_reserve(const FwdParams& p, int id) {
+    return atomicAdd(p.bin_cursor + (size_t)((uint32_t)id >> p.bin_shift) * kCursorStride, 1u);
+}
+__device__ __forceinline__ uint32_t bin_low(const FwdParams& p, uint32_t b_flag, int id) {
+    return b_flag | (((uint32_t)id & ((1u << p.bin_shift) - 1u)) << p.bin_bbits);
+}
+
 template <int K, int OFF>
 struct TransposeReduce {
     // K partial sums per lane -> full sums; lane L ends up owning element L / (32 / K0)
@@ -97,11 +105,13 @@ __device__ __forceinline__ BatchMeta load_meta(const FwdParams& p, size_t rowbas
     if (HINT) {        // ids / slots are read exactly once: same eviction priority as the rows
         m.id = valid ? (int)ldg32_hint(reinterpret_cast<const uint32_t*>(p.neg) + rowbase + j, pol) : 0;
         if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
-        m.slot = valid ? ldg32_hint(p.slot_neg + rowbase + j, pol) : kNoSlot;
+        if (p.bin_cursor) m.slot = (valid && m.id != 0) ? 0u : kNoSlot;
+        else m.slot = valid ? ldg32_hint(p.slot_neg + rowbase + j, pol) : kNoSlot;
     } else {
         m.id = valid ? __ldg(p.neg + rowbase + j) : 0;
         if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
-        m.slot = valid ? __ldg(p.slot_neg + rowbase + j) : kNoSlot;
+        if (p.bin_cursor) m.slot = (valid && m.id != 0) ? 0u : kNoSlot;      // binned grouping: no per-touch slot array
+        else m.slot = valid ? __ldg(p.slot_neg + rowbase + j) : kNoSlot;
     }
     m.lq = 0.f;
     if (LOSS == RSB200_LOSS_SSM && p.logq_neg != nullptr && valid) m.lq = __ldg(p.logq_neg + rowbase + j);
@@ -270,8 +280,12 @@ __device__ __forceinline__ void finish_query(const FwdParams& p, WarpState<VPL>&
         p.loss_part[b] = loss_b;
         if (LOSS == RSB200_LOSS_SSM) p.lse[b] = lse_b;
         if (p.pos_score) p.pos_score[b] = sp;
-        uint32_t sl = p.slot_pos[b];
-        if (sl != kNoSlot) p.ent_item[__ldg(p.off_item + pid) + sl] = pack_entry((uint32_t)b | kDirect, cpos);
+        if (p.bin_cursor) {
+            if (pid != 0) p.ent_item[bin_reserve(p, (int)pid)] = pack_entry(bin_low(p, (uint32_t)b | kDirect, (int)pid), cpos);
+        } else {
+            uint32_t sl = p.slot_pos[b];
+            if (sl != kNoSlot) p.ent_item[__ldg(p.off_item + pid) + sl] = pack_entry((uint32_t)b | kDirect, cpos);
+        }
         uint32_t su = p.slot_user[b];
         if (su != kNoSlot) p.ent_user[__ldg(p.off_user + uid) + su] = pack_entry((uint32_t)b | kDirect, 1.0f);
     }
@@ -383,7 +397,8 @@ pair_fwd_kernel(const FwdParams p) {
         uint32_t epos = 0;
         if (HINT && (p.hint & 8)) cur.slot = kNoSlot;        // variant 32 (timing diagnostic only): no grouping metadata
         if (cur.slot != kNoSlot)                                                  // consumed after the groups
-            epos = p.slot_abs ? cur.slot
+            epos = p.bin_cursor ? bin_reserve(p, cur.id)
+                 : p.slot_abs ? cur.slot
                               : (HINT ? ldg32_hint(p.off_item + cur.id, pol_off) : __ldg(p.off_item + cur.id)) + cur.slot;
         st.val_out = 0.f; st.sc_out = 0.f;
 
@@ -405,8 +420,11 @@ pair_fwd_kernel(const FwdParams p) {
             }
             if (valid) {
                 if (p.neg_score) p.neg_score[rowbase + jb + lane] = st.sc_out;
-                if (cur.slot != kNoSlot)
-                    p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
+                if (cur.slot != kNoSlot) {
+                    uint32_t low = (uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u);
+                    if (p.bin_cursor) low = bin_low(p, low, cur.id);
+                    p.ent_item[epos] = pack_entry(low, st.val_out);
+                }
             }
             cur = nxt; nxt = nn;
         } else {
@@ -431,7 +449,9 @@ pair_fwd_kernel(const FwdParams p) {
                 if (p.cstage) {
                     p.cstage[rowbase + jb + lane] = st.val_out;          // touch order: coalesced; permuted into ent later
                 } else if (cur.slot != kNoSlot) {
-                    const uint64_t en = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
+                    uint32_t low = (uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u);
+                    if (p.bin_cursor) low = bin_low(p, low, cur.id);
+                    const uint64_t en = pack_entry(low, st.val_out);
                     if (HINT) stg64_hint(p.ent_item + epos, en, pol_ent);
                     else p.ent_item[epos] = en;
                 }
@@ -570,7 +590,7 @@ pair_fwd_tma_kernel(const FwdParams p) {
     st.csum = 0.f; st.lossacc = 0.f; st.m_run = -INFINITY; st.l_run = 0.f;
     st.val_out = 0.f; st.sc_out = 0.f;
     uint32_t epos = 0;
-    if (cur.slot != kNoSlot) epos = p.slot_abs ? cur.slot : __ldg(p.off_item + cur.id) + cur.slot;
+    if (cur.slot != kNoSlot) epos = p.bin_cursor ? bin_reserve(p, cur.id) : (p.slot_abs ? cur.slot : __ldg(p.off_item + cur.id) + cur.slot);
 
     int batch = 0;
     for (int gi = 0; gi < total_groups; ++gi) {
@@ -588,15 +608,18 @@ pair_fwd_tma_kernel(const FwdParams p) {
         if (g == NG - 1 || gi == total_groups - 1) {            // batch complete: emit and rotate metadata
             if (jb + lane < j1) {
                 if (p.neg_score) p.neg_score[rowbase + jb + lane] = st.sc_out;
-                if (cur.slot != kNoSlot)
-                    p.ent_item[epos] = pack_entry((uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u), st.val_out);
+                if (cur.slot != kNoSlot) {
+                    uint32_t low = (uint32_t)b | (LOSS == RSB200_LOSS_BPR ? kDirect : 0u);
+                    if (p.bin_cursor) low = bin_low(p, low, cur.id);
+                    p.ent_item[epos] = pack_entry(low, st.val_out);
+                }
             }
             ++batch;
             cur = nxt; nxt = nn;
             const int jn = j0 + (batch + 2) * 32;
             if (jn < j1) nn = load_meta<LOSS>(p, rowbase, jn, j1, lane);
             epos = 0;
-            if (cur.slot != kNoSlot) epos = p.slot_abs ? cur.slot : __ldg(p.off_item + cur.id) + cur.slot;
+            if (cur.slot != kNoSlot) epos = p.bin_cursor ? bin_reserve(p, cur.id) : (p.slot_abs ? cur.slot : __ldg(p.off_item + cur.id) + cur.slot);
             st.val_out = 0.f; st.sc_out = 0.f;
         }
     }

@@ -12,6 +12,7 @@ training_step + loss.backward()
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -32,7 +33,7 @@ class PairWorkspace:
 
     def __init__(self, num_items: int, num_users: int, B: int, n: int, d: int, device,
                  sink: str = "compact", want_scores: bool = False, stage_entries: bool = False, cap_item: Optional[int] = None,
-                 alloc_vals: bool = True):
+                 alloc_vals: bool = True, grouping: Optional[int] = None, bin_shift: Optional[int] = None):
         _lib.require_cuda()
         self.device = torch.device(device)
         self.shape = (num_items, num_users, B, n, d)
@@ -46,17 +47,34 @@ class PairWorkspace:
         def buf(nelem, dtype):
             return torch.empty(max(int(nelem), 1), dtype=dtype, device=dev)
 
-        self.off_item = buf(sz.off_item, u32)
+        # grouping of the item-side touches: 1 = bins (csrc/bins.cu, the default wherever the library offers a bin size),
+        # 0 = N-bucket counting sort (csrc/group.cu); RSB200_GROUPING overrides for A/B runs
+        if grouping is None:
+            grouping = int(os.environ.get("RSB200_GROUPING", "1"))
+        if stage_entries or not sz.bin_shift:
+            grouping = 0
+        self.grouping = int(grouping)
+        self.bin_shift = int(bin_shift if bin_shift is not None else os.environ.get("RSB200_BIN_SHIFT", sz.bin_shift)) if self.grouping else 0
+        if self.grouping:
+            nbins = -(-num_items // (1 << self.bin_shift))
+            self.nbins = nbins
+            self.bin_cnt, self.bin_off = buf(nbins, u32), buf(nbins + 1, u32)
+            self.bin_cursor, self.bin_status = buf(nbins * 8, u32), buf(nbins, i64)
+            self.bin_ticket, self.bin_heavy = torch.zeros(1, dtype=u32, device=dev), buf(sz.bin_heavy, u32)
+            self.off_item = self.slot_neg = self.slot_pos = self.urow_item = None
+        else:
+            self.off_item = buf(sz.off_item, u32)
+            self.slot_neg = buf(sz.slot_neg, u32)
+            self.slot_pos = buf(sz.slot_pos, u32)
         self.off_user = buf(sz.off_user, u32)
         self.neg32_buf = buf(sz.neg32_buf, i32)
-        self.slot_neg = buf(sz.slot_neg, u32)
-        self.slot_pos = buf(sz.slot_pos, u32)
         self.slot_user = buf(sz.slot_user, u32)
         self.ent_item = buf(sz.ent_item, i64)
         self.ent_user = buf(sz.ent_user, i64)
         self.cap_item = int(cap_item) if cap_item is not None else int(sz.cap_item)
         self.cap_user = int(sz.cap_user)
-        self.urow_item = buf(self.cap_item, u32)
+        if not self.grouping:
+            self.urow_item = buf(self.cap_item, u32)
         self.urow_user = buf(self.cap_user, u32)
         self.q_buf = buf(sz.q_buf, f32)
         self.dq_buf = buf(sz.dq_buf, f32)
@@ -158,6 +176,10 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
     a.urow_item, a.urow_user = ptr(ws.urow_item), ptr(ws.urow_user)
     a.q_buf, a.dq_buf, a.loss_part, a.lse = ptr(ws.q_buf), ptr(ws.dq_buf), ptr(ws.loss_part), ptr(ws.lse)
     a.scan_tmp, a.err_flag = ptr(ws.scan_tmp), ptr(ws.err_flag)
+    a.grouping, a.bin_shift = ws.grouping, ws.bin_shift
+    if ws.grouping:
+        a.bin_cnt, a.bin_off, a.bin_cursor = ptr(ws.bin_cnt), ptr(ws.bin_off), ptr(ws.bin_cursor)
+        a.bin_status, a.bin_ticket, a.bin_heavy = ptr(ws.bin_status), ptr(ws.bin_ticket), ptr(ws.bin_heavy)
     a.num_items, a.num_users, a.B, a.n, a.d = num_items, num_users, B, n, d
     a.cap_item, a.cap_user, a.scan_tmp_elems = ws.cap_item, ws.cap_user, ws.scan_tmp.numel()
     a.grad_scale = float(grad_scale)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(L):
     assert len(names) >= 20
     missing = [s for s in names if not hasattr(L, s)]
     assert not missing, missing
-    assert L.rsb200_version() == 100
+    assert L.rsb200_version() == 200
     assert L.rsb200_sizeof_pair_args() == C.sizeof(_lib.PairArgs)
 
 
