@@ -224,20 +224,22 @@ typedef struct rsb200_pair_args {
                                       * random 8-byte write per touch inside the row stream.  Measured at config 2: forward
                                       * 0.786 -> 0.703 ms, permute pass +0.097 ms: the random writes cost the same wherever
                                       * they run, so the direct write stays the default. */
-    /* Binned grouping of the item-side touches (grouping = 1; csrc/bins.cu).  The table is cut into bins of 2^bin_shift
-     * consecutive rows; PHASE_COUNT histograms the touches per bin, PHASE_SCAN turns the histogram into list offsets and
-     * append cursors, PHASE_FWD appends each touch's entry to its bin's list, and PHASE_SCATTER groups one bin's entries by
-     * row inside shared memory and writes every touched row once (deterministic: a row's entries are summed in ascending
-     * (query, value) order).  off_item / slot_neg / slot_pos / urow_item are then unused and may be NULL.  grouping = 0 is
-     * the N-bucket counting sort of round 1 (csrc/group.cu + scatter.cu), kept for A/B runs and for shapes the bins do not
-     * cover (rsb200_pair_workspace_sizes reports bin_shift = 0 for those). */
+    /* Binned grouping of the touches (grouping = 1; csrc/bins.cu).  Each table is cut into bins of 2^bin_shift consecutive
+     * rows; PHASE_COUNT histograms the touches per bin, PHASE_SCAN turns the histograms into list offsets and append
+     * cursors, PHASE_FWD appends each touch's entry to its bin's list, and PHASE_SCATTER groups one bin's entries by row
+     * inside shared memory and writes every touched row once (deterministic: a row's entries are summed in ascending order
+     * of their encoding, whatever order the appends landed in).  off_* / slot_* / urow_* / scan_tmp are then unused and may be
+     * NULL.  The bin arrays hold the item table's bins first, then the user table's (nbins_item + nbins_user elements;
+     * bin_off has one more per table).  grouping = 0 is the N-bucket counting sort of round 1 (csrc/group.cu + scatter.cu),
+     * kept for A/B runs and for shapes the bins do not cover (rsb200_pair_workspace_sizes reports bin_shift = 0 for those). */
     int32_t   grouping;
-    int32_t   bin_shift;
-    uint32_t* bin_cnt;               /* [nbins], nbins = ceil(num_items / 2^bin_shift)                       */
-    uint32_t* bin_off;               /* [nbins + 1]                                                          */
-    uint32_t* bin_cursor;            /* [nbins * 8]  one 32-byte sector per bin                              */
-    uint64_t* bin_status;            /* [nbins]      look-back words of the compact sink                     */
-    uint32_t* bin_ticket;            /* [1]                                                                  */
+    int32_t   bin_shift;             /* item table: rows per bin = 2^bin_shift                               */
+    int32_t   bin_shift_user;        /* user table                                                           */
+    uint32_t* bin_cnt;               /* [nbins_item + nbins_user], nbins = ceil(rows / 2^shift)              */
+    uint32_t* bin_off;               /* [nbins_item + 1 + nbins_user + 1]                                    */
+    uint32_t* bin_cursor;            /* [(nbins_item + nbins_user) * 8]  one 32-byte sector per bin          */
+    uint64_t* bin_status;            /* [nbins_item + nbins_user]  look-back words of the compact sink       */
+    uint32_t* bin_ticket;            /* [2]                                                                  */
     uint32_t* bin_heavy;             /* [bin_heavy elements] per-CTA scratch for bins with more than 4096 touches */
 } rsb200_pair_args;
 
@@ -246,8 +248,8 @@ typedef struct rsb200_pair_args {
 typedef struct rsb200_pair_sizes {
     int64_t off_item, off_user, neg32_buf, slot_neg, slot_pos, slot_user, ent_item, ent_user,
             urow_item, urow_user, q_buf, dq_buf, loss_part, lse, scan_tmp, cap_item, cap_user,
-            bin_shift /* suggested rows-per-bin exponent, 0 = use grouping 0 */, nbins, bin_cnt, bin_off, bin_cursor,
-            bin_status, bin_heavy;
+            bin_shift /* suggested rows-per-bin exponent of the item table, 0 = use grouping 0 */, bin_shift_user,
+            nbins /* item table */, nbins_user, bin_cnt, bin_off, bin_cursor, bin_status, bin_heavy;
 } rsb200_pair_sizes;
 int32_t rsb200_pair_workspace_sizes(int64_t num_items, int64_t num_users, int64_t B, int64_t n, int64_t d,
                                     rsb200_pair_sizes* out);

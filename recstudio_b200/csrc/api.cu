@@ -86,15 +86,18 @@ extern "C" int32_t rsb200_pair_workspace_sizes(int64_t num_items, int64_t num_us
     o->lse = B;
     int64_t a = scan_tmp_elems(num_items), b = scan_tmp_elems(num_users);
     o->scan_tmp = a > b ? a : b;
-    // binned grouping of the item side (bins.cu)
-    const int shift = bin_shift_for(num_items, B * (n + 1), B);
-    o->bin_shift = shift >= kMinBinShift ? shift : 0;
-    o->nbins = o->bin_shift ? cdiv(num_items, (int64_t)1 << shift) : 0;
-    o->bin_cnt = o->nbins;
-    o->bin_off = o->nbins + 1;
-    o->bin_cursor = o->nbins * kCursorStride;
-    o->bin_status = o->nbins;
-    o->bin_heavy = o->bin_shift ? bin_scatter_grid() * ((int64_t)1 << kMaxBinShift) : 0;
+    // binned grouping (bins.cu)
+    const int shift = bin_shift_for(num_items, B * (n + 1), B), shift_u = bin_shift_for(num_users, B, B);
+    const bool ok = shift >= kMinBinShift && shift_u >= kMinBinShift && B * d < ((int64_t)1 << 30);
+    o->bin_shift = ok ? shift : 0;
+    o->bin_shift_user = ok ? shift_u : 0;
+    o->nbins = ok ? cdiv(num_items, (int64_t)1 << shift) : 0;
+    o->nbins_user = ok ? cdiv(num_users, (int64_t)1 << shift_u) : 0;
+    o->bin_cnt = o->nbins + o->nbins_user;
+    o->bin_off = o->bin_cnt + 2;
+    o->bin_cursor = o->bin_cnt * kCursorStride;
+    o->bin_status = o->bin_cnt;
+    o->bin_heavy = ok ? bin_scatter_grid() * ((int64_t)1 << kMaxBinShift) : 0;
     return 0;
 }
 
@@ -124,18 +127,20 @@ static int32_t check_pair(const rsb200_pair_args* a) {
                     RSB200_EINVAL, "optimizer state2 missing");
     }
     RSB_REQUIRE(a->grouping == 0 || a->grouping == 1, RSB200_EINVAL, "grouping must be 0 (counting sort) or 1 (bins)");
-    RSB_REQUIRE(a->off_user && a->slot_user && a->ent_item && a->ent_user && a->urow_user && a->q_buf && a->dq_buf &&
-                a->loss_part && a->lse && a->scan_tmp && a->err_flag && a->totals && a->loss, RSB200_EINVAL, "null workspace pointer");
+    RSB_REQUIRE(a->ent_item && a->ent_user && a->q_buf && a->dq_buf && a->loss_part && a->lse && a->err_flag && a->totals && a->loss,
+                RSB200_EINVAL, "null workspace pointer");
     if (a->grouping == 0) {
-        RSB_REQUIRE(a->off_item && a->slot_neg && a->slot_pos && a->urow_item, RSB200_EINVAL, "null workspace pointer (grouping 0)");
+        RSB_REQUIRE(a->off_item && a->slot_neg && a->slot_pos && a->urow_item && a->off_user && a->slot_user && a->urow_user &&
+                    a->scan_tmp, RSB200_EINVAL, "null workspace pointer (grouping 0)");
     } else {
-        RSB_REQUIRE(a->bin_shift >= kMinBinShift && a->bin_shift <= kMaxBinShift, RSB200_EINVAL,
-                    "bin_shift must be in [%d, %d]", kMinBinShift, kMaxBinShift);
-        RSB_REQUIRE(a->B <= ((int64_t)1 << (31 - a->bin_shift)), RSB200_EUNSUPPORTED,
-                    "B = %lld does not fit the %d query bits of a binned entry", (long long)a->B, 31 - a->bin_shift);
+        RSB_REQUIRE(a->bin_shift >= kMinBinShift && a->bin_shift <= kMaxBinShift && a->bin_shift_user >= kMinBinShift &&
+                    a->bin_shift_user <= kMaxBinShift, RSB200_EINVAL, "bin_shift / bin_shift_user must be in [%d, %d]", kMinBinShift, kMaxBinShift);
+        RSB_REQUIRE(a->B <= ((int64_t)1 << (31 - (a->bin_shift > a->bin_shift_user ? a->bin_shift : a->bin_shift_user))), RSB200_EUNSUPPORTED,
+                    "B = %lld does not fit the query bits of a binned entry", (long long)a->B);
         RSB_REQUIRE(a->bin_cnt && a->bin_off && a->bin_cursor && a->bin_status && a->bin_ticket && a->bin_heavy, RSB200_EINVAL,
                     "null bin workspace pointer (grouping 1)");
         RSB_REQUIRE(a->variant != 7 && a->variant != 6, RSB200_EUNSUPPORTED, "variants 6 / 7 belong to grouping 0");
+        RSB_REQUIRE(a->B * a->d < ((int64_t)1 << 30), RSB200_EUNSUPPORTED, "B * d must be < 2^30 (32-bit byte offsets into the query matrix)");
     }
     return 0;
 }
@@ -148,35 +153,45 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
     const int32_t* neg32 = a->neg_i32 ? a->neg_i32 : a->neg32_buf;
 
     const bool bins = a->grouping == 1;
-    const int nbins = bins ? (int)cdiv(a->num_items, (int64_t)1 << a->bin_shift) : 0;
+    BinTable ti = {}, tu = {};
+    if (bins) {
+        ti.nbins = (int)cdiv(a->num_items, (int64_t)1 << a->bin_shift); ti.shift = a->bin_shift; ti.num_rows = a->num_items;
+        tu.nbins = (int)cdiv(a->num_users, (int64_t)1 << a->bin_shift_user); tu.shift = a->bin_shift_user; tu.num_rows = a->num_users;
+        ti.cnt = a->bin_cnt; ti.off = a->bin_off; ti.cursor = a->bin_cursor; ti.status = a->bin_status; ti.ticket = a->bin_ticket;
+        ti.totals = a->totals;
+        tu.cnt = a->bin_cnt + ti.nbins; tu.off = a->bin_off + ti.nbins + 1; tu.cursor = a->bin_cursor + (size_t)ti.nbins * kCursorStride;
+        tu.status = a->bin_status + ti.nbins; tu.ticket = a->bin_ticket + 1; tu.totals = a->totals + 2;
+    }
     if (phases & RSB200_PHASE_COUNT) {
-        RSB_CUDA(cudaMemsetAsync(a->off_user, 0, sizeof(uint32_t) * (size_t)(a->num_users + 1), st));
         if (bins) {
-            if (a->neg_i32) rc = launch_bin_count<int32_t>(a->neg_i32, B * n, a->pos, B, a->num_items, a->bin_shift, nbins, a->bin_cnt,
-                                                           nullptr, a->err_flag, st);
-            else            rc = launch_bin_count<int64_t>(a->neg_i64, B * n, a->pos, B, a->num_items, a->bin_shift, nbins, a->bin_cnt,
-                                                           a->neg32_buf, a->err_flag, st);
+            if (a->neg_i32) rc = launch_bin_count<int32_t>(a->neg_i32, B * n, a->pos, B, ti, a->user, B, tu, nullptr, a->err_flag, st);
+            else            rc = launch_bin_count<int64_t>(a->neg_i64, B * n, a->pos, B, ti, a->user, B, tu, a->neg32_buf, a->err_flag, st);
             if (rc) return rc;
         } else {
             RSB_CUDA(cudaMemsetAsync(a->off_item, 0, sizeof(uint32_t) * (size_t)(a->num_items + 1), st));
+            RSB_CUDA(cudaMemsetAsync(a->off_user, 0, sizeof(uint32_t) * (size_t)(a->num_users + 1), st));
             if (a->neg_i32) rc = launch_count<int32_t>(a->neg_i32, B * n, a->num_items, a->off_item, a->slot_neg, nullptr, a->err_flag, st);
             else            rc = launch_count<int64_t>(a->neg_i64, B * n, a->num_items, a->off_item, a->slot_neg, a->neg32_buf, a->err_flag, st);
             if (rc) return rc;
             rc = launch_count<int64_t>(a->pos, B, a->num_items, a->off_item, a->slot_pos, nullptr, a->err_flag, st);
             if (rc) return rc;
+            rc = launch_count<int64_t>(a->user, B, a->num_users, a->off_user, a->slot_user, nullptr, a->err_flag, st);
+            if (rc) return rc;
         }
-        rc = launch_count<int64_t>(a->user, B, a->num_users, a->off_user, a->slot_user, nullptr, a->err_flag, st);
-        if (rc) return rc;
     }
     if (phases & RSB200_PHASE_SCAN) {
-        if (bins) rc = launch_bin_scan(a->bin_cnt, nbins, a->bin_off, a->bin_cursor, kCursorStride, a->bin_status, a->bin_ticket, a->totals, st);
-        else rc = launch_scan(a->off_item, a->num_items, a->urow_item, a->cap_item, a->totals, a->scan_tmp, a->scan_tmp_elems, st);
-        if (rc) return rc;
-        rc = launch_scan(a->off_user, a->num_users, a->urow_user, a->cap_user, a->totals + 2, a->scan_tmp, a->scan_tmp_elems, st);
-        if (rc) return rc;
-        if (!bins && a->variant != 6) {       // slot -> absolute entry position while the offsets are L2-resident (variant 6: legacy lookup in FWD)
-            rc = launch_resolve(neg32, a->slot_neg, a->off_item, B * n, st);
+        if (bins) {
+            rc = launch_bin_scan(ti, tu, st);
             if (rc) return rc;
+        } else {
+            rc = launch_scan(a->off_item, a->num_items, a->urow_item, a->cap_item, a->totals, a->scan_tmp, a->scan_tmp_elems, st);
+            if (rc) return rc;
+            rc = launch_scan(a->off_user, a->num_users, a->urow_user, a->cap_user, a->totals + 2, a->scan_tmp, a->scan_tmp_elems, st);
+            if (rc) return rc;
+            if (a->variant != 6) {       // slot -> absolute entry position while the offsets are L2-resident (variant 6: legacy lookup in FWD)
+                rc = launch_resolve(neg32, a->slot_neg, a->off_item, B * n, st);
+                if (rc) return rc;
+            }
         }
     }
     if (phases & RSB200_PHASE_FWD) {
@@ -198,7 +213,8 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         p.hint = (a->variant >= 16 && a->variant < 32) ? (a->variant & 7) : 0;   // variants 16..31: L2 eviction hints
         if (a->variant == 32) p.hint = 8;    // timing diagnostic: skip the offset lookups / entry writes (gradients invalid)
         p.ncount = nullptr; p.sp_in = nullptr; p.stats_part = nullptr;
-        p.bin_cursor = bins ? a->bin_cursor : nullptr; p.bin_shift = a->bin_shift; p.bin_bbits = 31 - a->bin_shift;
+        p.bin_cursor = bins ? ti.cursor : nullptr; p.bin_shift = a->bin_shift; p.bin_bbits = 31 - a->bin_shift;
+        p.bin_cursor_user = bins ? tu.cursor : nullptr; p.bin_shift_user = a->bin_shift_user;
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
         if (rc) return rc;
@@ -227,17 +243,24 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         }
         if (bins) {
             BinScatterParams b;
-            b.ent = a->ent_item; b.bin_off = a->bin_off; b.status = a->bin_status; b.ticket = a->bin_ticket; b.totals = a->totals;
+            b.ent = a->ent_item; b.bin_off = ti.off; b.status = ti.status; b.ticket = ti.ticket; b.totals = ti.totals;
             b.heavy_counts = a->bin_heavy; b.src = a->q_buf; b.lse = a->lse; b.w = a->w_item; b.gscale = a->grad_scale_dev;
             b.rows_out = a->item_rows; b.vals = a->item_vals; b.cap = a->cap_item;
-            b.nbins = nbins; b.shift = a->bin_shift; b.bbits = 31 - a->bin_shift; b.D = (int)a->d;
+            b.nbins = ti.nbins; b.shift = ti.shift; b.bbits = 31 - ti.shift; b.D = (int)a->d;
             b.ssm_scale = s.ssm_scale; b.dense = s.dense; b.accumulate = s.accumulate; b.euclid = s.euclid;
             b.opt = s.opt; b.w_rw = s.w_rw; b.s1 = s.s1; b.s2 = s.s2;
             b.lr = s.lr; b.b1 = s.b1; b.b2 = s.b2; b.eps = s.eps; b.step_size = s.step_size;
+            b.tune = (a->variant >= 50 && a->variant < 60) ? a->variant - 50 : 0;      // variants 51..53: scatter depth / occupancy A/B
             rc = launch_bin_scatter(b, st);
-        } else {
-            rc = launch_scatter(s, a->cap_item, st);
+            if (rc) return rc;
+            // user table: every entry is (query b, 1.0) and the source rows are d loss / d query
+            b.ent = a->ent_user; b.bin_off = tu.off; b.status = tu.status; b.ticket = tu.ticket; b.totals = tu.totals;
+            b.src = a->dq_buf; b.lse = nullptr; b.w = a->w_user; b.rows_out = a->user_rows; b.vals = a->user_vals; b.cap = a->cap_user;
+            b.nbins = tu.nbins; b.shift = tu.shift; b.bbits = 31 - tu.shift; b.euclid = 0;
+            if (a->sink == RSB200_SINK_APPLY) { b.w_rw = a->w_user_rw; b.s1 = a->user_state1; b.s2 = a->user_state2; }
+            return launch_bin_scatter(b, st);
         }
+        rc = launch_scatter(s, a->cap_item, st);
         if (rc) return rc;
         ScatterParams u = s;
         u.off = a->off_user; u.urow = a->urow_user; u.totals = a->totals + 2; u.ent = a->ent_user; u.src = a->dq_buf;

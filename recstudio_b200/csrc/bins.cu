@@ -13,8 +13,8 @@
 //   level 2  bin_scatter_kernel: one CTA per bin loads the bin's entries into shared memory, groups them
 //            by row there (counting sort over the 2^shift local rows), and forms every touched row's
 //            gradient  g[row] = sum_e c_e * src[b_e]  exactly once: no fp atomics, no [N,d] zero-fill.
-//            Entries of one row are summed in ascending (query, value) order, so the result does not
-//            depend on the order in which the forward kernel's atomics landed: same inputs => same bits.
+//            Entries of one row are summed in ascending order of their 64-bit encoding, so the result does
+//            not depend on the order in which the forward kernel's atomics landed: same inputs => same bits.
 //            The compact sink needs the rank of a bin's first unique row among all unique rows: bins are
 //            taken in ticket order and chained with a decoupled look-back over per-bin status words.
 //
@@ -33,6 +33,8 @@ constexpr int kMaxBinRows = 1 << kMaxBinShift;   // 4096
 constexpr uint64_t kStAgg = 1ull << 62;          // status word: own unique-row count published
 constexpr uint64_t kStPre = 2ull << 62;          // status word: inclusive prefix published
 constexpr uint32_t kLast = 0x8000u;              // idx flag: last entry of its row
+constexpr int kBsDepth = 16;                     // query-row loads in flight per warp (d <= 128)
+constexpr int kBsOcc = 2;                        // CTAs per SM
 
 // ------------------------------------------------------------------------------------------ policy
 // bins of 2^shift rows, sized so that a bin receives ~kBinTarget touches on average (one chunk), limited by the
@@ -49,17 +51,22 @@ int bin_shift_for(int64_t num_rows, int64_t touches, int64_t num_queries) {
 }
 
 // ------------------------------------------------------------------------------------------ BIN_COUNT
+// Histogram of the touches per bin for up to two tables in one launch: table 0 is touched by ids[M] and pos[B]
+// (negatives and positives of the item table), table 1 by ids1[B1] (the user table).  Every CTA aggregates in shared
+// memory and flushes once: one global atomic per CTA and non-empty bin.
 template <typename IdT>
 __global__ void __launch_bounds__(256)
-bin_count_kernel(const IdT* __restrict__ ids, int64_t M, const int64_t* __restrict__ pos, int64_t B, int64_t num_rows,
-                 int shift, int nbins, int use_smem, uint32_t* __restrict__ bin_cnt, int32_t* __restrict__ ids32_out,
+bin_count_kernel(const IdT* __restrict__ ids, int64_t M, const int64_t* __restrict__ pos, int64_t B, const BinTable t0,
+                 const int64_t* __restrict__ ids1, int64_t B1, const BinTable t1, int use_smem, int32_t* __restrict__ ids32_out,
                  uint32_t* __restrict__ err_flag) {
     extern __shared__ uint32_t s_hist[];
+    const int nb0 = t0.nbins, nb1 = t1.nbins;
     if (use_smem) {
-        for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0u;
+        for (int i = threadIdx.x; i < nb0 + nb1; i += blockDim.x) s_hist[i] = 0u;
         __syncthreads();
     }
-    uint32_t* hist = use_smem ? s_hist : bin_cnt;
+    uint32_t* h0 = use_smem ? s_hist : t0.cnt;
+    uint32_t* h1 = use_smem ? s_hist + nb0 : t1.cnt;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool bad = false;
@@ -74,66 +81,72 @@ bin_count_kernel(const IdT* __restrict__ ids, int64_t M, const int64_t* __restri
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
             const int64_t i = base + k * stride;
-            if (id[k] > 0 && id[k] < num_rows) atomicAdd(hist + (id[k] >> shift), 1u);
+            if (id[k] > 0 && id[k] < t0.num_rows) atomicAdd(h0 + (id[k] >> t0.shift), 1u);
             else if (id[k] != 0) bad = true;
-            if (ids32_out && i < M) ids32_out[i] = (id[k] >= 0 && id[k] < num_rows) ? (int32_t)id[k] : 0;
+            if (ids32_out && i < M) ids32_out[i] = (id[k] >= 0 && id[k] < t0.num_rows) ? (int32_t)id[k] : 0;
         }
     }
     for (int64_t i = i0; i < B; i += stride) {
         const int64_t id = pos[i];
-        if (id > 0 && id < num_rows) atomicAdd(hist + (id >> shift), 1u);
+        if (id > 0 && id < t0.num_rows) atomicAdd(h0 + (id >> t0.shift), 1u);
+        else if (id != 0) bad = true;
+    }
+    for (int64_t i = i0; i < B1; i += stride) {
+        const int64_t id = ids1[i];
+        if (id > 0 && id < t1.num_rows) atomicAdd(h1 + (id >> t1.shift), 1u);
         else if (id != 0) bad = true;
     }
     if (bad) *err_flag = 1u;
     if (use_smem) {
         __syncthreads();
-        for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+        for (int i = threadIdx.x; i < nb0 + nb1; i += blockDim.x) {
             const uint32_t c = s_hist[i];
-            if (c) atomicAdd(bin_cnt + i, c);
+            if (c) atomicAdd(i < nb0 ? t0.cnt + i : t1.cnt + (i - nb0), c);
         }
     }
 }
 
 template <typename IdT>
-int32_t launch_bin_count(const IdT* ids, int64_t M, const int64_t* pos, int64_t B, int64_t num_rows, int shift, int nbins,
-                         uint32_t* bin_cnt, int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st) {
-    RSB_CUDA(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)nbins, st));
-    if (M + B == 0) return 0;
-    const int use_smem = nbins <= 8192;
-    int64_t blocks = cdiv(M + B, 256 * 16);
+int32_t launch_bin_count(const IdT* ids, int64_t M, const int64_t* pos, int64_t B, const BinTable& t0, const int64_t* ids1,
+                         int64_t B1, const BinTable& t1, int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st) {
+    RSB_CUDA(cudaMemsetAsync(t0.cnt, 0, sizeof(uint32_t) * (size_t)t0.nbins, st));
+    if (t1.nbins) RSB_CUDA(cudaMemsetAsync(t1.cnt, 0, sizeof(uint32_t) * (size_t)t1.nbins, st));
+    if (M + B + B1 == 0) return 0;
+    const int use_smem = t0.nbins + t1.nbins <= 8192;
+    int64_t blocks = cdiv(M + B + B1, 256 * 16);
     const int64_t cap = (int64_t)sm_count() * 2;           // few CTAs: one flush of the shared histogram per CTA
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    const size_t smem = use_smem ? sizeof(uint32_t) * (size_t)nbins : 0;
-    bin_count_kernel<IdT><<<(unsigned)blocks, 256, smem, st>>>(ids, M, pos, B, num_rows, shift, nbins, use_smem, bin_cnt,
-                                                               ids32_out, err_flag);
+    const size_t smem = use_smem ? sizeof(uint32_t) * (size_t)(t0.nbins + t1.nbins) : 0;
+    bin_count_kernel<IdT><<<(unsigned)blocks, 256, smem, st>>>(ids, M, pos, B, t0, ids1, B1, t1, use_smem, ids32_out, err_flag);
     RSB_LAUNCH_CHECK();
     return 0;
 }
-template int32_t launch_bin_count<int32_t>(const int32_t*, int64_t, const int64_t*, int64_t, int64_t, int, int, uint32_t*, int32_t*,
-                                           uint32_t*, cudaStream_t);
-template int32_t launch_bin_count<int64_t>(const int64_t*, int64_t, const int64_t*, int64_t, int64_t, int, int, uint32_t*, int32_t*,
-                                           uint32_t*, cudaStream_t);
+template int32_t launch_bin_count<int32_t>(const int32_t*, int64_t, const int64_t*, int64_t, const BinTable&, const int64_t*, int64_t,
+                                           const BinTable&, int32_t*, uint32_t*, cudaStream_t);
+template int32_t launch_bin_count<int64_t>(const int64_t*, int64_t, const int64_t*, int64_t, const BinTable&, const int64_t*, int64_t,
+                                           const BinTable&, int32_t*, uint32_t*, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------ BIN_SCAN
-// one CTA: exclusive scan of the bin counts -> bin_off[nbins + 1]; arms the append cursors (cursor[b * stride] =
-// bin_off[b]) and clears the look-back status words and the bin ticket for bin_scatter_kernel.
+// one CTA per table: exclusive scan of the bin counts -> off[nbins + 1]; arms the append cursors (cursor[b * stride] =
+// off[b]) and clears the look-back status words and the bin ticket for bin_scatter_kernel.
 __global__ void __launch_bounds__(1024)
-bin_scan_kernel(const uint32_t* __restrict__ bin_cnt, int nbins, uint32_t* __restrict__ bin_off, uint32_t* __restrict__ cursor,
-                int cursor_stride, uint64_t* __restrict__ status, uint32_t* __restrict__ ticket, uint32_t* __restrict__ totals) {
+bin_scan_kernel(const BinTable t0, const BinTable t1) {
+    const BinTable& t = blockIdx.x == 0 ? t0 : t1;
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_carry;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nbins = t.nbins;
     if (threadIdx.x == 0) s_carry = 0u;
     __syncthreads();
     for (int base = 0; base < nbins; base += 1024) {
         const int i = base + threadIdx.x;
-        const uint32_t v = i < nbins ? bin_cnt[i] : 0u;
+        const uint32_t v = i < nbins ? t.cnt[i] : 0u;
         uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += t;
+            const uint32_t x = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += x;
         }
         if (lane == 31) warp_tot[w] = inc;
         __syncthreads();
@@ -145,24 +158,23 @@ bin_scan_kernel(const uint32_t* __restrict__ bin_cnt, int nbins, uint32_t* __res
         }
         const uint32_t ex = s_carry + wbase + inc - v;
         if (i < nbins) {
-            bin_off[i] = ex;
-            cursor[(size_t)i * cursor_stride] = ex;
-            status[i] = 0ull;
+            t.off[i] = ex;
+            t.cursor[(size_t)i * kCursorStride] = ex;
+            t.status[i] = 0ull;
         }
         __syncthreads();
         if (threadIdx.x == 0) s_carry += tot;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        bin_off[nbins] = s_carry;
-        totals[0] = s_carry;
-        ticket[0] = 0u;
+        t.off[nbins] = s_carry;
+        t.totals[0] = s_carry;
+        t.ticket[0] = 0u;
     }
 }
 
-int32_t launch_bin_scan(const uint32_t* bin_cnt, int nbins, uint32_t* bin_off, uint32_t* cursor, int cursor_stride,
-                        uint64_t* status, uint32_t* ticket, uint32_t* totals, cudaStream_t st) {
-    bin_scan_kernel<<<1, 1024, 0, st>>>(bin_cnt, nbins, bin_off, cursor, cursor_stride, status, ticket, totals);
+int32_t launch_bin_scan(const BinTable& t0, const BinTable& t1, cudaStream_t st) {
+    bin_scan_kernel<<<t1.nbins ? 2 : 1, 1024, 0, st>>>(t0, t1);
     RSB_LAUNCH_CHECK();
     return 0;
 }
@@ -175,7 +187,6 @@ struct BinSmem {
     uint16_t idx[kEcap];               //  8 KB  row-sorted position -> stash index | kLast
     uint16_t scratch[kEcap];           //  8 KB  permutation buffer of the long-segment sort
     uint32_t warp_tot[kBsWarps];
-    uint32_t bounds[kBsWarps + 1];
     uint32_t long_rows[192];           // rows with more than kShortSeg entries in the current range (<= kEcap / kShortSeg)
     uint32_t bin, base, uniq, nst, nlong, ra, rb, giant;
 };
@@ -262,20 +273,34 @@ __device__ __forceinline__ void sort_segment_warp(BinSmem& sm, uint32_t lo, uint
     __syncwarp();
 }
 
-// Decoupled look-back (one thread): sm.base <- number of touched rows in all bins before `bin`; publishes this bin's
-// inclusive prefix.  Bins are taken in ticket order, so every predecessor is resident and publishes its own count
-// without waiting for anybody: the spin cannot deadlock.
-__device__ __forceinline__ void resolve_base(const BinScatterParams& p, BinSmem& sm, uint32_t bin) {
+// Decoupled look-back by ONE WARP: sm.base <- number of touched rows in all bins before `bin`; publishes this bin's
+// inclusive prefix.  The warp inspects 32 predecessors per round trip (all resident CTAs took their tickets at about the
+// same time, so a one-thread walk would cross ~300 unresolved bins at one L2 round trip each).  Bins are taken in ticket
+// order, so every predecessor is resident and publishes its own count without waiting for anybody: no deadlock.
+__device__ __forceinline__ void resolve_base(const BinScatterParams& p, BinSmem& sm, uint32_t bin, int lane) {
     uint32_t prefix = 0;
-    for (int64_t j = (int64_t)bin - 1; j >= 0; --j) {
-        unsigned long long v;
-        do { v = *reinterpret_cast<volatile unsigned long long*>(p.status + j); } while ((v >> 62) == 0ull);
-        prefix += (uint32_t)v;
-        if ((v >> 62) == 2ull) break;
+    int64_t j = (int64_t)bin - 1;
+    while (j >= 0) {
+        const int64_t k = j - lane;
+        // the virtual predecessor of bin 0 is an inclusive prefix of 0
+        const unsigned long long v = k >= 0 ? *reinterpret_cast<volatile unsigned long long*>(p.status + k) : kStPre;
+        const uint32_t flag = (uint32_t)(v >> 62);
+        const uint32_t pmask = __ballot_sync(kFull, flag == 2u), zmask = __ballot_sync(kFull, flag == 0u);
+        const int first_p = pmask ? __ffs(pmask) - 1 : 32;
+        const uint32_t need = first_p >= 31 ? 0xFFFFFFFFu : ((2u << first_p) - 1u);   // lanes 0 .. first_p
+        if (zmask & need) continue;                                   // somebody in the window has not published yet
+        uint32_t x = (lane <= first_p) ? (uint32_t)v : 0u;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+        prefix += x;
+        if (first_p < 32) break;
+        j -= 32;
     }
-    if (bin != 0) *reinterpret_cast<volatile unsigned long long*>(p.status + bin) = kStPre | (unsigned long long)(prefix + sm.uniq);
-    if (bin == (uint32_t)p.nbins - 1) p.totals[1] = prefix + sm.uniq;
-    sm.base = prefix;
+    if (lane == 0) {
+        if (bin != 0) *reinterpret_cast<volatile unsigned long long*>(p.status + bin) = kStPre | (unsigned long long)(prefix + sm.uniq);
+        if (bin == (uint32_t)p.nbins - 1) p.totals[1] = prefix + sm.uniq;
+        sm.base = prefix;
+    }
 }
 
 // write (or apply) the finished gradient of local row lr
@@ -314,10 +339,14 @@ __device__ __forceinline__ void flush_row(const BinScatterParams& p, const BinSm
 
 // stash[0, m) holds the entries of rows [ra, rb) and cur[] their per-row counts: group, order and sum them
 // (WHOLE: the range is the whole bin, cur already holds the row starts, and the touched rows are reported here)
-template <int VPL, bool FULL, int OPT, bool WHOLE>
+// PLAIN: compact sink, inner product, overwrite, no optimizer -- the touched rows of a range have consecutive ranks, so
+// the output is a running pointer and a finished row costs one 16-byte store per lane.
+template <int VPL, bool FULL, int OPT, bool WHOLE, bool PLAIN, int DEPTH>
 __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem& sm, uint32_t m, uint32_t row0, float gs,
                                               const bool (&act)[VPL]) {
-    constexpr int UNR = VPL == 1 ? 4 : (VPL == 2 ? 2 : 1);          // query rows in flight per warp
+    // query rows in flight per warp.  The loop is latency-bound (entry -> query row from L2 -> FMA, ~1.2 us per
+    // round trip): throughput = rows in flight per SM / latency, so registers are spent on depth (2 CTAs/SM, 128 regs)
+    constexpr int UNR = VPL == 1 ? DEPTH : (VPL == 2 ? DEPTH / 2 : DEPTH / 4);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int D = p.D;
     const int R = 1 << p.shift;
@@ -329,8 +358,8 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
     }
     if (t == 0) sm.nlong = 0u;
     __syncthreads();
-    // per row: order its entries by (query, value) -- the arrival order of the forward kernel's atomics must not reach the
-    // floating-point sums -- and flag its last entry
+    // per row: order its entries by their 64-bit encoding -- the arrival order of the forward kernel's atomics must not
+    // reach the floating-point sums -- and flag its last entry
     for (int r = t; r < R; r += kBsThreads) {
         const uint32_t e1 = sm.cur[r], e0 = r ? sm.cur[r - 1] : 0u;
         if (e1 != e0) {
@@ -338,7 +367,10 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
             else if (e1 - e0 > 1) sort_segment_small(sm, e0, e1);
         }
     }
-    if (WHOLE && t == 0) resolve_base(p, sm, sm.bin);               // as late as possible: predecessors have published by now
+    if (WHOLE && warp == 0) {                                       // as late as possible: predecessors have published by now
+        __syncwarp();
+        resolve_base(p, sm, sm.bin, lane);
+    }
     __syncthreads();
     for (uint32_t k = warp; k < sm.nlong; k += kBsWarps) {
         const uint32_t r = sm.long_rows[k];
@@ -353,50 +385,71 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
                 p.rows_out[(size_t)sm.base + sm.urank[r]] = (int64_t)(row0 + r);
         }
     }
-    if (t <= kBsWarps) {        // warp w sums sorted positions [bounds[w], bounds[w + 1]): equal shares snapped to row ends
-        uint32_t b = (uint32_t)(((uint64_t)m * t) / kBsWarps);
-        if (t == kBsWarps) b = m;
-        else if (b > 0) b = sm.cur[((uint32_t)sm.stash[sm.idx[b - 1] & 0x7FFFu] >> p.bbits) & rmask];
-        sm.bounds[t] = b;
-    }
     __syncthreads();
-    const uint32_t p0 = sm.bounds[warp], p1 = sm.bounds[warp + 1];
-    const float* src_lane = p.src + lane * 4;
+    // warp w sums the sorted positions [bound(w), bound(w + 1)): equal shares of the range snapped to row ends
+    auto bound = [&](int w) -> uint32_t {
+        if (w >= kBsWarps) return m;
+        uint32_t b = (uint32_t)(((uint64_t)m * (uint32_t)w) / kBsWarps);
+        if (b > 0) b = sm.cur[((uint32_t)sm.stash[sm.idx[b - 1] & 0x7FFFu] >> p.bbits) & rmask];
+        return b;
+    };
+    const uint32_t p0 = bound(warp), p1 = bound(warp + 1);
+    const char* src_lane = reinterpret_cast<const char*>(p.src) + lane * 16;   // 32-bit byte offsets below: B * D * 4 < 2^32
+    const uint32_t row_bytes = (uint32_t)D * 4u;
     float4 acc[VPL];
 #pragma unroll
     for (int x = 0; x < VPL; ++x) acc[x] = make_float4(0, 0, 0, 0);
     float csum = 0.f;
-    for (uint32_t q0 = p0; q0 < p1; q0 += UNR) {
-        float4 v[UNR][VPL];
-        float cc[UNR];
-        uint32_t lrk[UNR];
-        bool last[UNR];
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) {
-            cc[k] = 0.f; lrk[k] = 0u; last[k] = false;
-#pragma unroll
-            for (int x = 0; x < VPL; ++x) v[k][x] = make_float4(0, 0, 0, 0);
-            if (q0 + k < p1) {
-                const uint32_t ix = sm.idx[q0 + k];
-                const unsigned long long e = sm.stash[ix & 0x7FFFu];
-                const uint32_t lo = (uint32_t)e;
-                const float val = __uint_as_float((uint32_t)(e >> 32));
-                const uint32_t bq = lo & bmask;
-                last[k] = (ix & kLast) != 0u;
-                lrk[k] = (lo >> p.bbits) & rmask;
-                cc[k] = ((lo & kDirect) ? val : expf(val - __ldg(p.lse + bq)) * p.ssm_scale) * gs;
-                const float* srow = src_lane + (size_t)bq * D;
-#pragma unroll
-                for (int x = 0; x < VPL; ++x)
-                    if (FULL || act[x]) v[k][x] = ldg128(srow + x * 128);
-            }
+    float* dst_run = nullptr;                                          // PLAIN: output row of the current (unfinished) row
+    if (PLAIN && p0 < p1) {
+        const uint32_t lr0 = ((uint32_t)sm.stash[sm.idx[p0] & 0x7FFFu] >> p.bbits) & rmask;
+        dst_run = p.vals + ((size_t)sm.base + sm.urank[lr0]) * D + lane * 4;
+    }
+    for (uint32_t q0 = p0; q0 < p1; q0 += 32) {
+        // lane l decodes entry q0 + l of the sorted list (coefficient incl. the softmax denominator and the upstream gradient)
+        uint32_t bq = 0u, meta = 0u;                                   // meta = local row | last-of-row << 31
+        float c = 0.f;
+        if (q0 + lane < p1) {
+            const uint32_t ix = sm.idx[q0 + lane];
+            const unsigned long long e = sm.stash[ix & 0x7FFFu];
+            const uint32_t lo = (uint32_t)e;
+            const float val = __uint_as_float((uint32_t)(e >> 32));
+            bq = (lo & bmask) * row_bytes;                             // byte offset of the query row
+            meta = ((lo >> p.bbits) & rmask) | ((ix & kLast) ? 0x80000000u : 0u);
+            c = ((lo & kDirect) ? val : expf(val - __ldg(p.lse + (lo & bmask))) * p.ssm_scale) * gs;
         }
+        const uint32_t lastmask = __ballot_sync(kFull, (meta >> 31) != 0u);
+        const int cnt = (int)min(32u, p1 - q0);
+        for (int t0 = 0; t0 < cnt; t0 += UNR) {                        // lanes >= cnt hold (offset 0, c = 0): harmless
+            float4 v[UNR][VPL];
+            float cc[UNR];
 #pragma unroll
-        for (int k = 0; k < UNR; ++k) {
+            for (int k = 0; k < UNR; ++k) {
+                const uint32_t off = __shfl_sync(kFull, bq, t0 + k);
+                cc[k] = __shfl_sync(kFull, c, t0 + k);
+                const float* srow = reinterpret_cast<const float*>(src_lane + off);
 #pragma unroll
-            for (int x = 0; x < VPL; ++x) fma4(acc[x], cc[k], v[k][x]);
-            csum += cc[k];
-            if (last[k]) flush_row<VPL, FULL, OPT>(p, sm, acc, csum, lrk[k], row0, lane, act);   // warp-uniform
+                for (int x = 0; x < VPL; ++x) v[k][x] = (FULL || act[x]) ? ldg128(srow + x * 128) : make_float4(0, 0, 0, 0);
+            }
+            const uint32_t lm = lastmask >> t0;
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+#pragma unroll
+                for (int x = 0; x < VPL; ++x) fma4(acc[x], cc[k], v[k][x]);
+                if (!PLAIN) csum += cc[k];
+                if ((lm >> k) & 1u) {                                  // warp-uniform: this row is complete
+                    if (PLAIN) {
+#pragma unroll
+                        for (int x = 0; x < VPL; ++x) {
+                            if (FULL || act[x]) stg128_stream(dst_run + x * 128, acc[x]);
+                            acc[x] = make_float4(0, 0, 0, 0);
+                        }
+                        dst_run += D;
+                    } else {
+                        flush_row<VPL, FULL, OPT>(p, sm, acc, csum, __shfl_sync(kFull, meta, t0 + k) & 0x7FFFFFFFu, row0, lane, act);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -465,8 +518,8 @@ __device__ __forceinline__ void process_giant_row(const BinScatterParams& p, Bin
     __syncthreads();
 }
 
-template <int VPL, bool FULL, int OPT>
-__global__ void __launch_bounds__(kBsThreads, 3)
+template <int VPL, bool FULL, int OPT, bool PLAIN, int DEPTH, int OCC>
+__global__ void __launch_bounds__(kBsThreads, OCC)
 bin_scatter_kernel(const BinScatterParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BinSmem& sm = *reinterpret_cast<BinSmem*>(smem_raw);
@@ -525,11 +578,14 @@ bin_scatter_kernel(const BinScatterParams p) {
         if (t == 0) {
             sm.uniq = tot >> 16;
             *reinterpret_cast<volatile unsigned long long*>(p.status + bin) = (bin == 0 ? kStPre : kStAgg) | (unsigned long long)sm.uniq;
-            if (cnt == 0 || heavy) resolve_base(p, sm, bin);          // else: resolved late, inside process_range
+        }
+        if (warp == 0 && (cnt == 0 || heavy)) {                       // else: resolved late, inside process_range
+            __syncwarp();
+            resolve_base(p, sm, bin, lane);
         }
         if (cnt == 0) continue;
         if (!heavy) {                                                 // cur already holds the row starts
-            process_range<VPL, FULL, OPT, true>(p, sm, cnt, row0, gs, act);
+            process_range<VPL, FULL, OPT, true, PLAIN, DEPTH>(p, sm, cnt, row0, gs, act);
             continue;
         }
         __syncthreads();                                              // sm.base
@@ -585,7 +641,7 @@ bin_scatter_kernel(const BinScatterParams p) {
                 }
                 __syncthreads();
                 const uint32_t m = sm.nst;
-                if (m) process_range<VPL, FULL, OPT, false>(p, sm, m, row0, gs, act);
+                if (m) process_range<VPL, FULL, OPT, false, PLAIN, DEPTH>(p, sm, m, row0, gs, act);
             }
             __syncthreads();
             ra = rb;
@@ -593,28 +649,37 @@ bin_scatter_kernel(const BinScatterParams p) {
     }
 }
 
-int64_t bin_scatter_grid() { return (int64_t)sm_count() * 3; }
+int64_t bin_scatter_grid() { return (int64_t)sm_count() * 3; }          // upper bound over the configurations below (sizes bin_heavy)
+
+template <int VPL, bool FULL, int OPT, bool PLAIN, int DEPTH, int OCC>
+static int32_t launch_bs(const BinScatterParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(BinSmem);
+    int64_t blocks = (int64_t)sm_count() * OCC;
+    if (blocks > p.nbins) blocks = p.nbins;
+    if (blocks < 1) blocks = 1;
+    RSB_CUDA(cudaFuncSetAttribute(bin_scatter_kernel<VPL, FULL, OPT, PLAIN, DEPTH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bin_scatter_kernel<VPL, FULL, OPT, PLAIN, DEPTH, OCC><<<(unsigned)blocks, kBsThreads, smem, st>>>(p);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
 
 template <int VPL>
 static int32_t launch_bin_scatter_v(const BinScatterParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(BinSmem);
-    int64_t blocks = bin_scatter_grid();
-    if (blocks > p.nbins) blocks = p.nbins;
-    if (blocks < 1) blocks = 1;
     const bool full = p.D == 128 * VPL;
-#define RSB_BS(FULLV, OPTV)                                                                                          \
-    do {                                                                                                             \
-        RSB_CUDA(cudaFuncSetAttribute(bin_scatter_kernel<VPL, FULLV, OPTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)smem));                                                                   \
-        bin_scatter_kernel<VPL, FULLV, OPTV><<<(unsigned)blocks, kBsThreads, smem, st>>>(p);                         \
-    } while (0)
-    if (p.opt == 0) { if (full) RSB_BS(true, 0); else RSB_BS(false, 0); }
-    else if (p.opt == 1) { if (full) RSB_BS(true, 1); else RSB_BS(false, 1); }
-    else if (p.opt == 2) { if (full) RSB_BS(true, 2); else RSB_BS(false, 2); }
-    else { if (full) RSB_BS(true, -1); else RSB_BS(false, -1); }
-#undef RSB_BS
-    RSB_LAUNCH_CHECK();
-    return 0;
+    const bool plain = !p.dense && !p.accumulate && !p.euclid && p.opt < 0;
+    if (plain && full) {
+        if constexpr (VPL == 1) {                                     // the hot configuration; p.tune: A/B of depth x occupancy
+            if (p.tune == 1) return launch_bs<VPL, true, -1, true, 8, 3>(p, st);
+            if (p.tune == 2) return launch_bs<VPL, true, -1, true, 8, 2>(p, st);
+            if (p.tune == 3) return launch_bs<VPL, true, -1, true, 4, 3>(p, st);
+        }
+        return launch_bs<VPL, true, -1, true, kBsDepth, kBsOcc>(p, st);
+    }
+    if (plain) return launch_bs<VPL, false, -1, true, kBsDepth, kBsOcc>(p, st);
+    if (p.opt == 0) return full ? launch_bs<VPL, true, 0, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, 0, false, kBsDepth, kBsOcc>(p, st);
+    if (p.opt == 1) return full ? launch_bs<VPL, true, 1, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, 1, false, kBsDepth, kBsOcc>(p, st);
+    if (p.opt == 2) return full ? launch_bs<VPL, true, 2, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, 2, false, kBsDepth, kBsOcc>(p, st);
+    return full ? launch_bs<VPL, true, -1, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, -1, false, kBsDepth, kBsOcc>(p, st);
 }
 
 int32_t launch_bin_scatter(const BinScatterParams& p, cudaStream_t st) {

@@ -24,6 +24,7 @@ struct FwdParams {
     // binned grouping (bins.cu): entries are appended to the list of their row's bin with a cursor atomic
     uint32_t* bin_cursor;    // [nbins * kCursorStride] or null (= row-sorted positions from slot_neg / off_item)
     int bin_shift, bin_bbits;
+    uint32_t* bin_cursor_user; int bin_shift_user;    // the same for the user table's entries (null in the owner-compute step)
     const int32_t* ncount;   // [B] length of each query's compacted negative list (stride n)
     const float* sp_in;      // [B] positive score (computed by the positive's owner)
     float* stats_part;       // [B, 2] {csum, loss} (BPR) | {m, l} (SSM)
@@ -74,14 +75,24 @@ struct BinScatterParams {
     int opt;                  // < 0: gradient sink; 0 SGD, 1 Adagrad, 2 SparseAdam applied in the epilogue
     float* w_rw; float* s1; float* s2;
     float lr, b1, b2, eps, step_size;
+    int tune;                 // A/B switch of the hot configuration's (loads in flight, CTAs/SM); 0 = default
 };
 int bin_shift_for(int64_t num_rows, int64_t touches, int64_t num_queries);
 int64_t bin_scatter_grid();
+struct BinTable {             // the bin arrays of one table
+    uint32_t* cnt;            // [nbins] touches per bin
+    uint32_t* off;            // [nbins + 1] entry offsets
+    uint32_t* cursor;         // [nbins * kCursorStride] append cursors
+    uint64_t* status;         // [nbins]
+    uint32_t* ticket;         // [1]
+    uint32_t* totals;         // totals[0] <- entries, totals[1] <- touched rows
+    int nbins, shift;
+    int64_t num_rows;
+};
 template <typename IdT>
-int32_t launch_bin_count(const IdT* ids, int64_t M, const int64_t* pos, int64_t B, int64_t num_rows, int shift, int nbins,
-                         uint32_t* bin_cnt, int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st);
-int32_t launch_bin_scan(const uint32_t* bin_cnt, int nbins, uint32_t* bin_off, uint32_t* cursor, int cursor_stride,
-                        uint64_t* status, uint32_t* ticket, uint32_t* totals, cudaStream_t st);
+int32_t launch_bin_count(const IdT* ids, int64_t M, const int64_t* pos, int64_t B, const BinTable& t0, const int64_t* ids1,
+                         int64_t B1, const BinTable& t1, int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st);
+int32_t launch_bin_scan(const BinTable& t0, const BinTable& t1, cudaStream_t st);
 int32_t launch_bin_scatter(const BinScatterParams& p, cudaStream_t st);
 // group.cu
 int64_t scan_tmp_elems(int64_t num_rows);

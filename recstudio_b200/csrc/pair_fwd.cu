@@ -286,8 +286,16 @@ __device__ __forceinline__ void finish_query(const FwdParams& p, WarpState<VPL>&
             uint32_t sl = p.slot_pos[b];
             if (sl != kNoSlot) p.ent_item[__ldg(p.off_item + pid) + sl] = pack_entry((uint32_t)b | kDirect, cpos);
         }
-        uint32_t su = p.slot_user[b];
-        if (su != kNoSlot) p.ent_user[__ldg(p.off_user + uid) + su] = pack_entry((uint32_t)b | kDirect, 1.0f);
+        if (p.bin_cursor_user) {
+            if (uid != 0) {
+                const uint32_t at = atomicAdd(p.bin_cursor_user + (size_t)((uint32_t)uid >> p.bin_shift_user) * kCursorStride, 1u);
+                const uint32_t lr = ((uint32_t)uid & ((1u << p.bin_shift_user) - 1u)) << (31 - p.bin_shift_user);
+                p.ent_user[at] = pack_entry((uint32_t)b | kDirect | lr, 1.0f);
+            }
+        } else {
+            uint32_t su = p.slot_user[b];
+            if (su != kNoSlot) p.ent_user[__ldg(p.off_user + uid) + su] = pack_entry((uint32_t)b | kDirect, 1.0f);
+        }
     }
 }
 
@@ -619,6 +627,7 @@ pair_fwd_tma_kernel(const FwdParams p) {
             const int jn = j0 + (batch + 2) * 32;
             if (jn < j1) nn = load_meta<LOSS>(p, rowbase, jn, j1, lane);
             epos = 0;
+            if (j0 + batch * 32 >= j1) cur.slot = kNoSlot;          // past the last batch: `cur` is stale -- reserve nothing
             if (cur.slot != kNoSlot) epos = p.bin_cursor ? bin_reserve(p, cur.id) : (p.slot_abs ? cur.slot : __ldg(p.off_item + cur.id) + cur.slot);
             st.val_out = 0.f; st.sc_out = 0.f;
         }

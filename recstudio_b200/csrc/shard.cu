@@ -316,7 +316,7 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         p.num_items = (int)a->local_rows; p.num_users = (int)G; p.B = (int)G; p.n = (int)n; p.D = (int)a->d;
         p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0; p.hint = 0; p.slot_abs = 1; p.cstage = nullptr;
         p.ncount = a->ncount; p.sp_in = a->sp; p.stats_part = a->stats_all + 2 * (size_t)a->rank * (size_t)G;
-        p.bin_cursor = nullptr; p.bin_shift = 0; p.bin_bbits = 0;
+        p.bin_cursor = nullptr; p.bin_shift = 0; p.bin_bbits = 0; p.bin_cursor_user = nullptr; p.bin_shift_user = 0;
         rc = launch_pair_fwd_partial(p, a->loss_kind, a->score_kind, st);
         if (rc) return rc;
     }

@@ -56,31 +56,35 @@ class PairWorkspace:
         self.grouping = int(grouping)
         self.bin_shift = int(bin_shift if bin_shift is not None else os.environ.get("RSB200_BIN_SHIFT", sz.bin_shift)) if self.grouping else 0
         if self.grouping:
-            nbins = -(-num_items // (1 << self.bin_shift))
-            self.nbins = nbins
-            self.bin_cnt, self.bin_off = buf(nbins, u32), buf(nbins + 1, u32)
-            self.bin_cursor, self.bin_status = buf(nbins * 8, u32), buf(nbins, i64)
-            self.bin_ticket, self.bin_heavy = torch.zeros(1, dtype=u32, device=dev), buf(sz.bin_heavy, u32)
+            self.bin_shift_user = int(sz.bin_shift_user)
+            self.nbins = -(-num_items // (1 << self.bin_shift))
+            self.nbins_user = -(-num_users // (1 << self.bin_shift_user))
+            nb = self.nbins + self.nbins_user
+            self.bin_cnt, self.bin_off = buf(nb, u32), buf(nb + 2, u32)
+            self.bin_cursor, self.bin_status = buf(nb * 8, u32), buf(nb, i64)
+            self.bin_ticket, self.bin_heavy = torch.zeros(2, dtype=u32, device=dev), buf(sz.bin_heavy, u32)
             self.off_item = self.slot_neg = self.slot_pos = self.urow_item = None
+            self.off_user = self.slot_user = self.urow_user = self.scan_tmp = None
         else:
+            self.bin_shift_user = 0
             self.off_item = buf(sz.off_item, u32)
             self.slot_neg = buf(sz.slot_neg, u32)
             self.slot_pos = buf(sz.slot_pos, u32)
-        self.off_user = buf(sz.off_user, u32)
+            self.off_user = buf(sz.off_user, u32)
+            self.slot_user = buf(sz.slot_user, u32)
+            self.scan_tmp = buf(sz.scan_tmp, i64)
         self.neg32_buf = buf(sz.neg32_buf, i32)
-        self.slot_user = buf(sz.slot_user, u32)
         self.ent_item = buf(sz.ent_item, i64)
         self.ent_user = buf(sz.ent_user, i64)
         self.cap_item = int(cap_item) if cap_item is not None else int(sz.cap_item)
         self.cap_user = int(sz.cap_user)
         if not self.grouping:
             self.urow_item = buf(self.cap_item, u32)
-        self.urow_user = buf(self.cap_user, u32)
+            self.urow_user = buf(self.cap_user, u32)
         self.q_buf = buf(sz.q_buf, f32)
         self.dq_buf = buf(sz.dq_buf, f32)
         self.loss_part = buf(sz.loss_part, f32)
         self.lse = buf(sz.lse, f32)
-        self.scan_tmp = buf(sz.scan_tmp, i64)
         self.err_flag = torch.zeros(1, dtype=i32, device=dev)
         self.totals = torch.zeros(4, dtype=i32, device=dev)
         self.loss = torch.zeros(1, dtype=f32, device=dev)
@@ -176,12 +180,12 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
     a.urow_item, a.urow_user = ptr(ws.urow_item), ptr(ws.urow_user)
     a.q_buf, a.dq_buf, a.loss_part, a.lse = ptr(ws.q_buf), ptr(ws.dq_buf), ptr(ws.loss_part), ptr(ws.lse)
     a.scan_tmp, a.err_flag = ptr(ws.scan_tmp), ptr(ws.err_flag)
-    a.grouping, a.bin_shift = ws.grouping, ws.bin_shift
+    a.grouping, a.bin_shift, a.bin_shift_user = ws.grouping, ws.bin_shift, ws.bin_shift_user
     if ws.grouping:
         a.bin_cnt, a.bin_off, a.bin_cursor = ptr(ws.bin_cnt), ptr(ws.bin_off), ptr(ws.bin_cursor)
         a.bin_status, a.bin_ticket, a.bin_heavy = ptr(ws.bin_status), ptr(ws.bin_ticket), ptr(ws.bin_heavy)
     a.num_items, a.num_users, a.B, a.n, a.d = num_items, num_users, B, n, d
-    a.cap_item, a.cap_user, a.scan_tmp_elems = ws.cap_item, ws.cap_user, ws.scan_tmp.numel()
+    a.cap_item, a.cap_user, a.scan_tmp_elems = ws.cap_item, ws.cap_user, (ws.scan_tmp.numel() if ws.scan_tmp is not None else 0)
     a.grad_scale = float(grad_scale)
     a.loss_kind, a.score_kind = int(loss_kind), int(score_kind)
     a.sink = _lib.SINK_APPLY if apply is not None else (SINK_DENSE if dense else SINK_COMPACT)
