@@ -458,7 +458,41 @@ typedef struct rsb200_shard_args {
     const uint64_t* regen_state;   /* DEVICE [world, 2] = (seed, philox offset) of every rank, or NULL (ids given in neg) */
     int64_t regen_B;               /* queries per rank (G == world * regen_B)                   */
     int32_t regen_sm_count, regen_max_threads_per_sm;   /* ATen draw policy, as for rsb200_sample_uniform */
+    /* The same for PopularSamplerModel (regen_kind = 1; recstudio/ann/sampler.py:243-258): rank r's ids are
+     * searchsorted(table, torch.rand(regen_B, n, device='cuda')) for its (seed, offset), and an owner needs only ITS slices of
+     * the sampler's buffers: a draw u lands on an owned row iff pop_cdf_lo < u <= pop_cdf_hi (pop_cdf_lo = table[row0 - 1],
+     * -inf for the first owner; pop_cdf_hi = table[row0 + local_rows - 1], +inf for the last), the search runs inside the
+     * slice, and log Q(neg) = log(pop_prob_local[id]) is written to lq_c.  pop_guide_local (optional) holds
+     * first-i-with-table_local[i] >= k / 2^pop_guide_bits for k = pop_guide_k0 ... (rsb200_popular_build_guide_range). */
+    int32_t        regen_kind;         /* 0 UniformSampler, 1 PopularSamplerModel                                */
+    int32_t        pop_guide_bits;
+    const float*   pop_table_local;    /* [local_rows] table[row0 .. row0 + local_rows)                          */
+    const float*   pop_prob_local;     /* [local_rows] pop_prob[row0 .. row0 + local_rows)                       */
+    const int32_t* pop_guide_local;    /* [pop_guide_len] or NULL                                                */
+    int64_t        pop_guide_k0;
+    float          pop_cdf_lo, pop_cdf_hi;
+    float*         lq_pos_out;         /* [G] or NULL: PREP writes log(pop_prob_local[pos]) for owned positives, else 0
+                                          (all-reduce SUM it together with sp to obtain logq_pos for FINISH)     */
+    /* Binned grouping of the owned touches (grouping = 1), exactly as in rsb200_pair_args: bins of 2^bin_shift LOCAL rows;
+     * slot_neg / slot_pos / off / urow / scan_tmp are then unused and may be NULL. */
+    int32_t   grouping;
+    int32_t   bin_shift;
+    uint32_t* bin_cnt;                 /* [nbins], nbins = ceil(local_rows / 2^bin_shift)                        */
+    uint32_t* bin_off;                 /* [nbins + 1]                                                            */
+    uint32_t* bin_cursor;              /* [nbins * 8]                                                            */
+    uint64_t* bin_status;              /* [nbins]                                                                */
+    uint32_t* bin_ticket;              /* [1]                                                                    */
+    uint32_t* bin_heavy;               /* [rsb200_bin_heavy_elems()]                                             */
 } rsb200_shard_args;
+
+/* rows-per-bin exponent the library suggests for a table block of num_rows rows that receives `touches` gradient touches
+ * per step from num_queries queries (0 = not supported: use grouping 0), and the size of the bin_heavy scratch */
+int32_t rsb200_bin_shift(int64_t num_rows, int64_t touches, int64_t num_queries);
+int64_t rsb200_bin_heavy_elems(void);
+/* guide entries k0 .. k0 + len - 1 of a table slice: out[i] = first j in [0, num_rows - 1] with table_local[j] >= (k0 + i) / 2^bits
+ * (num_rows - 1 if none) */
+int32_t rsb200_popular_build_guide_range(const float* table_local, int64_t num_rows, int32_t guide_bits, int64_t k0, int64_t len,
+                                         int32_t* guide_out, void* stream);
 
 int32_t rsb200_shard_step(const rsb200_shard_args* args, int32_t phases, void* stream);
 size_t  rsb200_sizeof_shard_args(void);

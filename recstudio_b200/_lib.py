@@ -101,6 +101,7 @@ def lib():
         L.rsb200_scan_tmp_elems.restype = C.c_int64
         L.rsb200_scan_tmp_elems.argtypes = [C.c_int64]
         L.rsb200_launch_count.restype = C.c_uint64
+        L.rsb200_bin_heavy_elems.restype = C.c_int64
         L.rsb200_philox_counter_offset.restype = C.c_int64
         L.rsb200_philox_counter_offset.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         L.rsb200_topk_workspace_bytes.restype = C.c_size_t
@@ -115,6 +116,8 @@ def lib():
             "rsb200_sample_uniform": [u64, u64, i64, i64, i64, i32, i32, v, v, v],
             "rsb200_sample_uniform_dev": [v, i64, i64, i64, i32, i32, v, v, v],
             "rsb200_popular_build_guide": [v, i64, i32, v, v],
+            "rsb200_popular_build_guide_range": [v, i64, i32, i64, i64, v, v],
+            "rsb200_bin_shift": [i64, i64, i64],
             "rsb200_sample_popular": [u64, u64, v, v, i64, i64, i64, i32, i32, v, i32, v, v, v, v],
             "rsb200_popular_logq": [v, i64, v, i64, v, v],
             "rsb200_masked_workspace_elems": [i64, i64, v, v],

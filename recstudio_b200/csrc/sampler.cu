@@ -272,6 +272,25 @@ extern "C" int32_t rsb200_popular_build_guide(const float* table, int64_t num_it
     return 0;
 }
 
+__global__ void __launch_bounds__(256)
+guide_range_kernel(const float* __restrict__ table, int num_rows, int guide_bits, int64_t k0, int64_t len, int32_t* __restrict__ guide) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    const float u = (float)(k0 + i) / (float)(1 << guide_bits);            // exact (k <= 2^24)
+    guide[i] = lower_bound(table, 0, num_rows - 1, u);
+}
+
+extern "C" int32_t rsb200_popular_build_guide_range(const float* table_local, int64_t num_rows, int32_t guide_bits, int64_t k0,
+                                                    int64_t len, int32_t* guide_out, void* stream) {
+    RSB_REQUIRE(table_local && guide_out, RSB200_EINVAL, "null pointer");
+    RSB_REQUIRE(guide_bits >= 1 && guide_bits <= 24, RSB200_EINVAL, "guide_bits must be in [1, 24]");
+    RSB_REQUIRE(num_rows >= 1 && num_rows < ((int64_t)1 << 31) && k0 >= 0 && len >= 1 && k0 + len - 1 <= ((int64_t)1 << guide_bits) + 1,
+                RSB200_EINVAL, "bad slice / guide range");
+    guide_range_kernel<<<(unsigned)cdiv(len, 256), 256, 0, (cudaStream_t)stream>>>(table_local, (int)num_rows, guide_bits, k0, len, guide_out);
+    RSB_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int32_t rsb200_sample_popular(uint64_t seed, uint64_t philox_offset, const float* table,
                                          const float* pop_prob, int64_t num_items, int64_t num_queries,
                                          int64_t num_neg, int32_t sm_cnt, int32_t max_tpsm,

@@ -162,6 +162,181 @@ shard_resolve_kernel(const int32_t* __restrict__ neg_c, uint32_t* __restrict__ s
     }
 }
 
+// ------------------------------------------------------------------------------------------ PREP, binned grouping
+// One warp per query: candidates -> owned? -> stable compaction to LOCAL ids (+ log Q) + per-bin touch histogram
+// (bins.cu; shared-memory aggregated, persistent CTAs).  Where do the candidates come from (MODE):
+//   0  neg[G, n] global ids all-gathered by the caller;
+//   1  owner-side regeneration of every rank's UniformSampler draw:  torch.randint(1, N, (B, n)) of rank r is
+//      element li = lb * n + j -> ATen thread idx = li mod T, round (li / T) / 4, word (li / T) mod 4.  With T = t * n
+//      the four words of one Philox call belong to the SAME position j of four queries t apart, so a CTA of four warps
+//      takes the queries {4 t R + x + t ii, ii = 0..3} of one rank: every thread computes whole Philox blocks, the ids go
+//      through shared memory, and no random bit is computed twice (the per-query formulation recomputed each block 4x);
+//   2  the same for PopularSamplerModel (sampler.py:243-258): u = torch.rand(B, n) of rank r, id = searchsorted(table, u).
+//      An owner only needs ITS slice of the cumulative table: id lands in [row0, row0 + L) iff cdf_lo < u <= cdf_hi
+//      (cdf_lo = table[row0 - 1], cdf_hi = table[row0 + L - 1]; -inf / +inf at the ends), and the search runs inside the
+//      slice (guide table + short bisection), log Q = log(pop_prob_local[id]).
+struct PrepBinParams {
+    const float* w_local; const float* q_all; const int64_t* pos;
+    const int32_t* neg; const float* logq_neg;
+    int32_t* neg_c; float* lq_c; int32_t* ncount; int32_t* pos_local; float* sp; float* lq_pos_out;
+    uint32_t* err;
+    BinTable bt;
+    int64_t num_items, row0, local_rows;
+    int G, n, D, euclid, use_smem;
+    // regeneration
+    const uint64_t* regen_state; int regen_B; int64_t regen_T; int t_per; int n_round_blocks;
+    const float* pop_table; const float* pop_prob; const int32_t* pop_guide; int pop_bits; int64_t pop_k0;
+    float cdf_lo, cdf_hi;
+};
+
+__device__ __forceinline__ int local_lower_bound(const float* __restrict__ table, int lo, int hi, float u) {
+    // first i in [lo, hi] with table[i] >= u (hi if none): bisection down to <= 8 entries, then independent loads
+    constexpr int kLinear = 8;
+    while (hi - lo > kLinear) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (__ldg(table + mid) < u) lo = mid + 1; else hi = mid;
+    }
+    int id = lo;
+#pragma unroll
+    for (int t = 0; t < kLinear; ++t)
+        if (lo + t < hi) id += (__ldg(table + lo + t) < u) ? 1 : 0;
+    return id;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 4)
+shard_prep_bins_kernel(const PrepBinParams p) {
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* s_hist = s_dyn;                                         // [nbins] (use_smem)
+    uint32_t* s_cand = s_dyn + (p.use_smem ? p.bt.nbins : 0);         // [4][n] candidates of the CTA's four queries (MODE 1, 2)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.D, n = p.n;
+    if (p.use_smem) {
+        for (int i = threadIdx.x; i < p.bt.nbins; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    uint32_t* hist = p.use_smem ? s_hist : p.bt.cnt;
+    bool bad = false;
+    // shared Philox blocks need T = t_per * n; any other shape regenerates per id (t_per = 0: every block computed 4x)
+    const bool shared = MODE != 0 && p.t_per > 0;
+    const int64_t nitems = !shared ? ((int64_t)p.G + 3) / 4 : (int64_t)(p.G / p.regen_B) * p.n_round_blocks * p.t_per;
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        int g;                                                        // global query of this warp, -1 = none
+        uint64_t seed = 0, off = 0;
+        int64_t li0 = 0;                                              // per-id regeneration: first element of the query
+        if (!shared) {
+            g = (int)(item * 4 + warp);
+            if (g >= p.G) g = -1;
+            if (MODE != 0 && g >= 0) {
+                const int r = g / p.regen_B;
+                seed = __ldg(p.regen_state + 2 * r); off = __ldg(p.regen_state + 2 * r + 1);
+                li0 = (int64_t)(g - r * p.regen_B) * n;
+            }
+        } else {
+            const int per_rank = p.n_round_blocks * p.t_per;
+            const int r = (int)(item / per_rank), rem = (int)(item % per_rank);
+            const int R = rem / p.t_per, x = rem % p.t_per;
+            const int lb = 4 * p.t_per * R + x + p.t_per * warp;      // this warp's query inside rank r's batch
+            g = lb < p.regen_B ? r * p.regen_B + lb : -1;
+            // ---- Philox: thread handles positions j = tid, tid + 128, ...; idx = x * n + j, round R
+            seed = __ldg(p.regen_state + 2 * r); off = __ldg(p.regen_state + 2 * r + 1);
+            __syncthreads();                                          // previous item's candidates are consumed
+            for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                const uint4 w = Philox::gen(seed, (uint64_t)((int64_t)x * n + j), off / 4 + (uint64_t)R);
+                const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) s_cand[ii * n + j] = words[ii];
+            }
+            __syncthreads();
+        }
+        if (g < 0) continue;                                          // (whole warp) -- no barrier below depends on it
+
+        // ---- positive: owned? -> score, local row, histogram, log Q
+        int64_t gp = __ldg(p.pos + g);
+        if (gp < 0 || gp >= p.num_items) { bad = true; gp = 0; }
+        const int64_t lp = gp - p.row0;
+        const bool own = lp >= 0 && lp < p.local_rows;
+        float sp = 0.f;
+        if (own) {
+            for (int c = lane * 4; c < D; c += 128) {
+                const float4 qv = ldg128(p.q_all + (size_t)g * D + c);
+                const float4 vv = ldg128(p.w_local + (size_t)lp * D + c);
+                sp += p.euclid ? sqdist4(qv, vv) : dot4(qv, vv);
+            }
+            sp = warp_sum_s(sp);
+            if (p.euclid) sp = -sp;
+        }
+        if (lane == 0) {
+            p.sp[g] = own ? sp : 0.f;
+            p.pos_local[g] = own ? (int32_t)lp : -1;
+            if (own && gp != 0) atomicAdd(hist + (lp >> p.bt.shift), 1u);
+            if (p.lq_pos_out) p.lq_pos_out[g] = own ? logf(__ldg(p.pop_prob + lp)) : 0.f;
+        }
+
+        // ---- negatives
+        const size_t base = (size_t)g * n;
+        int kept = 0;
+        for (int jb = 0; jb < n; jb += 32) {
+            const int j = jb + lane;
+            const bool valid = j < n;
+            bool mine = false;
+            int lid = 0;
+            float lq = 0.f;
+            uint32_t word = 0u;                                       // the random word of this candidate (MODE 1, 2)
+            if (MODE != 0 && valid) {
+                if (shared) {
+                    word = s_cand[warp * n + j];
+                } else {
+                    const int64_t li = li0 + j, qq = li / p.regen_T, idx = li - qq * p.regen_T;
+                    const uint4 w = Philox::gen(seed, (uint64_t)idx, off / 4 + (uint64_t)(qq >> 2));
+                    const int ii = (int)(qq & 3);
+                    word = ii == 0 ? w.x : (ii == 1 ? w.y : (ii == 2 ? w.z : w.w));
+                }
+            }
+            if (MODE == 2) {
+                float u = curand_uniform_from_u32(word);              // (0, 1]
+                u = u * 1.0f + 0.0f;
+                if (u == 1.0f) u = 0.0f;                              // -> [0, 1)   (ATen uniform_, DistributionTemplates.h:485-506)
+                mine = valid && u > p.cdf_lo && u <= p.cdf_hi;
+                if (mine) {
+                    int lo = 0, hi = (int)p.local_rows - 1;
+                    if (p.pop_guide) {
+                        const int64_t k = (int64_t)(u * (float)(1 << p.pop_bits)) - p.pop_k0;    // exact: power-of-two scale
+                        lo = __ldg(p.pop_guide + k); hi = __ldg(p.pop_guide + k + 1);
+                    }
+                    lid = local_lower_bound(p.pop_table, lo, hi, u);
+                    lq = logf(__ldg(p.pop_prob + lid));
+                }
+            } else {
+                int64_t gid = -1;
+                if (valid) gid = MODE == 0 ? (int64_t)__ldg(p.neg + base + j) : (int64_t)(word % (uint32_t)(p.num_items - 1) + 1u);
+                if (valid && (gid < 0 || gid >= p.num_items)) { bad = true; gid = 0; }
+                const int64_t l = gid - p.row0;
+                mine = valid && l >= 0 && l < p.local_rows;
+                lid = (int)l;
+                if (MODE == 0 && mine && p.logq_neg) lq = __ldg(p.logq_neg + base + j);
+            }
+            const uint32_t mask = __ballot_sync(kFull, mine);
+            if (mine) {
+                const int k = kept + __popc(mask & ((1u << lane) - 1u));
+                p.neg_c[base + k] = lid;
+                if (p.lq_c) p.lq_c[base + k] = lq;
+                if (p.row0 + lid != 0) atomicAdd(hist + ((uint32_t)lid >> p.bt.shift), 1u);   // padding row: scored, no gradient
+            }
+            kept += __popc(mask);
+        }
+        if (lane == 0) p.ncount[g] = kept;
+    }
+    if (bad) atomicOr(p.err, 1u);
+    if (p.use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.bt.nbins; i += blockDim.x) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(p.bt.cnt + i, c);
+        }
+    }
+}
+
 struct FinishParams {
     const float* w_local; const float* q_all;
     const float* stats_all;        // [world, G, 2]
@@ -170,6 +345,8 @@ struct FinishParams {
     uint64_t* ent; float* dq; float* loss_part; float* lse;
     int G, D, world, rank, ssm, euclid;
     float coef_scale, loss_scale;
+    uint32_t* bin_cursor; int bin_shift;       // binned grouping: the positive's entry is appended to its bin's list
+    int64_t row0;
 };
 
 // one warp per query
@@ -231,7 +408,13 @@ shard_finish_kernel(const FinishParams p) {
     if (lane == 0) {
         p.loss_part[b] = loss_b;
         p.lse[b] = lse_b;
-        if (lp >= 0) {
+        if (lp >= 0 && p.bin_cursor) {
+            if (p.row0 + lp != 0) {                                   // global row 0 is the padding row: no gradient
+                const uint32_t at = atomicAdd(p.bin_cursor + (size_t)((uint32_t)lp >> p.bin_shift) * kCursorStride, 1u);
+                const uint32_t low = (uint32_t)b | kDirect | (((uint32_t)lp & ((1u << p.bin_shift) - 1u)) << (31 - p.bin_shift));
+                p.ent[at] = (uint64_t)low | ((uint64_t)__float_as_uint(cpos) << 32);
+            }
+        } else if (lp >= 0) {
             const uint32_t sl = p.slot_pos[b];
             if (sl != kNoSlot)
                 p.ent[__ldg(p.off + lp) + sl] = (uint64_t)((uint32_t)b | kDirect) | ((uint64_t)__float_as_uint(cpos) << 32);
@@ -244,6 +427,11 @@ shard_finish_kernel(const FinishParams p) {
 using namespace rsb;
 
 extern "C" size_t rsb200_sizeof_shard_args(void) { return sizeof(rsb200_shard_args); }
+extern "C" int32_t rsb200_bin_shift(int64_t num_rows, int64_t touches, int64_t num_queries) {
+    const int s = bin_shift_for(num_rows, touches, num_queries);
+    return s >= kMinBinShift ? s : 0;
+}
+extern "C" int64_t rsb200_bin_heavy_elems(void) { return bin_scatter_grid() * ((int64_t)1 << kMaxBinShift); }
 extern "C" int64_t rsb200_scan_tmp_elems(int64_t num_rows) { return scan_tmp_elems(num_rows); }
 
 extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases, void* stream) {
@@ -263,13 +451,15 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
     if (a->regen_state) {
         RSB_REQUIRE(a->regen_B >= 1 && a->regen_B * a->world == a->G, RSB200_EINVAL, "regen_B * world must equal G");
         RSB_REQUIRE(a->regen_sm_count > 0 && a->regen_max_threads_per_sm >= 256, RSB200_EINVAL, "bad draw policy");
-        RSB_REQUIRE(a->logq_neg == nullptr, RSB200_EUNSUPPORTED, "owner-side regeneration implements the uniform sampler (log Q = 0)");
+        RSB_REQUIRE(a->logq_neg == nullptr, RSB200_EINVAL, "owner-side regeneration computes log Q itself: logq_neg must be NULL");
+        RSB_REQUIRE(a->regen_kind == 0 || a->regen_kind == 1, RSB200_EINVAL, "regen_kind must be 0 (uniform) or 1 (popularity)");
         RSB_REQUIRE(a->num_items - 1 < ((int64_t)1 << 28) && a->regen_B * a->n * 8 < ((int64_t)1 << 31), RSB200_EUNSUPPORTED,
                     "draw outside ATen's 32-bit path (see rsb200_sample_uniform)");
     }
-    RSB_REQUIRE(a->neg_c && a->slot_neg && a->ncount && a->pos_local && a->slot_pos && a->off && a->urow && a->ent &&
-                a->loss_part && a->lse && a->scan_tmp && a->totals && a->err_flag, RSB200_EINVAL, "null workspace pointer");
-    RSB_REQUIRE(a->logq_neg == nullptr || a->lq_c != nullptr, RSB200_EINVAL, "logq_neg needs the lq_c workspace");
+    RSB_REQUIRE(a->neg_c && a->ncount && a->pos_local && a->ent && a->loss_part && a->lse && a->totals && a->err_flag, RSB200_EINVAL,
+                "null workspace pointer");
+    RSB_REQUIRE((a->logq_neg == nullptr && !(a->regen_state && a->regen_kind == 1)) || a->lq_c != nullptr, RSB200_EINVAL,
+                "logq_neg / the regenerated popularity draw need the lq_c workspace");
     RSB_REQUIRE(aligned16(a->w_local) && aligned16(a->q_all) && aligned16(a->dq) && aligned16(a->item_vals) &&
                 (reinterpret_cast<uintptr_t>(a->stats_all) & 7u) == 0, RSB200_EINVAL, "row buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -280,7 +470,71 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
     const unsigned qblocks = (unsigned)cdiv(G > 0 ? G : 1, kPrepWarps);
     int32_t rc;
 
-    if (phases & RSB200_SHARD_PREP) {
+    const bool bins = a->grouping == 1;
+    BinTable bt = {}, none = {};
+    if (bins) {
+        RSB_REQUIRE(a->bin_shift >= kMinBinShift && a->bin_shift <= kMaxBinShift, RSB200_EINVAL, "bin_shift must be in [%d, %d]",
+                    kMinBinShift, kMaxBinShift);
+        RSB_REQUIRE(G <= ((int64_t)1 << (31 - a->bin_shift)), RSB200_EUNSUPPORTED, "G = %lld does not fit the query bits of a binned entry",
+                    (long long)G);
+        RSB_REQUIRE(G * a->d < ((int64_t)1 << 30), RSB200_EUNSUPPORTED, "G * d must be < 2^30");
+        RSB_REQUIRE(a->bin_cnt && a->bin_off && a->bin_cursor && a->bin_status && a->bin_ticket && a->bin_heavy, RSB200_EINVAL,
+                    "null bin workspace pointer (grouping 1)");
+        bt.cnt = a->bin_cnt; bt.off = a->bin_off; bt.cursor = a->bin_cursor; bt.status = a->bin_status; bt.ticket = a->bin_ticket;
+        bt.totals = a->totals; bt.shift = a->bin_shift; bt.num_rows = a->local_rows;
+        bt.nbins = (int)cdiv(a->local_rows, (int64_t)1 << a->bin_shift);
+    } else {
+        RSB_REQUIRE(a->slot_neg && a->slot_pos && a->off && a->urow && a->scan_tmp, RSB200_EINVAL, "null workspace pointer (grouping 0)");
+        RSB_REQUIRE(a->regen_kind == 0, RSB200_EUNSUPPORTED, "owner-side regeneration of the popularity draw needs grouping 1");
+    }
+    if (a->regen_state && a->regen_kind == 1) {
+        RSB_REQUIRE(a->pop_table_local && a->pop_prob_local, RSB200_EINVAL, "regen_kind 1 needs this owner's slices of table / pop_prob");
+        RSB_REQUIRE(a->pop_guide_local == nullptr || (a->pop_guide_bits >= 1 && a->pop_guide_bits <= 24), RSB200_EINVAL, "bad guide_bits");
+    }
+
+    if ((phases & RSB200_SHARD_PREP) && bins) {
+        RSB_CUDA(cudaMemsetAsync(bt.cnt, 0, sizeof(uint32_t) * (size_t)bt.nbins, st));
+        if (G > 0) {
+            PrepBinParams p;
+            p.w_local = a->w_local; p.q_all = a->q_all; p.pos = a->pos; p.neg = a->neg; p.logq_neg = a->logq_neg;
+            p.neg_c = a->neg_c; p.lq_c = (a->logq_neg || (a->regen_state && a->regen_kind == 1)) ? a->lq_c : nullptr;
+            p.ncount = a->ncount; p.pos_local = a->pos_local; p.sp = a->sp; p.lq_pos_out = a->lq_pos_out; p.err = a->err_flag;
+            p.bt = bt; p.num_items = a->num_items; p.row0 = a->row0; p.local_rows = a->local_rows;
+            p.G = (int)G; p.n = (int)n; p.D = (int)a->d; p.euclid = eu;
+            p.regen_state = a->regen_state; p.regen_B = (int)a->regen_B; p.regen_T = 0; p.t_per = 0; p.n_round_blocks = 0;
+            p.pop_table = a->pop_table_local; p.pop_prob = a->pop_prob_local; p.pop_guide = a->pop_guide_local;
+            p.pop_bits = a->pop_guide_bits; p.pop_k0 = a->pop_guide_k0; p.cdf_lo = a->pop_cdf_lo; p.cdf_hi = a->pop_cdf_hi;
+            RSB_REQUIRE(p.lq_pos_out == nullptr || p.pop_prob != nullptr, RSB200_EINVAL, "lq_pos_out needs pop_prob_local");
+            int mode = 0;
+            if (a->regen_state) {        // ATen policy: grid = min(sm * (max_threads / 256), ceil(numel / 256)), T = 256 grid
+                const int64_t numel = a->regen_B * n;
+                int64_t grid = (int64_t)a->regen_sm_count * (a->regen_max_threads_per_sm / 256);
+                if (cdiv(numel, 256) < grid) grid = cdiv(numel, 256);
+                p.regen_T = 256 * (grid > 0 ? grid : 1);
+                if (n > 0 && p.regen_T % n == 0 && n <= 2048) {       // four queries share every Philox block
+                    p.t_per = (int)(p.regen_T / n);
+                    p.n_round_blocks = (int)cdiv(a->regen_B, 4 * (int64_t)p.t_per);
+                }
+                mode = a->regen_kind == 1 ? 2 : 1;
+            }
+            p.use_smem = bt.nbins <= 8192;
+            const size_t smem = sizeof(uint32_t) * ((p.use_smem ? (size_t)bt.nbins : 0) + (p.t_per ? 4 * (size_t)n : 0));
+            const int64_t nitems = p.t_per ? (G / a->regen_B) * p.n_round_blocks * p.t_per : cdiv(G, 4);
+            int64_t blocks = (int64_t)sm_count() * 4;
+            if (blocks > nitems) blocks = nitems;
+#define RSB_PREP(M)                                                                                                       \
+    do {                                                                                                                  \
+        RSB_CUDA(cudaFuncSetAttribute(shard_prep_bins_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        shard_prep_bins_kernel<M><<<(unsigned)blocks, 128, smem, st>>>(p);                                                \
+    } while (0)
+            if (mode == 0) RSB_PREP(0); else if (mode == 1) RSB_PREP(1); else RSB_PREP(2);
+#undef RSB_PREP
+            RSB_LAUNCH_CHECK();
+        }
+        rc = launch_bin_scan(bt, none, st);
+        if (rc) return rc;
+    }
+    if ((phases & RSB200_SHARD_PREP) && !bins) {
         RSB_CUDA(cudaMemsetAsync(a->off, 0, sizeof(uint32_t) * (size_t)(a->local_rows + 1), st));
         if (G > 0) {
             PrepParams p;
@@ -316,7 +570,9 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         p.num_items = (int)a->local_rows; p.num_users = (int)G; p.B = (int)G; p.n = (int)n; p.D = (int)a->d;
         p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0; p.hint = 0; p.slot_abs = 1; p.cstage = nullptr;
         p.ncount = a->ncount; p.sp_in = a->sp; p.stats_part = a->stats_all + 2 * (size_t)a->rank * (size_t)G;
-        p.bin_cursor = nullptr; p.bin_shift = 0; p.bin_bbits = 0; p.bin_cursor_user = nullptr; p.bin_shift_user = 0;
+        p.bin_cursor = bins ? bt.cursor : nullptr; p.bin_shift = a->bin_shift; p.bin_bbits = 31 - a->bin_shift;
+        p.bin_cursor_user = nullptr; p.bin_shift_user = 0;
+        if (a->regen_state && a->regen_kind == 1) p.logq_neg = a->lq_c;            // log Q of the regenerated popularity draw
         rc = launch_pair_fwd_partial(p, a->loss_kind, a->score_kind, st);
         if (rc) return rc;
     }
@@ -327,6 +583,7 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
             f.pos_local = a->pos_local; f.slot_pos = a->slot_pos; f.off = a->off; f.ent = a->ent; f.dq = a->dq;
             f.loss_part = a->loss_part; f.lse = a->lse; f.G = (int)G; f.D = (int)a->d; f.world = a->world; f.rank = a->rank;
             f.ssm = ssm; f.euclid = eu; f.coef_scale = coef_scale; f.loss_scale = loss_scale;
+            f.bin_cursor = bins ? bt.cursor : nullptr; f.bin_shift = a->bin_shift; f.row0 = a->row0;
             shard_finish_kernel<<<qblocks, kPrepWarps * 32, 0, st>>>(f);
             RSB_LAUNCH_CHECK();
         }
@@ -335,6 +592,16 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
     }
     if (phases & RSB200_SHARD_SCATTER) {
         RSB_REQUIRE(a->item_rows && a->item_vals, RSB200_EINVAL, "SCATTER needs item_rows / item_vals");
+        if (bins) {
+            BinScatterParams b;
+            b.ent = a->ent; b.bin_off = bt.off; b.status = bt.status; b.ticket = bt.ticket; b.totals = bt.totals;
+            b.heavy_counts = a->bin_heavy; b.src = a->q_all; b.lse = a->lse; b.w = a->w_local; b.gscale = a->grad_scale_dev;
+            b.rows_out = a->item_rows; b.vals = a->item_vals; b.cap = a->cap;
+            b.nbins = bt.nbins; b.shift = bt.shift; b.bbits = 31 - bt.shift; b.D = (int)a->d;
+            b.ssm_scale = coef_scale; b.dense = a->sink == RSB200_SINK_DENSE; b.accumulate = a->accumulate; b.euclid = eu;
+            b.opt = -1; b.w_rw = nullptr; b.s1 = nullptr; b.s2 = nullptr; b.lr = b.b1 = b.b2 = b.eps = b.step_size = 0.f; b.tune = 0;
+            return launch_bin_scatter(b, st);
+        }
         ScatterParams s;
         s.off = a->off; s.urow = a->urow; s.totals = a->totals; s.ent = a->ent; s.src = a->q_all; s.lse = a->lse;
         s.w = a->w_local; s.gscale = a->grad_scale_dev; s.rows_out = a->item_rows; s.vals = a->item_vals; s.cap = a->cap;

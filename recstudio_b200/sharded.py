@@ -213,47 +213,79 @@ class OwnerComputeCuda:
     """One owner's workspace and the four kernel phases of ``rsb200_shard_step`` (csrc/shard.cu).
 
     Nothing here talks to other ranks: ``owner_compute_step`` (or a test that loops over the owners
-    on one device) performs the three exchanges between the phases."""
+    on one device) performs the three exchanges between the phases.
+
+    ``grouping``: 1 = binned grouping of the owned touches (csrc/bins.cu, default), 0 = counting sort over the
+    owner's rows (round 1).  ``expected_touches``: how many gradient touches this owner receives per step
+    (sizes the bins; default G * (n + 1) / world, the uniform expectation)."""
 
     def __init__(self, num_items: int, row0: int, local_rows: int, weight: torch.Tensor, world: int, rank: int,
-                 G: int, n: int, with_logq: bool = False):
+                 G: int, n: int, with_logq: bool = False, grouping: Optional[int] = None, bin_shift: Optional[int] = None,
+                 expected_touches: Optional[int] = None):
+        import os
         _lib.require_cuda()
         dev, d = weight.device, weight.shape[1]
         self.weight, self.world, self.rank, self.G, self.n, self.d = weight, world, rank, G, n, d
         self.num_items, self.row0, self.local_rows = num_items, row0, local_rows
         i32, f32, i64 = torch.int32, torch.float32, torch.int64
         E = lambda *shape, dtype=f32: torch.empty(*shape, dtype=dtype, device=dev)
+        L = _lib.lib()
+        if grouping is None:
+            grouping = int(os.environ.get("RSB200_GROUPING", "1"))
+        if bin_shift is None:
+            touches = expected_touches if expected_touches is not None else max(1, G * (n + 1) // max(world, 1))
+            bin_shift = int(L.rsb200_bin_shift(max(local_rows, 1), int(touches), max(G, 1)))
+        if not bin_shift or G * d >= (1 << 30):
+            grouping = 0
+        self.grouping, self.bin_shift = int(grouping), (int(bin_shift) if grouping else 0)
         self.cap = max(1, min(G * (n + 1), local_rows))
-        self.neg_c, self.slot_neg = E(max(G * n, 1), dtype=i32), E(max(G * n, 1), dtype=i32)
+        self.neg_c = E(max(G * n, 1), dtype=i32)
         self.lq_c = E(max(G * n, 1)) if with_logq else None
-        self.ncount, self.pos_local, self.slot_pos = E(max(G, 1), dtype=i32), E(max(G, 1), dtype=i32), E(max(G, 1), dtype=i32)
-        self.off, self.urow = E(local_rows + 1, dtype=i32), E(self.cap, dtype=i32)
+        self.ncount, self.pos_local = E(max(G, 1), dtype=i32), E(max(G, 1), dtype=i32)
         self.ent = E(max(G * (n + 1), 1), dtype=i64)
         self.loss_part, self.lse = E(max(G, 1)), E(max(G, 1))
-        self.scan_elems = int(_lib.lib().rsb200_scan_tmp_elems(local_rows))
-        self.scan_tmp = E(self.scan_elems, dtype=i64)
+        if self.grouping:
+            nb = -(-max(local_rows, 1) // (1 << self.bin_shift))
+            self.nbins = nb
+            self.bin_cnt, self.bin_off, self.bin_cursor = E(nb, dtype=i32), E(nb + 1, dtype=i32), E(nb * 8, dtype=i32)
+            self.bin_status, self.bin_ticket = E(nb, dtype=i64), torch.zeros(1, dtype=i32, device=dev)
+            self.bin_heavy = E(int(L.rsb200_bin_heavy_elems()), dtype=i32)
+            self.slot_neg = self.slot_pos = self.off = self.urow = self.scan_tmp = None
+            self.scan_elems = 0
+        else:
+            self.slot_neg, self.slot_pos = E(max(G * n, 1), dtype=i32), E(max(G, 1), dtype=i32)
+            self.off, self.urow = E(local_rows + 1, dtype=i32), E(self.cap, dtype=i32)
+            self.scan_elems = int(L.rsb200_scan_tmp_elems(local_rows))
+            self.scan_tmp = E(self.scan_elems, dtype=i64)
         self.err, self.totals = torch.zeros(1, dtype=i32, device=dev), torch.zeros(2, dtype=i32, device=dev)
-        self.sp, self.stats_all, self.dq = E(max(G, 1)), E(world, max(G, 1), 2), E(max(G, 1), d)
+        self.sp2 = torch.zeros(2, max(G, 1), dtype=f32, device=dev)         # [0] positive scores, [1] log Q(pos) (popularity regen)
+        self.sp = self.sp2[0]
+        self.stats_all, self.dq = E(world, max(G, 1), 2), E(max(G, 1), d)
         self.loss = E(1)
         self.item_rows, self.item_vals = E(self.cap, dtype=i64), E(self.cap, d)
         self._args = None
+        self._sum_lqp = False
 
     def bind(self, q_all, pos_all, neg_all, loss_kind, score_kind, logq_pos=None, logq_neg=None, grad_scale: float = 1.0,
-             regen_state: Optional[torch.Tensor] = None):
+             regen_state: Optional[torch.Tensor] = None, pop: Optional["PopularSlice"] = None):
         """``neg_all`` [G, n] int32 GLOBAL ids -- or ``None`` with ``regen_state`` [world, 2] int64 (seed, philox offset of
-        every rank's CUDA generator): the owner then recomputes every rank's ``torch.randint(1, N, (B, n))`` draw itself
-        (UniformSampler; nothing id-sized crosses NVLink)."""
+        every rank's CUDA generator): the owner then recomputes every rank's draw itself (nothing id-sized crosses NVLink):
+        ``torch.randint(1, N, (B, n))`` (UniformSampler), or with ``pop`` (this owner's ``PopularSlice``)
+        ``searchsorted(table, torch.rand(B, n))`` of the PopularSamplerModel incl. its log-probabilities."""
         G, n, d = self.G, self.n, self.d
         assert q_all.shape == (G, d) and q_all.dtype == torch.float32 and pos_all.shape == (G,) and pos_all.dtype == torch.int64
         if regen_state is None:
-            assert neg_all.shape == (G, n) and neg_all.dtype == torch.int32
+            assert neg_all.shape == (G, n) and neg_all.dtype == torch.int32 and pop is None
         else:
             assert neg_all is None and regen_state.shape == (self.world, 2) and regen_state.dtype == torch.int64 \
                 and regen_state.is_cuda and logq_neg is None and G % self.world == 0
-        if logq_neg is not None and self.lq_c is None:
+            if pop is not None and not self.grouping:
+                raise _lib.Rsb200Error("owner-side regeneration of the popularity draw needs the binned grouping")
+        if (logq_neg is not None or pop is not None) and self.lq_c is None:
             raise _lib.Rsb200Error("OwnerComputeCuda was built without the logq workspace (with_logq=True)")
         self._keep = [t.contiguous() if t is not None else None for t in (q_all, pos_all, neg_all, logq_pos, logq_neg, regen_state)]
         q_all, pos_all, neg_all, logq_pos, logq_neg, regen_state = self._keep
+        self._pop = pop
         a = _lib.ShardArgs()
         P = _lib.ptr
         a.w_local, a.q_all, a.pos, a.neg = P(self.weight), P(q_all), P(pos_all), (P(neg_all) if neg_all is not None else None)
@@ -261,6 +293,16 @@ class OwnerComputeCuda:
             dev = self.weight.device
             sm, mt, _, _ = _lib.device_info(dev.index if dev.index is not None else torch.cuda.current_device())
             a.regen_state, a.regen_B, a.regen_sm_count, a.regen_max_threads_per_sm = P(regen_state), G // self.world, sm, mt
+        # SampledSoftmax with a regenerated popularity draw: log Q(pos) comes from the positive's owner (summed with sp)
+        self._sum_lqp = pop is not None and int(loss_kind) == _lib.LOSS_SSM
+        if pop is not None:
+            a.regen_kind = 1
+            a.pop_table_local, a.pop_prob_local = P(pop.table), P(pop.prob)
+            a.pop_guide_local, a.pop_guide_bits, a.pop_guide_k0 = P(pop.guide), pop.guide_bits, pop.k0
+            a.pop_cdf_lo, a.pop_cdf_hi = pop.cdf_lo, pop.cdf_hi
+            if self._sum_lqp:
+                a.lq_pos_out = P(self.sp2[1])
+                logq_pos = self.sp2[1]
         a.logq_pos = P(logq_pos) if logq_pos is not None else None
         a.logq_neg = P(logq_neg) if logq_neg is not None else None
         a.grad_scale_dev = None
@@ -275,15 +317,19 @@ class OwnerComputeCuda:
         a.cap, a.scan_tmp_elems, a.grad_scale = self.cap, self.scan_elems, float(grad_scale)
         a.world, a.rank, a.loss_kind, a.score_kind = self.world, self.rank, int(loss_kind), int(score_kind)
         a.sink, a.accumulate = _lib.SINK_COMPACT, 0
+        a.grouping, a.bin_shift = self.grouping, self.bin_shift
+        if self.grouping:
+            a.bin_cnt, a.bin_off, a.bin_cursor = P(self.bin_cnt), P(self.bin_off), P(self.bin_cursor)
+            a.bin_status, a.bin_ticket, a.bin_heavy = P(self.bin_status), P(self.bin_ticket), P(self.bin_heavy)
         self._args = a
 
     def _run(self, phases: int, what: str):
         with torch.cuda.device(self.weight.device):
             _lib.check(_lib.lib().rsb200_shard_step(C.byref(self._args), phases, _lib.stream_ptr()), what)
 
-    def prep(self) -> torch.Tensor:            # -> sp[G]   (all-reduce SUM next)
+    def prep(self) -> torch.Tensor:            # -> sp[G] (or [2, G] with log Q(pos))   (all-reduce SUM next)
         self._run(_lib.SHARD_PREP, "shard_step(PREP)")
-        return self.sp[:self.G]
+        return self.sp2[:, :self.G] if self._sum_lqp else self.sp[:self.G]
 
     def fwd(self) -> torch.Tensor:             # -> this owner's stats slice [G, 2]   (all-gather next)
         self._run(_lib.SHARD_FWD, "shard_step(FWD)")
@@ -302,6 +348,53 @@ class OwnerComputeCuda:
             raise _lib.Rsb200Error("shard_step: item id outside [0, num_items)")
 
 
+class PopularSlice:
+    """One owner's share of a ``PopularSamplerModel`` (recstudio/ann/sampler.py:224-258) for the owner-side
+    regeneration of the draw: the slices ``table[row0 : row0 + L]`` / ``pop_prob[row0 : row0 + L]`` of the sampler's
+    buffers (built ONCE, on the CPU, by the very torch ops of the reference constructor, so every rank holds bit-identical
+    values), the two CDF values that bound the owner's share of the unit interval, and a guide table over that share."""
+
+    def __init__(self, table_cpu: torch.Tensor, prob_cpu: torch.Tensor, row0: int, local_rows: int, device):
+        N = table_cpu.numel()
+        assert prob_cpu.numel() == N and 0 <= row0 and row0 + local_rows <= N and local_rows >= 1
+        self.row0, self.local_rows = row0, local_rows
+        self.cdf_lo = float(table_cpu[row0 - 1]) if row0 > 0 else float("-inf")
+        self.cdf_hi = float(table_cpu[row0 + local_rows - 1]) if row0 + local_rows < N else float("inf")
+        self.table = table_cpu[row0:row0 + local_rows].to(device).contiguous()
+        self.prob = prob_cpu[row0:row0 + local_rows].to(device).contiguous()
+        bits = 1
+        while (1 << bits) * 8 < N and bits < 24:           # ~8 table entries per guide bucket, as the single-GPU sampler
+            bits += 1
+        self.guide_bits = bits
+        K = 1 << bits
+        lo = max(self.cdf_lo, 0.0)
+        hi = min(self.cdf_hi, 1.0)
+        self.k0 = int(lo * K)
+        k1 = min(int(hi * K), K - 1)
+        length = k1 - self.k0 + 2
+        self.guide = torch.empty(length, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().rsb200_popular_build_guide_range(_lib.ptr(self.table), local_rows, bits, self.k0, length,
+                                                                   _lib.ptr(self.guide), _lib.stream_ptr()), "build_guide_range")
+
+    @staticmethod
+    def tables(pop_count, mode: int = 0):
+        """(table, pop_prob) of PopularSamplerModel(pop_count, mode) on the CPU: sampler.py:225-241 op for op."""
+        with torch.no_grad():
+            pc = torch.as_tensor(pop_count).to(torch.float)
+            if mode == 0:
+                pc = torch.log(pc + 1)
+            elif mode == 1:
+                pc = torch.log(pc + 1) + 1e-6
+            elif mode == 2:
+                pc = pc ** 0.75
+            pc[0] = 1
+            prob = pc / pc.sum()
+            table = torch.cumsum(prob, dim=0)
+            prob[-1] = 1.0
+        return table, prob
+
+
 def uniform_regen_state(device, B: int, n: int, group=None, generator=None) -> torch.Tensor:
     """[world, 2] int64 (seed, philox offset) of every rank's CUDA generator, all-gathered (16 bytes per rank), and this
     rank's generator advanced by exactly what ``torch.randint(1, N, (B, n), device=cuda)`` would have consumed: the
@@ -317,15 +410,17 @@ def uniform_regen_state(device, B: int, n: int, group=None, generator=None) -> t
 
 def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: Optional[torch.Tensor], loss_kind: int, score_kind: int,
                        logq_pos: Optional[torch.Tensor] = None, logq_neg: Optional[torch.Tensor] = None, group=None,
-                       gathered=None, regen_state: Optional[torch.Tensor] = None):
+                       gathered=None, regen_state: Optional[torch.Tensor] = None, pop: Optional[PopularSlice] = None):
     """One data-parallel step over the row-sharded item table WITHOUT moving rows.
 
     Every rank passes its own B queries (vectors ``q`` [B, d], GLOBAL ids ``pos`` [B], ``neg`` [B, n] int32);
-    ``engine`` holds this rank's row block (``OwnerComputeCuda`` on GPUs).  Returns
+    ``engine`` holds this rank's row block (``OwnerComputeCuda`` on GPUs).  With ``regen_state``
+    (``uniform_regen_state(...)``) the negatives are not passed at all: every owner regenerates every rank's draw --
+    UniformSampler, or PopularSamplerModel when ``pop`` (this owner's ``PopularSlice``) is given.  Returns
     ``(loss, (rows, vals, totals), dq_all)``: the global mean loss (identical on every rank), the gradient rows
     of the rows THIS rank owns (LOCAL ids, ``R = totals[1]`` valid rows) and ``d loss / d query`` of all
     ``G = world x B`` queries (rank r's queries are ``dq_all[r*B:(r+1)*B]``).  No host synchronisation."""
-    if gathered is None and regen_state is not None:          # uniform negatives regenerated by the owners: no id exchange
+    if gathered is None and regen_state is not None:          # negatives regenerated by the owners: no id exchange
         q_all, pos_all, neg_all, lqp, lqn = _all_gather_cat(q, group), _all_gather_cat(pos, group), None, None, None
     elif gathered is None:
         q_all, pos_all, neg_all = _all_gather_cat(q, group), _all_gather_cat(pos, group), _all_gather_cat(neg, group)
@@ -334,7 +429,8 @@ def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: Optional
     else:
         q_all, pos_all, neg_all, lqp, lqn = gathered
     if regen_state is not None:
-        engine.bind(q_all, pos_all, None, loss_kind, score_kind, lqp, lqn, regen_state=regen_state)
+        kw = {"pop": pop} if pop is not None else {}
+        engine.bind(q_all, pos_all, None, loss_kind, score_kind, lqp, lqn, regen_state=regen_state, **kw)
     else:
         engine.bind(q_all, pos_all, neg_all, loss_kind, score_kind, lqp, lqn)
     sp = engine.prep()

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def run_owners(w_item, q_all, pos, neg, world, loss_kind, score_kind, lqp=None, lqn=None):
+def run_owners(w_item, q_all, pos, neg, world, loss_kind, score_kind, lqp=None, lqn=None, grouping=None):
     """-> (loss, dense d_item [N, d], dq [G, d]) assembled from `world` owners run back to back."""
     from recstudio_b200 import sharded
     N, d = w_item.shape
@@ -25,7 +25,8 @@ def run_owners(w_item, q_all, pos, neg, world, loss_kind, score_kind, lqp=None, 
         row0 = r * per
         local = max(0, min(per, N - row0))
         e = sharded.OwnerComputeCuda(N, row0, local, w_item[row0:row0 + local].contiguous(), world, r, G, n,
-                                     with_logq=lqn is not None)
+                                     with_logq=lqn is not None, grouping=grouping)
+        assert grouping is None or e.grouping == grouping
         e.bind(q_all, pos, neg, loss_kind, score_kind, lqp, lqn)
         engines.append(e)
     sp = torch.stack([e.prep().clone() for e in engines]).sum(0)          # all-reduce SUM
@@ -62,9 +63,10 @@ def _case(N, U, d, G, n, seed, pad=True):
     return w_item, w_user, user, pos, neg, lqp, lqn
 
 
+@pytest.mark.parametrize("grouping", [0, 1])      # 0: counting sort over the owner's rows, 1: bins (default)
 @pytest.mark.parametrize("world", [1, 2, 3, 7])
 @pytest.mark.parametrize("loss_kind,score_kind", [(R.BPR, R.IP), (R.BPR, R.EUCLID), (R.SSM, R.IP), (R.SSM, R.EUCLID)])
-def test_owners_sum_to_the_reference_step(world, loss_kind, score_kind):
+def test_owners_sum_to_the_reference_step(world, loss_kind, score_kind, grouping):
     N, U, d, G, n = 211, 40, 24, 37, 45          # n not a multiple of 32, d < 128, ids include the padding row
     w_item, w_user, user, pos, neg, lqp, lqn = _case(N, U, d, G, n, seed=world)
     ssm = loss_kind == R.SSM
@@ -72,7 +74,7 @@ def test_owners_sum_to_the_reference_step(world, loss_kind, score_kind):
     ref = R.training_step_aten(w_item, w_user, user, pos, neg, loss=loss_kind, scorer=score_kind, **kw)
     q_all = w_user[user].to(DEV)
     loss, d_item, dq = run_owners(w_item.to(DEV), q_all, pos.to(DEV), neg.to(DEV).int(), world, loss_kind, score_kind,
-                                  lqp.to(DEV) if ssm else None, lqn.to(DEV) if ssm else None)
+                                  lqp.to(DEV) if ssm else None, lqn.to(DEV) if ssm else None, grouping=grouping)
     assert abs(loss - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item())
     gi = ref["d_item"].numpy()
     assert np.abs(d_item.cpu().numpy() - gi).max() <= 1e-5 * np.abs(gi).max()
@@ -130,14 +132,16 @@ def test_matches_the_single_table_fused_step(loss_kind):
     assert (dq - ref_dq).abs().max().item() <= 1e-5 * ref_dq.abs().max().item()
 
 
+@pytest.mark.parametrize("shape", [(24, 300), (48, 256), (1300, 256)])   # T % n != 0 (per-id Philox) | T = t n: shared Philox blocks, 1 and 2 rounds
 @pytest.mark.parametrize("world", [1, 2, 4])
 @pytest.mark.parametrize("loss_kind", [R.BPR, R.SSM])
-def test_owner_side_regeneration_of_the_uniform_draw(world, loss_kind):
+def test_owner_side_regeneration_of_the_uniform_draw(world, loss_kind, shape):
     """Instead of receiving every rank's negative ids, the owners recompute them from the ranks' generator states
     (rsb200_shard_args.regen_state): rank r's ids are exactly torch.randint(1, N, (B, n), device=cuda) for its
     (seed, offset).  The step must be bit-identical to the one fed with the explicitly drawn, gathered ids."""
     from recstudio_b200 import sampling, sharded
-    N, U, d, B, n = 40_001, 301, 64, 24, 300           # numel = B * n above one ATen grid row for some lanes of T
+    N, U, d = 40_001, 301, 64
+    B, n = shape
     G = world * B
     g = torch.Generator().manual_seed(world)
     w_item = (torch.randn(N, d, generator=g) * 0.3).to(DEV); w_item[0] = 0
@@ -195,3 +199,87 @@ def test_owner_side_regeneration_of_the_uniform_draw(world, loss_kind):
         dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
     st = sharded.uniform_regen_state(DEV, B, n)
     assert st.shape == (1, 2) and torch.equal(torch.rand(2, device=DEV), ref_after)
+
+
+def _popular_case(N, world, B, n, mode, seed):
+    """every rank's PopularSamplerModel draw on its own generator state, with the single-GPU sampler (bit-equal to
+    torch.rand + searchsorted, tests/test_gpu_sampler.py) -> (tables, states, gathered ids, gathered log Q)"""
+    from recstudio_b200 import sampling, sharded
+    rng = np.random.RandomState(seed)
+    counts = np.floor(rng.zipf(1.3, size=N)).clip(max=1e6); counts[0] = 0
+    table, prob = sharded.PopularSlice.tables(counts, mode)
+    tab_d, prob_d = table.to(DEV), prob.to(DEV)
+    guide, bits = sampling.build_guide(tab_d)
+    states, negs, lqs = [], [], []
+    for r in range(world):
+        torch.manual_seed(500 + r)
+        torch.rand(13 * (r + 1), device=DEV)
+        gen = torch.cuda.default_generators[0]
+        states.append([gen.initial_seed(), gen.get_offset()])
+        _, neg32, lq = sampling.popular_draw(tab_d, prob_d, B, n, guide, bits, want_i64=False, want_i32=True)
+        negs.append(neg32); lqs.append(lq)
+    return table, prob, torch.tensor(states, dtype=torch.int64, device=DEV), torch.cat(negs, 0), torch.cat(lqs, 0)
+
+
+@pytest.mark.parametrize("shape", [(24, 300), (48, 256), (1300, 256)])
+@pytest.mark.parametrize("world", [1, 2, 5])
+@pytest.mark.parametrize("loss_kind,mode", [(R.BPR, 0), (R.SSM, 2)])
+def test_owner_side_regeneration_of_the_popularity_draw(world, loss_kind, mode, shape):
+    """regen_kind 1: every owner regenerates every rank's PopularSamplerModel draw from the generator states and ITS slice of
+    the cumulative table (PopularSlice): same owned negatives, same log Q, bit-identical loss / dq as the step fed with
+    the gathered ids and log-probabilities; SampledSoftmax takes log Q(pos) from the positive's owner."""
+    from recstudio_b200 import sampling, sharded
+    N, d = 30_011, 64
+    B, n = shape
+    G = world * B
+    table, prob, state, neg_all, lq_all = _popular_case(N, world, B, n, mode, seed=world + n)
+    assert int(neg_all.min()) >= 0 and int(neg_all.max()) < N
+    g = torch.Generator().manual_seed(7)
+    w_item = (torch.randn(N, d, generator=g) * 0.3).to(DEV); w_item[0] = 0
+    q_all = (torch.randn(G, d, generator=g) * 0.3).to(DEV)
+    pos = torch.randint(1, N, (G,), generator=g).to(DEV)
+    lqp = sampling.popular_logq(prob.to(DEV), pos)
+    ssm = loss_kind == R.SSM
+    per = sharded.rows_per_rank(N, world)
+    outs = []
+    for regen in (False, True):
+        engines = []
+        for r in range(world):
+            row0 = r * per; local = max(0, min(per, N - row0))
+            e = sharded.OwnerComputeCuda(N, row0, local, w_item[row0:row0 + local].contiguous(), world, r, G, n, with_logq=True)
+            if regen:
+                e.bind(q_all, pos, None, loss_kind, R.IP, regen_state=state, pop=sharded.PopularSlice(table, prob, row0, local, DEV))
+            else:
+                e.bind(q_all, pos, neg_all, loss_kind, R.IP, lqp if ssm else None, lq_all if ssm else None)
+            engines.append(e)
+        sp = torch.stack([e.prep().clone() for e in engines]).sum(0)
+        for e in engines:
+            if regen and ssm:
+                e.sp2[:, :G] = sp
+            else:
+                e.sp[:G] = sp
+        if regen and ssm:                                    # log Q(pos) assembled from the owners == the global lookup
+            assert torch.equal(sp[1], lqp)
+        stats = torch.stack([e.fwd().clone() for e in engines])
+        for e in engines:
+            e.stats_all[:, :G] = stats
+        res = []
+        for e in engines:
+            loss, dq = e.finish()
+            rows, vals, totals = e.scatter()
+            R_ = int(totals[1].item())
+            res.append((loss.clone(), dq.clone(), rows[:R_].clone(), vals[:R_].clone(), e.ncount[:G].clone(), int(totals[0].item()),
+                        e.neg_c.clone(), e.lq_c.clone()))
+            e.check()
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert torch.equal(a[4], b[4]) and a[5] == b[5]
+        cnt = a[4].cpu().numpy()
+        for q in (0, G // 2, G - 1):                         # compacted local ids / log Q of a few queries, element by element
+            sl = slice(q * n, q * n + int(cnt[q]))
+            assert torch.equal(a[6][sl], b[6][sl])
+            if ssm:
+                assert torch.equal(a[7][sl], b[7][sl])
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])       # gradient rows: bit-identical (deterministic bins)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert sum(r[5] for r in outs[1]) == int((neg_all > 0).sum()) + G   # every non-padding touch has exactly one owner
