@@ -214,7 +214,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
         if (a->variant == 32) p.hint = 8;    // timing diagnostic: skip the offset lookups / entry writes (gradients invalid)
         p.ncount = nullptr; p.sp_in = nullptr; p.stats_part = nullptr;
         p.bin_cursor = bins ? ti.cursor : nullptr; p.bin_shift = a->bin_shift; p.bin_bbits = 31 - a->bin_shift;
-        p.bin_cursor_user = bins ? tu.cursor : nullptr; p.bin_shift_user = a->bin_shift_user;
+        p.bin_cursor_user = bins ? tu.cursor : nullptr; p.bin_shift_user = a->bin_shift_user; p.pad_row = 0;
         p.coef_scale = (float)((double)a->grad_scale / (denom > 0 ? denom : 1.0));
         rc = launch_pair_fwd(p, a->loss_kind, a->score_kind, a->variant, st);
         if (rc) return rc;

@@ -24,6 +24,7 @@ struct FwdParams {
     // binned grouping (bins.cu): entries are appended to the list of their row's bin with a cursor atomic
     uint32_t* bin_cursor;    // [nbins * kCursorStride] or null (= row-sorted positions from slot_neg / off_item)
     int bin_shift, bin_bbits;
+    int pad_row;             // (binned grouping) id of the padding row in `neg`: 0, or -1 for an owner whose block does not hold global row 0
     uint32_t* bin_cursor_user; int bin_shift_user;    // the same for the user table's entries (null in the owner-compute step)
     const int32_t* ncount;   // [B] length of each query's compacted negative list (stride n)
     const float* sp_in;      // [B] positive score (computed by the positive's owner)

@@ -105,12 +105,12 @@ __device__ __forceinline__ BatchMeta load_meta(const FwdParams& p, size_t rowbas
     if (HINT) {        // ids / slots are read exactly once: same eviction priority as the rows
         m.id = valid ? (int)ldg32_hint(reinterpret_cast<const uint32_t*>(p.neg) + rowbase + j, pol) : 0;
         if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
-        if (p.bin_cursor) m.slot = (valid && m.id != 0) ? 0u : kNoSlot;
+        if (p.bin_cursor) m.slot = (valid && m.id != p.pad_row) ? 0u : kNoSlot;
         else m.slot = valid ? ldg32_hint(p.slot_neg + rowbase + j, pol) : kNoSlot;
     } else {
         m.id = valid ? __ldg(p.neg + rowbase + j) : 0;
         if ((unsigned)m.id >= (unsigned)p.num_items) m.id = 0;
-        if (p.bin_cursor) m.slot = (valid && m.id != 0) ? 0u : kNoSlot;      // binned grouping: no per-touch slot array
+        if (p.bin_cursor) m.slot = (valid && m.id != p.pad_row) ? 0u : kNoSlot;      // binned grouping: no per-touch slot array
         else m.slot = valid ? __ldg(p.slot_neg + rowbase + j) : kNoSlot;
     }
     m.lq = 0.f;

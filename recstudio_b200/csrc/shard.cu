@@ -571,7 +571,7 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         p.coef_scale = coef_scale; p.loss_scale = loss_scale; p.prefetch = 0; p.hint = 0; p.slot_abs = 1; p.cstage = nullptr;
         p.ncount = a->ncount; p.sp_in = a->sp; p.stats_part = a->stats_all + 2 * (size_t)a->rank * (size_t)G;
         p.bin_cursor = bins ? bt.cursor : nullptr; p.bin_shift = a->bin_shift; p.bin_bbits = 31 - a->bin_shift;
-        p.bin_cursor_user = nullptr; p.bin_shift_user = 0;
+        p.bin_cursor_user = nullptr; p.bin_shift_user = 0; p.pad_row = a->row0 == 0 ? 0 : -1;
         if (a->regen_state && a->regen_kind == 1) p.logq_neg = a->lq_c;            // log Q of the regenerated popularity draw
         rc = launch_pair_fwd_partial(p, a->loss_kind, a->score_kind, st);
         if (rc) return rc;
