@@ -408,6 +408,41 @@ def uniform_regen_state(device, B: int, n: int, group=None, generator=None) -> t
     return _all_gather_cat(mine.to(device, non_blocking=True), group)
 
 
+class DrawStates:
+    """The generator states of all ranks, resident on the device: what ``uniform_regen_state`` returns, without the
+    per-step host-to-device copy and all-gather.  ``resync()`` (collective) gathers every rank's current (seed, offset);
+    ``next()`` hands out the [world, 2] state tensor for this step's draw of B x n numbers per rank and advances the
+    device copy and this rank's torch generator by what the draw consumes -- valid as long as nothing else consumes the
+    generators between steps (``next()`` checks the local one and raises, asking for a ``resync()`` on all ranks)."""
+
+    def __init__(self, device, B: int, n: int, group=None, generator=None):
+        from . import sampling
+        self.device, self.group = torch.device(device), group
+        self.gen = sampling._generator(self.device, generator)
+        self.inc = sampling.counter_offset(B * n, self.device)
+        self.B, self.n = B, n
+        self._inc_dev = torch.tensor([0, self.inc], dtype=torch.int64, device=self.device)
+        self.resync()
+
+    def resync(self):
+        seed, off = self.gen.initial_seed(), self.gen.get_offset()
+        mine = torch.tensor([[seed - (1 << 64) if seed >= (1 << 63) else seed, off]], dtype=torch.int64).to(self.device)
+        self.state = _all_gather_cat(mine, self.group)
+        self._expect = (seed, off)
+        self._pending = False
+
+    def next(self) -> torch.Tensor:
+        if (self.gen.initial_seed(), self.gen.get_offset()) != self._expect:
+            raise _lib.Rsb200Error("DrawStates: the CUDA generator was used outside the sharded step; call resync() on every rank")
+        if self._pending:                      # the previous step's PREP is already enqueued on this stream: advance after it
+            self.state += self._inc_dev
+        self._pending = True
+        seed, off = self._expect
+        self.gen.set_offset(off + self.inc)
+        self._expect = (seed, off + self.inc)
+        return self.state
+
+
 def owner_compute_step(engine, q: torch.Tensor, pos: torch.Tensor, neg: Optional[torch.Tensor], loss_kind: int, score_kind: int,
                        logq_pos: Optional[torch.Tensor] = None, logq_neg: Optional[torch.Tensor] = None, group=None,
                        gathered=None, regen_state: Optional[torch.Tensor] = None, pop: Optional[PopularSlice] = None):

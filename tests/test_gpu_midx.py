@@ -132,7 +132,9 @@ def test_sampler_update_and_draw_match_reference_golden(tag, monkeypatch):
         if tag == "cp_ip" and key == "pos1":
             continue        # the reference broadcasts [B] + [B,1] -> [B,B] here (sampler.py:486-490) and then fails in view_as
         got = smp.compute_item_p(query, torch.from_numpy(g[f"mx_{key}"]).to(DEV))
-        np.testing.assert_allclose(got.cpu().numpy(), g[f"{tag}_{key}_p"], rtol=1e-5, atol=1e-6)
+        # atol 1e-5: the centres come out of k-means with shared-memory fp32 atomics (summation order varies run to run by
+        # ~1e-6 relative) and these log-probabilities are differences of O(10) scores
+        np.testing.assert_allclose(got.cpu().numpy(), g[f"{tag}_{key}_p"], rtol=1e-5, atol=1e-5)
     if tag == "mu_ip":      # the next epoch's update warm-starts from the stored centres
         smp.update(torch.from_numpy(g["mu_ip2_emb"]).to(DEV), max_iter=3)
         np.testing.assert_array_equal(smp.indices.cpu().numpy(), g["mu_ip2_indices"])

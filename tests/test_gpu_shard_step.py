@@ -283,3 +283,32 @@ def test_owner_side_regeneration_of_the_popularity_draw(world, loss_kind, mode, 
         assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])       # gradient rows: bit-identical (deterministic bins)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert sum(r[5] for r in outs[1]) == int((neg_all > 0).sum()) + G   # every non-padding touch has exactly one owner
+
+
+def test_draw_states_track_the_generator_on_the_device():
+    """sharded.DrawStates: the [world, 2] (seed, offset) tensor advanced on the device step by step equals what
+    uniform_regen_state would gather each step, and the local torch generator ends where the replaced draws leave it."""
+    import torch.distributed as dist
+    from recstudio_b200 import _lib, sharded
+    if not dist.is_initialized():
+        import os
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29571")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(DEV))
+    B, n, N = 48, 256, 5001
+    torch.manual_seed(77)
+    want = []
+    for _ in range(3):
+        gen = torch.cuda.default_generators[0]
+        want.append((gen.initial_seed(), gen.get_offset()))
+        torch.randint(1, N, (B, n), device=DEV)
+    after = torch.rand(3, device=DEV)
+    torch.manual_seed(77)
+    ds = sharded.DrawStates(DEV, B, n)
+    got = [ds.next().clone().cpu().tolist()[0] for _ in range(3)]
+    assert [tuple(g) for g in got] == want
+    assert torch.equal(torch.rand(3, device=DEV), after)
+    with pytest.raises(_lib.Rsb200Error):                # the rand above consumed the generator behind its back
+        ds.next()
+    ds.resync()
+    assert tuple(ds.next().cpu().tolist()[0]) == (torch.cuda.default_generators[0].initial_seed(),
+                                                  torch.cuda.default_generators[0].get_offset() - ds.inc)

@@ -40,7 +40,7 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         ev[0].record()
         q = sh.CudaOps.gather_rows(sb.wu, u)
-        state = sh.uniform_regen_state(dev, bench.BATCH, bench.NEG)
+        state = sb.states.next()
         ev[1].record()
         q_all, pos_all = sh._all_gather_cat(q), sh._all_gather_cat(p)
         ev[2].record()
