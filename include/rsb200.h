@@ -411,6 +411,11 @@ int32_t rsb200_segment_search(const int64_t* k01, const float* u, int64_t num_dr
 #define RSB200_SHARD_FWD      2
 #define RSB200_SHARD_FINISH   4
 #define RSB200_SHARD_SCATTER  8
+/* PREP may be issued in two halves (grouping 1): PREP_NEG filters / compacts the negatives -- it needs the draw (neg or
+ * regen_state) but NOT q_all / pos, so it can run while the queries are still being all-gathered -- and PREP_POS scores the
+ * owned positives and closes the bin histogram.  RSB200_SHARD_PREP = both. */
+#define RSB200_SHARD_PREP_NEG 16
+#define RSB200_SHARD_PREP_POS 32
 
 typedef struct rsb200_shard_args {
     /* owner's table block and the global batch (device pointers) */

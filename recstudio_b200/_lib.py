@@ -21,7 +21,7 @@ LOSS_BPR, LOSS_SSM, LOSS_FULL = 0, 1, 2
 SCORE_IP, SCORE_EUCLID = 0, 1
 PHASE_COUNT, PHASE_SCAN, PHASE_FWD, PHASE_SCATTER, PHASE_ALL = 1, 2, 4, 8, 15
 SINK_COMPACT, SINK_DENSE, SINK_APPLY = 0, 1, 2
-SHARD_PREP, SHARD_FWD, SHARD_FINISH, SHARD_SCATTER = 1, 2, 4, 8
+SHARD_PREP, SHARD_FWD, SHARD_FINISH, SHARD_SCATTER, SHARD_PREP_NEG, SHARD_PREP_POS = 1, 2, 4, 8, 16, 32
 
 
 class Rsb200Error(RuntimeError):

@@ -183,6 +183,7 @@ struct PrepBinParams {
     BinTable bt;
     int64_t num_items, row0, local_rows;
     int G, n, D, euclid, use_smem;
+    int do_pos, do_neg;            // PREP may be split: negatives (independent of the batch's queries) | positives
     // regeneration
     const uint64_t* regen_state; int regen_B; int64_t regen_T; int t_per; int n_round_blocks;
     const float* pop_table; const float* pop_prob; const int32_t* pop_guide; int pop_bits; int64_t pop_k0;
@@ -203,12 +204,22 @@ __device__ __forceinline__ int local_lower_bound(const float* __restrict__ table
     return id;
 }
 
+constexpr int kPrepSeg = 1024;                       // candidates of one query staged per pass
+constexpr int kPrepSegWords = (kPrepSeg / 32) * 33;  // lane-major staging with a 33-word pitch (conflict-free both ways)
+
+// One CTA = four warps = four queries.  Per segment of <= 1024 candidates of each query:
+//   A  stage the candidates in shared memory (ids from global memory, or random words from Philox -- in the shared-block
+//      formulation every thread computes whole Philox blocks and feeds all four queries);
+//   B  every LANE walks its own contiguous chunk of the segment, keeps what this owner holds (compacted in place,
+//      lane-private column), then one warp scan turns the per-lane counts into offsets: the compaction stays stable
+//      (query order) without a ballot per 32 candidates, and all 32 lanes test candidates all the time;
+//   C  every lane resolves and writes its kept candidates (the popularity search runs here, on owned draws only).
 template <int MODE>
 __global__ void __launch_bounds__(128, 4)
 shard_prep_bins_kernel(const PrepBinParams p) {
     extern __shared__ uint32_t s_dyn[];
     uint32_t* s_hist = s_dyn;                                         // [nbins] (use_smem)
-    uint32_t* s_cand = s_dyn + (p.use_smem ? p.bt.nbins : 0);         // [4][n] candidates of the CTA's four queries (MODE 1, 2)
+    uint32_t* s_cand = s_dyn + (p.use_smem ? p.bt.nbins : 0);         // [4][kPrepSegWords]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.D, n = p.n;
     if (p.use_smem) {
@@ -216,6 +227,7 @@ shard_prep_bins_kernel(const PrepBinParams p) {
         __syncthreads();
     }
     uint32_t* hist = p.use_smem ? s_hist : p.bt.cnt;
+    uint32_t* my = s_cand + warp * kPrepSegWords;
     bool bad = false;
     // shared Philox blocks need T = t_per * n; any other shape regenerates per id (t_per = 0: every block computed 4x)
     const bool shared = MODE != 0 && p.t_per > 0;
@@ -224,6 +236,7 @@ shard_prep_bins_kernel(const PrepBinParams p) {
         int g;                                                        // global query of this warp, -1 = none
         uint64_t seed = 0, off = 0;
         int64_t li0 = 0;                                              // per-id regeneration: first element of the query
+        int R = 0, x = 0;
         if (!shared) {
             g = (int)(item * 4 + warp);
             if (g >= p.G) g = -1;
@@ -235,70 +248,105 @@ shard_prep_bins_kernel(const PrepBinParams p) {
         } else {
             const int per_rank = p.n_round_blocks * p.t_per;
             const int r = (int)(item / per_rank), rem = (int)(item % per_rank);
-            const int R = rem / p.t_per, x = rem % p.t_per;
+            R = rem / p.t_per; x = rem % p.t_per;
             const int lb = 4 * p.t_per * R + x + p.t_per * warp;      // this warp's query inside rank r's batch
             g = lb < p.regen_B ? r * p.regen_B + lb : -1;
-            // ---- Philox: thread handles positions j = tid, tid + 128, ...; idx = x * n + j, round R
             seed = __ldg(p.regen_state + 2 * r); off = __ldg(p.regen_state + 2 * r + 1);
-            __syncthreads();                                          // previous item's candidates are consumed
-            for (int j = threadIdx.x; j < n; j += blockDim.x) {
-                const uint4 w = Philox::gen(seed, (uint64_t)((int64_t)x * n + j), off / 4 + (uint64_t)R);
-                const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) s_cand[ii * n + j] = words[ii];
-            }
-            __syncthreads();
         }
-        if (g < 0) continue;                                          // (whole warp) -- no barrier below depends on it
 
         // ---- positive: owned? -> score, local row, histogram, log Q
-        int64_t gp = __ldg(p.pos + g);
-        if (gp < 0 || gp >= p.num_items) { bad = true; gp = 0; }
-        const int64_t lp = gp - p.row0;
-        const bool own = lp >= 0 && lp < p.local_rows;
-        float sp = 0.f;
-        if (own) {
-            for (int c = lane * 4; c < D; c += 128) {
-                const float4 qv = ldg128(p.q_all + (size_t)g * D + c);
-                const float4 vv = ldg128(p.w_local + (size_t)lp * D + c);
-                sp += p.euclid ? sqdist4(qv, vv) : dot4(qv, vv);
+        if (g >= 0 && p.do_pos) {
+            int64_t gp = __ldg(p.pos + g);
+            if (gp < 0 || gp >= p.num_items) { bad = true; gp = 0; }
+            const int64_t lp = gp - p.row0;
+            const bool own = lp >= 0 && lp < p.local_rows;
+            float sp = 0.f;
+            if (own) {
+                for (int c = lane * 4; c < D; c += 128) {
+                    const float4 qv = ldg128(p.q_all + (size_t)g * D + c);
+                    const float4 vv = ldg128(p.w_local + (size_t)lp * D + c);
+                    sp += p.euclid ? sqdist4(qv, vv) : dot4(qv, vv);
+                }
+                sp = warp_sum_s(sp);
+                if (p.euclid) sp = -sp;
             }
-            sp = warp_sum_s(sp);
-            if (p.euclid) sp = -sp;
-        }
-        if (lane == 0) {
-            p.sp[g] = own ? sp : 0.f;
-            p.pos_local[g] = own ? (int32_t)lp : -1;
-            if (own && gp != 0) atomicAdd(hist + (lp >> p.bt.shift), 1u);
-            if (p.lq_pos_out) p.lq_pos_out[g] = own ? logf(__ldg(p.pop_prob + lp)) : 0.f;
+            if (lane == 0) {
+                p.sp[g] = own ? sp : 0.f;
+                p.pos_local[g] = own ? (int32_t)lp : -1;
+                if (own && gp != 0) atomicAdd(hist + (lp >> p.bt.shift), 1u);
+                if (p.lq_pos_out) p.lq_pos_out[g] = own ? logf(__ldg(p.pop_prob + lp)) : 0.f;
+            }
         }
 
-        // ---- negatives
-        const size_t base = (size_t)g * n;
-        int kept = 0;
-        for (int jb = 0; jb < n; jb += 32) {
-            const int j = jb + lane;
-            const bool valid = j < n;
-            bool mine = false;
-            int lid = 0;
-            float lq = 0.f;
-            uint32_t word = 0u;                                       // the random word of this candidate (MODE 1, 2)
-            if (MODE != 0 && valid) {
-                if (shared) {
-                    word = s_cand[warp * n + j];
-                } else {
-                    const int64_t li = li0 + j, qq = li / p.regen_T, idx = li - qq * p.regen_T;
-                    const uint4 w = Philox::gen(seed, (uint64_t)idx, off / 4 + (uint64_t)(qq >> 2));
-                    const int ii = (int)(qq & 3);
-                    word = ii == 0 ? w.x : (ii == 1 ? w.y : (ii == 2 ? w.z : w.w));
+        // ---- negatives, one segment of <= kPrepSeg candidates at a time
+        const size_t base = g >= 0 ? (size_t)g * n : 0;
+        int kept_total = 0;
+        for (int seg0 = 0; seg0 < (p.do_neg ? n : 0); seg0 += kPrepSeg) {
+            const int m = min(kPrepSeg, n - seg0);
+            const int c = (m + 31) >> 5;                              // candidates per lane
+            __syncthreads();                                          // the previous segment's staging area is consumed
+            // -- A: stage
+            if (shared) {
+                for (int j = threadIdx.x; j < m; j += blockDim.x) {
+                    const uint4 w = Philox::gen(seed, (uint64_t)((int64_t)x * n + seg0 + j), off / 4 + (uint64_t)R);
+                    const int slot = (j % c) * 33 + j / c;
+                    s_cand[0 * kPrepSegWords + slot] = w.x; s_cand[1 * kPrepSegWords + slot] = w.y;
+                    s_cand[2 * kPrepSegWords + slot] = w.z; s_cand[3 * kPrepSegWords + slot] = w.w;
+                }
+            } else if (g >= 0) {
+                for (int j = lane; j < m; j += 32) {
+                    uint32_t v;
+                    if (MODE == 0) {
+                        v = (uint32_t)__ldg(p.neg + base + seg0 + j);
+                    } else {
+                        const int64_t li = li0 + seg0 + j, qq = li / p.regen_T, idx = li - qq * p.regen_T;
+                        const uint4 w = Philox::gen(seed, (uint64_t)idx, off / 4 + (uint64_t)(qq >> 2));
+                        const int ii = (int)(qq & 3);
+                        v = ii == 0 ? w.x : (ii == 1 ? w.y : (ii == 2 ? w.z : w.w));
+                    }
+                    my[(j % c) * 33 + j / c] = v;
                 }
             }
-            if (MODE == 2) {
-                float u = curand_uniform_from_u32(word);              // (0, 1]
-                u = u * 1.0f + 0.0f;
-                if (u == 1.0f) u = 0.0f;                              // -> [0, 1)   (ATen uniform_, DistributionTemplates.h:485-506)
-                mine = valid && u > p.cdf_lo && u <= p.cdf_hi;
-                if (mine) {
+            __syncthreads();
+            if (g < 0) continue;
+            // -- B: lane-private filter + in-place compaction
+            int cnt = 0;
+            for (int i = 0; i < c; ++i) {
+                const int j = lane * c + i;
+                if (j >= m) break;
+                const uint32_t v = my[i * 33 + lane];
+                bool mine;
+                uint32_t keep;
+                if (MODE == 2) {
+                    float u = curand_uniform_from_u32(v);             // (0, 1]
+                    u = u * 1.0f + 0.0f;
+                    if (u == 1.0f) u = 0.0f;                          // -> [0, 1)   (ATen uniform_, DistributionTemplates.h:485-506)
+                    mine = u > p.cdf_lo && u <= p.cdf_hi;
+                    keep = __float_as_uint(u);
+                } else {
+                    int64_t gid = MODE == 0 ? (int64_t)(int32_t)v : (int64_t)(v % (uint32_t)(p.num_items - 1) + 1u);
+                    if (gid < 0 || gid >= p.num_items) { bad = true; gid = 0; }
+                    const int64_t l = gid - p.row0;
+                    mine = l >= 0 && l < p.local_rows;
+                    keep = MODE == 0 ? (uint32_t)j : (uint32_t)l;     // MODE 0 keeps the position: log Q is looked up in C
+                }
+                if (mine) { my[cnt * 33 + lane] = keep; ++cnt; }
+            }
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int total = __shfl_sync(kFull, inc, 31);
+            const size_t out0 = base + kept_total + (inc - cnt);
+            // -- C: resolve + write
+            for (int t = 0; t < cnt; ++t) {
+                const uint32_t v = my[t * 33 + lane];
+                int lid;
+                float lq = 0.f;
+                if (MODE == 2) {
+                    const float u = __uint_as_float(v);
                     int lo = 0, hi = (int)p.local_rows - 1;
                     if (p.pop_guide) {
                         const int64_t k = (int64_t)(u * (float)(1 << p.pop_bits)) - p.pop_k0;    // exact: power-of-two scale
@@ -306,26 +354,21 @@ shard_prep_bins_kernel(const PrepBinParams p) {
                     }
                     lid = local_lower_bound(p.pop_table, lo, hi, u);
                     lq = logf(__ldg(p.pop_prob + lid));
+                } else if (MODE == 0) {
+                    int64_t gid = (int64_t)__ldg(p.neg + base + seg0 + v);
+                    if (gid < 0 || gid >= p.num_items) gid = 0;
+                    lid = (int)(gid - p.row0);
+                    if (p.logq_neg) lq = __ldg(p.logq_neg + base + seg0 + v);
+                } else {
+                    lid = (int)v;
                 }
-            } else {
-                int64_t gid = -1;
-                if (valid) gid = MODE == 0 ? (int64_t)__ldg(p.neg + base + j) : (int64_t)(word % (uint32_t)(p.num_items - 1) + 1u);
-                if (valid && (gid < 0 || gid >= p.num_items)) { bad = true; gid = 0; }
-                const int64_t l = gid - p.row0;
-                mine = valid && l >= 0 && l < p.local_rows;
-                lid = (int)l;
-                if (MODE == 0 && mine && p.logq_neg) lq = __ldg(p.logq_neg + base + j);
-            }
-            const uint32_t mask = __ballot_sync(kFull, mine);
-            if (mine) {
-                const int k = kept + __popc(mask & ((1u << lane) - 1u));
-                p.neg_c[base + k] = lid;
-                if (p.lq_c) p.lq_c[base + k] = lq;
+                p.neg_c[out0 + t] = lid;
+                if (p.lq_c) p.lq_c[out0 + t] = lq;
                 if (p.row0 + lid != 0) atomicAdd(hist + ((uint32_t)lid >> p.bt.shift), 1u);   // padding row: scored, no gradient
             }
-            kept += __popc(mask);
+            kept_total += total;
         }
-        if (lane == 0) p.ncount[g] = kept;
+        if (g >= 0 && lane == 0 && p.do_neg) p.ncount[g] = kept_total;
     }
     if (bad) atomicOr(p.err, 1u);
     if (p.use_smem) {
@@ -492,8 +535,13 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
         RSB_REQUIRE(a->pop_guide_local == nullptr || (a->pop_guide_bits >= 1 && a->pop_guide_bits <= 24), RSB200_EINVAL, "bad guide_bits");
     }
 
-    if ((phases & RSB200_SHARD_PREP) && bins) {
-        RSB_CUDA(cudaMemsetAsync(bt.cnt, 0, sizeof(uint32_t) * (size_t)bt.nbins, st));
+    // PREP = PREP_NEG (negatives: needs only the draw; may run while the queries are still being gathered) + PREP_POS
+    // (positives + the scan of the bin histogram)
+    const bool prep_neg = (phases & (RSB200_SHARD_PREP | RSB200_SHARD_PREP_NEG)) != 0;
+    const bool prep_pos = (phases & (RSB200_SHARD_PREP | RSB200_SHARD_PREP_POS)) != 0;
+    RSB_REQUIRE(bins || !(phases & (RSB200_SHARD_PREP_NEG | RSB200_SHARD_PREP_POS)), RSB200_EUNSUPPORTED, "split PREP needs grouping 1");
+    if ((prep_neg || prep_pos) && bins) {
+        if (prep_neg) RSB_CUDA(cudaMemsetAsync(bt.cnt, 0, sizeof(uint32_t) * (size_t)bt.nbins, st));
         if (G > 0) {
             PrepBinParams p;
             p.w_local = a->w_local; p.q_all = a->q_all; p.pos = a->pos; p.neg = a->neg; p.logq_neg = a->logq_neg;
@@ -511,14 +559,16 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
                 int64_t grid = (int64_t)a->regen_sm_count * (a->regen_max_threads_per_sm / 256);
                 if (cdiv(numel, 256) < grid) grid = cdiv(numel, 256);
                 p.regen_T = 256 * (grid > 0 ? grid : 1);
-                if (n > 0 && p.regen_T % n == 0 && n <= 2048) {       // four queries share every Philox block
+                if (n > 0 && p.regen_T % n == 0) {                    // four queries share every Philox block
                     p.t_per = (int)(p.regen_T / n);
                     p.n_round_blocks = (int)cdiv(a->regen_B, 4 * (int64_t)p.t_per);
                 }
                 mode = a->regen_kind == 1 ? 2 : 1;
             }
+            p.do_neg = prep_neg ? 1 : 0; p.do_pos = prep_pos ? 1 : 0;       // one launch does whatever halves are requested
+            if (!p.do_neg) { p.t_per = 0; p.n_round_blocks = 0; mode = 0; }      // positives only: plain query-major mapping
             p.use_smem = bt.nbins <= 8192;
-            const size_t smem = sizeof(uint32_t) * ((p.use_smem ? (size_t)bt.nbins : 0) + (p.t_per ? 4 * (size_t)n : 0));
+            const size_t smem = sizeof(uint32_t) * ((p.use_smem ? (size_t)bt.nbins : 0) + 4 * (size_t)kPrepSegWords);
             const int64_t nitems = p.t_per ? (G / a->regen_B) * p.n_round_blocks * p.t_per : cdiv(G, 4);
             int64_t blocks = (int64_t)sm_count() * 4;
             if (blocks > nitems) blocks = nitems;
@@ -531,8 +581,10 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
 #undef RSB_PREP
             RSB_LAUNCH_CHECK();
         }
-        rc = launch_bin_scan(bt, none, st);
-        if (rc) return rc;
+        if (prep_pos) {
+            rc = launch_bin_scan(bt, none, st);
+            if (rc) return rc;
+        }
     }
     if ((phases & RSB200_SHARD_PREP) && !bins) {
         RSB_CUDA(cudaMemsetAsync(a->off, 0, sizeof(uint32_t) * (size_t)(a->local_rows + 1), st));

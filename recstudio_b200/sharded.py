@@ -331,6 +331,13 @@ class OwnerComputeCuda:
         self._run(_lib.SHARD_PREP, "shard_step(PREP)")
         return self.sp2[:, :self.G] if self._sum_lqp else self.sp[:self.G]
 
+    def prep_neg(self):                        # the half of PREP that does not need q_all / pos: may overlap their all-gather
+        self._run(_lib.SHARD_PREP_NEG, "shard_step(PREP_NEG)")
+
+    def prep_pos(self) -> torch.Tensor:        # the other half (+ the bin scan); same return value as prep()
+        self._run(_lib.SHARD_PREP_POS, "shard_step(PREP_POS)")
+        return self.sp2[:, :self.G] if self._sum_lqp else self.sp[:self.G]
+
     def fwd(self) -> torch.Tensor:             # -> this owner's stats slice [G, 2]   (all-gather next)
         self._run(_lib.SHARD_FWD, "shard_step(FWD)")
         return self.stats_all[self.rank, :self.G]

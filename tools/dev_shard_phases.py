@@ -31,7 +31,8 @@ def main():
     sb = bench.ShardedBench(a.items, dev, world, rank, sampler=a.sampler)
     eng, sh = sb.eng, sharded
     gen = torch.Generator(device=dev).manual_seed(rank)
-    names = ["gather_q+state", "allgather(q,pos)", "prep", "allreduce(sp)", "fwd", "allgather(stats)", "finish", "scatter", "allreduce(dq)"]
+    names = ["gather_q+state", "prep_neg (all-gather of q, pos in flight)", "all-gather wait + prep_pos", "allreduce(sp)", "fwd",
+             "allgather(stats)", "finish", "scatter", "allreduce(dq)"]
     tot = {k: 0.0 for k in names}
     for it in range(a.steps + 5):
         u = torch.randint(1, bench.N_USERS, (bench.BATCH,), device=dev, generator=gen)
@@ -42,11 +43,14 @@ def main():
         q = sh.CudaOps.gather_rows(sb.wu, u)
         state = sb.states.next()
         ev[1].record()
-        q_all, pos_all = sh._all_gather_cat(q), sh._all_gather_cat(p)
-        ev[2].record()
+        w1 = dist.all_gather_into_tensor(sb.q_all, q, async_op=True)
+        w2 = dist.all_gather_into_tensor(sb.pos_all, p, async_op=True)
         kw = {"pop": sb.pop} if sb.pop is not None else {}
-        eng.bind(q_all, pos_all, None, _lib.LOSS_BPR, _lib.SCORE_IP, regen_state=state, **kw)
-        sp = eng.prep()
+        eng.bind(sb.q_all, sb.pos_all, None, _lib.LOSS_BPR, _lib.SCORE_IP, regen_state=state, **kw)
+        eng.prep_neg()
+        ev[2].record()
+        w1.wait(); w2.wait()
+        sp = eng.prep_pos()
         ev[3].record()
         dist.all_reduce(sp)
         ev[4].record()
