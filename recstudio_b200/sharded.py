@@ -429,7 +429,6 @@ class DrawStates:
         self.inc = sampling.counter_offset(B * n, self.device)
         self.B, self.n = B, n
         self._inc_dev = torch.tensor([0, self.inc], dtype=torch.int64, device=self.device)
-        self.graph_owned = False               # True while a CUDA graph that contains the device-side advance is in use
         self.resync()
 
     def resync(self):
@@ -442,12 +441,9 @@ class DrawStates:
     def next(self) -> torch.Tensor:
         if (self.gen.initial_seed(), self.gen.get_offset()) != self._expect:
             raise _lib.Rsb200Error("DrawStates: the CUDA generator was used outside the sharded step; call resync() on every rank")
-        if self.graph_owned:                   # a captured step advances the device copy itself, after its PREP
-            pass
-        else:
-            if self._pending:                  # the previous step's PREP is already enqueued on this stream: advance after it
-                self.state += self._inc_dev
-            self._pending = True
+        if self._pending:                      # the previous step's PREP is already enqueued on this stream: advance after it
+            self.state += self._inc_dev
+        self._pending = True
         seed, off = self._expect
         self.gen.set_offset(off + self.inc)
         self._expect = (seed, off + self.inc)
