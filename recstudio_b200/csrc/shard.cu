@@ -183,6 +183,7 @@ struct PrepBinParams {
     BinTable bt;
     int64_t num_items, row0, local_rows;
     int G, n, D, euclid, use_smem;
+    uint64_t mod_magic;            // ceil(2^64 / (num_items - 1)): division-free v mod (num_items - 1)
     int do_pos, do_neg;            // PREP may be split: negatives (independent of the batch's queries) | positives
     // regeneration
     const uint64_t* regen_state; int regen_B; int64_t regen_T; int t_per; int n_round_blocks;
@@ -215,7 +216,7 @@ constexpr int kPrepSegWords = (kPrepSeg / 32) * 33;  // lane-major staging with 
 //      (query order) without a ballot per 32 candidates, and all 32 lanes test candidates all the time;
 //   C  every lane resolves and writes its kept candidates (the popularity search runs here, on owned draws only).
 template <int MODE>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 6)
 shard_prep_bins_kernel(const PrepBinParams p) {
     extern __shared__ uint32_t s_dyn[];
     uint32_t* s_hist = s_dyn;                                         // [nbins] (use_smem)
@@ -311,6 +312,7 @@ shard_prep_bins_kernel(const PrepBinParams p) {
             if (g < 0) continue;
             // -- B: lane-private filter + in-place compaction
             int cnt = 0;
+#pragma unroll 4
             for (int i = 0; i < c; ++i) {
                 const int j = lane * c + i;
                 if (j >= m) break;
@@ -324,11 +326,18 @@ shard_prep_bins_kernel(const PrepBinParams p) {
                     mine = u > p.cdf_lo && u <= p.cdf_hi;
                     keep = __float_as_uint(u);
                 } else {
-                    int64_t gid = MODE == 0 ? (int64_t)(int32_t)v : (int64_t)(v % (uint32_t)(p.num_items - 1) + 1u);
-                    if (gid < 0 || gid >= p.num_items) { bad = true; gid = 0; }
-                    const int64_t l = gid - p.row0;
-                    mine = l >= 0 && l < p.local_rows;
-                    keep = MODE == 0 ? (uint32_t)j : (uint32_t)l;     // MODE 0 keeps the position: log Q is looked up in C
+                    uint32_t gid;
+                    if (MODE == 0) {
+                        gid = v;
+                        if (gid >= (uint32_t)p.num_items) { bad = true; gid = 0u; }      // also catches negative ids
+                    } else {
+                        // v mod (N - 1) + 1 (ATen random_from_to, 32-bit path) without a division: Lemire's fastmod,
+                        // exact for every 32-bit v:  M = ceil(2^64 / d),  v mod d = mulhi64((M * v) mod 2^64, d)
+                        gid = (uint32_t)__umul64hi(p.mod_magic * (uint64_t)v, (uint64_t)(uint32_t)(p.num_items - 1)) + 1u;
+                    }
+                    const uint32_t l = gid - (uint32_t)p.row0;        // wraps for rows below the block: fails the test
+                    mine = l < (uint32_t)p.local_rows;
+                    keep = MODE == 0 ? (uint32_t)j : l;               // MODE 0 keeps the position: log Q is looked up in C
                 }
                 if (mine) { my[cnt * 33 + lane] = keep; ++cnt; }
             }
@@ -566,11 +575,12 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
                 mode = a->regen_kind == 1 ? 2 : 1;
             }
             p.do_neg = prep_neg ? 1 : 0; p.do_pos = prep_pos ? 1 : 0;       // one launch does whatever halves are requested
+            p.mod_magic = a->num_items > 1 ? (~(uint64_t)0) / (uint64_t)(a->num_items - 1) + 1 : 0;
             if (!p.do_neg) { p.t_per = 0; p.n_round_blocks = 0; mode = 0; }      // positives only: plain query-major mapping
             p.use_smem = bt.nbins <= 8192;
             const size_t smem = sizeof(uint32_t) * ((p.use_smem ? (size_t)bt.nbins : 0) + 4 * (size_t)kPrepSegWords);
             const int64_t nitems = p.t_per ? (G / a->regen_B) * p.n_round_blocks * p.t_per : cdiv(G, 4);
-            int64_t blocks = (int64_t)sm_count() * 4;
+            int64_t blocks = (int64_t)sm_count() * 6;
             if (blocks > nitems) blocks = nitems;
 #define RSB_PREP(M)                                                                                                       \
     do {                                                                                                                  \
