@@ -90,6 +90,12 @@ class FusedSASRecQueryEncoder(torch.nn.Module):
         self.dropout = torch.nn.Dropout(p=dropout)
         self.p_drop = float(dropout)
 
+    @property
+    def pools_to_2d(self) -> bool:
+        """whether forward() yields a [rows, d] matrix in the current mode (FusedRetrieverMixin decides from this, before the
+        encoder runs, whether the fused full-softmax step applies)"""
+        return (self.training_pooling_type if self.training else self.eval_pooling_type) in ("mask", "last", "sum", "mean", "concat")
+
     # one post-norm encoder layer (torch.nn.TransformerEncoderLayer.forward, norm_first=False) with the fused core
     def _layer(self, lyr, x: Tensor, hist: Tensor) -> Tensor:
         at = lyr.self_attn

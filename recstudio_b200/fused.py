@@ -197,9 +197,19 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
     return ws.loss[0]
 
 
+def check_ids(ws: PairWorkspace):
+    """Raise if any step on this workspace saw a user / item / negative id outside its table (host-synchronising).
+    Such ids are never dereferenced: they are scored as the padding row 0 and receive no gradient -- where the reference's
+    F.embedding raises an index error / device assert -- so a corrupted batch or an off-by-one ``num_items`` shows up here."""
+    if int(ws.err_flag.item()):
+        ws.err_flag.zero_()
+        raise _lib.Rsb200Error("fused step: an id of the batch was outside [0, rows) of its table (it was scored as the padding row)")
+
+
 def sparse_grads(ws: PairWorkspace):
     """Host-synchronising read-out of the compact gradients:
-    ((item_rows[R], item_vals[R,d]), (user_rows[Ru], user_vals[Ru,d]))."""
+    ((item_rows[R], item_vals[R,d]), (user_rows[Ru], user_vals[Ru,d])).  Also runs ``check_ids``."""
+    check_ids(ws)
     tot = ws.totals.tolist()
     ri, ru = tot[1], tot[3]
     return (ws.item_rows[:ri], ws.item_vals[:ri]), (ws.user_rows[:ru], ws.user_vals[:ru])

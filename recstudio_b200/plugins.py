@@ -37,10 +37,13 @@ def _need_cuda(t: Tensor, what: str):
 
 # ============================================================================ E1 / E2
 class _GatherFn(torch.autograd.Function):
-    """F.embedding forward (gather) / embedding_dense_backward (scatter-add, row 0 skipped)."""
+    """F.embedding forward (gather) / embedding backward.  The backward follows ``emb.grad_mode``:
+    'dense'  embedding_dense_backward (scatter-add into a zero-filled [N, d] gradient, row 0 skipped) -- the reference;
+    'sparse' the touched rows only, as a coalesced sparse-COO gradient (rsb200_rows_coalesce);
+    'rows'   the touched rows are left in ``emb._extra_row_grads`` for FusedRowOptimizer (no ``.grad`` at all)."""
 
     @staticmethod
-    def forward(ctx, weight: Tensor, ids: Tensor):
+    def forward(ctx, weight: Tensor, ids: Tensor, emb):
         _need_cuda(weight, "embedding table")
         ids_c = ids.to(device=weight.device, dtype=torch.int64).contiguous()
         out = torch.empty(ids_c.shape + (weight.shape[1],), dtype=torch.float32, device=weight.device)
@@ -49,17 +52,27 @@ class _GatherFn(torch.autograd.Function):
                                            ptr(out), stream_ptr()), "gather_rows")
         ctx.save_for_backward(ids_c)
         ctx.wshape = tuple(weight.shape)
+        ctx.emb = emb
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
         (ids_c,) = ctx.saved_tensors
         g = g.contiguous()
+        mode = getattr(ctx.emb, "grad_mode", "dense")
+        if mode != "dense":
+            from .sharded import CudaOps
+            rows, vals = CudaOps.coalesce_rows(ids_c.reshape(-1), g.reshape(-1, ctx.wshape[1]), ctx.wshape[0], skip_row0=True)
+            if mode == "rows":
+                ctx.emb.__dict__.setdefault("_extra_row_grads", []).append((rows, vals))
+                return None, None, None
+            gi = torch.sparse_coo_tensor(rows.unsqueeze(0), vals, size=ctx.wshape, is_coalesced=True, check_invariants=False)
+            return gi, None, None
         dw = torch.zeros(ctx.wshape, dtype=torch.float32, device=g.device)
         with torch.cuda.device(g.device):
             check(lib().rsb200_scatter_add_rows(ptr(dw), ctx.wshape[0], ctx.wshape[1], ptr(ids_c), ids_c.numel(),
                                                 ptr(g), stream_ptr()), "scatter_add_rows")
-        return dw, None
+        return dw, None, None
 
 
 class FusedEmbedding(torch.nn.Embedding):
@@ -69,7 +82,10 @@ class FusedEmbedding(torch.nn.Embedding):
     takes its O(1) ``weight[1:]`` path only for nn.Embedding, baseretriever.py:122-123),
     ``.weight`` stays a live Parameter for ``state_dict`` / optimizers / ``model.to()``.
     Accepts index tensors of any rank (SASRec calls it on [B, L], sasrec.py:42).
+    ``grad_mode`` ('dense' | 'sparse' | 'rows') selects the form of the backward, see ``_GatherFn``; a FusedRetriever
+    sets it from its ``fused_grad`` when the table is shared with a sequence encoder.
     """
+    grad_mode = "dense"
 
     def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: Optional[int] = 0, **kw):
         if embedding_dim % 4 != 0:
@@ -79,7 +95,7 @@ class FusedEmbedding(torch.nn.Embedding):
         super().__init__(num_embeddings, embedding_dim, padding_idx=0, **kw)
 
     def forward(self, ids: Tensor) -> Tensor:
-        return _GatherFn.apply(self.weight, ids)
+        return _GatherFn.apply(self.weight, ids, self)
 
 
 # ============================================================================ S1 / S2
@@ -602,9 +618,13 @@ class FusedRetrieverMixin:
         wi = self.item_encoder.weight
         if not wi.is_cuda or wi.shape[1] > 128:
             return None
+        # decided from static properties BEFORE the encoder runs: a [B, d] query needs a table / pooled sequence encoder
+        # (running the encoder first and then falling back would encode twice and consume its dropout stream twice)
+        if not (isinstance(self.query_encoder, torch.nn.Embedding) or getattr(self.query_encoder, "pools_to_2d", False)):
+            return None
         query = self.query_encoder(self._get_query_feat(batch))         # any query encoder (keeps its own autograd)
         if query.dim() != 2:
-            return None
+            raise _lib.Rsb200Error("query encoder declared a [B, d] output but returned %s" % (tuple(query.shape),))
         return _FullSoftmaxFn.apply(query, wi, batch[self.fiid])
 
     def training_step(self, batch):
@@ -645,6 +665,10 @@ class FusedRetrieverMixin:
             user = batch[self.fuid].to(wi.device, non_blocking=True).contiguous()
             ws = self._fused_ws(B, n, wu.shape[0])
         else:
+            # the item table may also be read by the query encoder (SASRec shares the module, sasrec.py:107): its
+            # encoder-side gradient takes the same form as the head's (dense | sparse rows | rows for the row optimizer)
+            if isinstance(self.item_encoder, FusedEmbedding):
+                self.item_encoder.grad_mode = {"dense": "dense", "sparse": "sparse", "rows": "rows"}.get(self.fused_grad, "dense")
             if query is None:
                 query = self.query_encoder(self._get_query_feat(batch))  # [B, d], keeps its own autograd graph
             if query.dim() != 2 or query.shape[0] != B:
@@ -663,6 +687,13 @@ class FusedRetrieverMixin:
         if two_tables:
             return _FusedStepFn.apply(wi, wu, self, ws, user, pos, neg32, lqp, lqn, loss_kind, score_kind)
         return _FusedHeadFn.apply(wi, query, self, ws, pos, neg32, lqp, lqn, loss_kind, score_kind)
+
+    def training_epoch_end(self, output_list):
+        """recommender.py:249-277, preceded by the id check of the epoch's fused steps: ids outside their table are scored
+        as the padding row instead of raising like F.embedding -- report them once per epoch (one host sync)."""
+        for ws in self.__dict__.get("_fused_ws_cache", {}).values():
+            fused.check_ids(ws)
+        return super().training_epoch_end(output_list)
 
     def topk(self, batch, k, user_h=None, return_query=False):
         """BaseRetriever.topk (baseretriever.py:374-397) on rsb200_topk_full when the scorer is

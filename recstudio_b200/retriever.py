@@ -60,18 +60,41 @@ class FusedRetriever(plugins.FusedRetrieverMixin, iface.BaseRetriever):
         the fused step's workspace; every other parameter keeps the reference's optimizer."""
         if self.fused_grad not in ("rows", "apply"):
             return super()._get_optimizers()
+        import warnings
         from .rowopt import FusedRowOptimizer
         tr = self.config["train"]
         name = str(tr.get("learner", "adam")).lower()
-        learner = {"sgd": "sgd", "adagrad": "adagrad"}.get(name, "sparse_adam")      # adam / sparse_adam -> SparseAdam semantics
+        learner = {"sgd": "sgd", "adagrad": "adagrad", "adam": "sparse_adam", "sparse_adam": "sparse_adam"}.get(name)
+        if learner is None:
+            raise ValueError("fused_grad=%r steps the embedding tables with a touched-row optimizer: learner must be one of "
+                             "sgd / adagrad / adam / sparse_adam, got %r" % (self.fused_grad, name))
+        if name == "adam":
+            warnings.warn("fused_grad=%r: the embedding tables are stepped with SparseAdam semantics (moments of untouched rows do "
+                          "not decay), not the reference's dense Adam; use fused_grad='dense' for the reference's optimizer"
+                          % self.fused_grad, stacklevel=2)
+        wd = tr.get("weight_decay", 0) or 0
+        if wd:
+            warnings.warn("fused_grad=%r: train.weight_decay=%g is NOT applied to the embedding tables (a touched-row optimizer "
+                          "cannot decay untouched rows); it still applies to every other parameter" % (self.fused_grad, wd), stacklevel=2)
         lr = tr.get("learning_rate", 0.001)
-        opts = [{"optimizer": FusedRowOptimizer(self, learner, lr=lr)}]
+        row_opt = FusedRowOptimizer(self, learner, lr=lr)
+        opts = [{"optimizer": row_opt}]
+        sched = self._get_scheduler(tr.get("scheduler", None), row_opt)     # torch schedulers only touch param_groups[i]['lr']
+        if sched:
+            m = self.val_metric if getattr(self, "val_check", False) else "train_loss"      # set by fit() (recommender.py:129-136)
+            opts[0]["lr_scheduler"] = {"scheduler": sched, "monitor": m, "interval": "epoch", "frequency": 1, "strict": False}
         tables = {id(self.item_encoder.weight)}
         if isinstance(self.query_encoder, torch.nn.Embedding):
             tables.add(id(self.query_encoder.weight))
         rest = [p for p in self.parameters() if id(p) not in tables]
         if rest:
-            opts.append({"optimizer": self._get_optimizer(name, rest, lr, tr.get("weight_decay", 0))})
+            opt = self._get_optimizer(name, rest, lr, tr.get("weight_decay", 0))
+            ent = {"optimizer": opt}
+            sched = self._get_scheduler(tr.get("scheduler", None), opt)
+            if sched:
+                m = self.val_metric if getattr(self, "val_check", False) else "train_loss"
+                ent["lr_scheduler"] = {"scheduler": sched, "monitor": m, "interval": "epoch", "frequency": 1, "strict": False}
+            opts.append(ent)
         return opts
 
 

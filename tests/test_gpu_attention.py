@@ -186,6 +186,50 @@ def test_sasrec_fused_head_training_step(mode):
     assert (gi.cpu()[sel] - want[sel]).abs().max().item() <= 1e-5 * want.abs().max().item()
 
 
+def test_sasrec_rows_mode_steps_the_shared_table_with_head_and_encoder_gradients():
+    """fused_grad='rows' with a sequence encoder that SHARES the item table (sasrec.py:107): the table receives gradient
+    through the head (rows in the fused workspace) AND through the encoder's [B, L] gather (FusedEmbedding.grad_mode =
+    'rows').  FusedRowOptimizer must apply both -- one update per row with the summed gradient -- so one SGD step equals
+    the reference-compatible dense mode + torch.optim.SGD, and no dense [N, d] .grad is left behind."""
+    from recstudio_b200 import retriever, rowopt
+    N, d, Lq, B, n, lr = 5_001, 128, 64, 16, 40, 0.5
+    models = {}
+    for mode in ("dense", "rows"):
+        m = retriever.build_sasrec_synthetic(N, d, n, max_seq_len=Lq, fused_grad=mode, device=DEV, init_std=0.1, seed=3)
+        m.config["train"].update({"learner": "sgd", "learning_rate": lr, "weight_decay": 0, "scheduler": None})
+        models[mode] = m
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    seqlen = torch.randint(1, Lq + 1, (B,), device=DEV, generator=gen)
+    ids = torch.randint(1, N, (B, Lq), device=DEV, generator=gen) * (torch.arange(Lq, device=DEV)[None, :] < seqlen[:, None])
+    batch = {"in_item_id": ids, "seqlen": seqlen, "item_id": torch.randint(1, N, (B,), device=DEV, generator=gen),
+             "rating": torch.ones(B, device=DEV)}
+    before = models["dense"].item_encoder.weight.detach().clone()
+    assert torch.equal(before, models["rows"].item_encoder.weight)
+    for mode, m in models.items():
+        m.train()
+        opts = m._get_optimizers()
+        assert (mode == "rows") == isinstance(opts[0]["optimizer"], rowopt.FusedRowOptimizer)
+        torch.manual_seed(11)
+        for o in opts:
+            o["optimizer"].zero_grad()
+        loss = m.training_step(dict(batch))
+        loss.backward()
+        if mode == "rows":
+            assert m.item_encoder.weight.grad is None            # no dense [N, d] gradient accumulates
+        for o in opts:
+            o["optimizer"].step()
+    da = models["dense"].item_encoder.weight.detach() - before
+    db = models["rows"].item_encoder.weight.detach() - before
+    touched_by_encoder = torch.zeros(N, dtype=torch.bool, device=DEV); touched_by_encoder[ids.unique()] = True
+    assert da[touched_by_encoder].abs().max().item() > 0         # the encoder-side gradient is really there ...
+    assert (da - db).abs().max().item() <= 2e-4 * da.abs().max().item()     # ... and the row optimizer applied it (bf16 attention noise)
+    assert float(models["rows"].item_encoder.weight[0].abs().sum()) == 0.0
+    # the transformer parameters were stepped by the reference optimizer in both modes
+    pa = models["dense"].query_encoder.transformer_layer.layers[0].linear1.weight
+    pb = models["rows"].query_encoder.transformer_layer.layers[0].linear1.weight
+    assert (pa - pb).abs().max().item() <= 2e-4 * pa.abs().max().item()
+
+
 def test_bert4rec_masked_training_step():
     """BERT4Rec on the fused kernels (bert4rec.py:8-58): bidirectional tcgen05 attention, 'mask' pooling (one query per
     masked position), the item table extended by the mask-token row, full-catalog SoftmaxLoss through

@@ -78,3 +78,44 @@ def test_apply_matches_rows(loss, scorer):
             wa, wb = getattr(models[0], name).weight, getattr(models[1], name).weight
             assert (wa - wb).abs().max().item() <= 1e-6 * wa.abs().max().item()
     assert float(models[1].item_encoder.weight[0].abs().sum()) == 0.0
+
+
+def test_row_optimizer_is_a_torch_optimizer_with_state_dict_and_scheduler():
+    """lr is read from param_groups at every step (torch lr schedulers drive it), the moments and the step
+    count survive state_dict() / load_state_dict(), and the reference's _get_optimizers hook keeps the configured scheduler
+    (returned under 'lr_scheduler' like recommender.py:431-441) and warns about semantics it cannot keep."""
+    import warnings
+    from recstudio_b200 import retriever, rowopt
+    U, N, d, B, n = 50, 400, 32, 16, 8
+    m = retriever.build_synthetic(U, N, d, n, fused_grad="rows", device=DEV, init_std=0.2, seed=1)
+    m.config["train"].update({"learner": "adam", "learning_rate": 0.1, "weight_decay": 1e-4, "scheduler": "exponential"})
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        opts = m._get_optimizers()
+    msgs = " ".join(str(x.message) for x in w)
+    assert "SparseAdam" in msgs and "weight_decay" in msgs
+    opt = opts[0]["optimizer"]
+    assert isinstance(opt, rowopt.FusedRowOptimizer) and isinstance(opt, torch.optim.Optimizer)
+    sched = opts[0]["lr_scheduler"]["scheduler"]
+    assert isinstance(sched, torch.optim.lr_scheduler.ExponentialLR)
+    batch = {"user_id": torch.arange(1, B + 1, device=DEV), "item_id": torch.arange(1, B + 1, device=DEV), "rating": torch.ones(B, device=DEV)}
+
+    def one_step(model, o):
+        torch.manual_seed(3)
+        o.zero_grad(); model.training_step(dict(batch)).backward(); o.step()
+
+    one_step(m, opt)
+    sched.step()
+    assert abs(opt.lr - 0.1 * 0.98) < 1e-12                        # the next step runs at the scheduled rate
+    sd = opt.state_dict()
+    assert sd["step_count"] == 1 and sd["state"]["item_encoder.weight"]["state1"].abs().sum().item() > 0
+    # resume in a fresh model / optimizer: same weights + loaded state => identical second step
+    m2 = retriever.build_synthetic(U, N, d, n, fused_grad="rows", device=DEV, init_std=0.2, seed=1)
+    m2.load_state_dict(m.state_dict())
+    opt2 = rowopt.FusedRowOptimizer(m2, "sparse_adam", lr=0.1)
+    opt2.load_state_dict(sd)
+    one_step(m, opt); one_step(m2, opt2)
+    assert torch.equal(m.item_encoder.weight, m2.item_encoder.weight) and torch.equal(m.query_encoder.weight, m2.query_encoder.weight)
+    with pytest.raises(ValueError):
+        m.config["train"]["learner"] = "rmsprop"
+        m._get_optimizers()
