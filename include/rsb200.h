@@ -255,6 +255,14 @@ int32_t rsb200_pair_workspace_sizes(int64_t num_items, int64_t num_users, int64_
                                     rsb200_pair_sizes* out);
 
 int32_t rsb200_pair_step(const rsb200_pair_args* args, int32_t phases, void* stream);
+/* UniformSampler draw fused with RSB200_PHASE_COUNT (grouping 1): the ids torch.randint(1, num_items, (B, n), device='cuda')
+ * would return for the generator state -- (seed, philox_offset), or state_dev[0..1] in DEVICE memory when state_dev != NULL
+ * (advanced on the device afterwards, as rsb200_sample_uniform_dev) -- are written to neg_out_i32 (which must be args->neg_i32)
+ * and histogrammed per bin while they are in registers, together with args->pos / args->user.  Follow it with
+ * rsb200_pair_step(args, RSB200_PHASE_SCAN | RSB200_PHASE_FWD | RSB200_PHASE_SCATTER, stream).
+ * Replaces UniformSampler.forward (recstudio/ann/sampler.py:86-114) + the grouping pass of the embedding backward. */
+int32_t rsb200_pair_draw_count(const rsb200_pair_args* args, uint64_t* state_dev, uint64_t seed, uint64_t philox_offset,
+                               int32_t sm_count, int32_t max_threads_per_sm, int32_t* neg_out_i32, void* stream);
 /* sizeof(rsb200_pair_args) as compiled into the library (binding sanity check) */
 size_t  rsb200_sizeof_pair_args(void);
 

@@ -129,6 +129,7 @@ def lib():
             "rsb200_segment_search": [v, v, i64, v, v, v, i64, v, v, v, v],
             "rsb200_pair_workspace_sizes": [i64, i64, i64, i64, i64, C.POINTER(PairSizes)],
             "rsb200_pair_step": [C.POINTER(PairArgs), i32, v],
+            "rsb200_pair_draw_count": [C.POINTER(PairArgs), v, u64, u64, i32, i32, v, v],
             "rsb200_shard_step": [C.POINTER(ShardArgs), i32, v],
             "rsb200_gather_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_scatter_add_rows": [v, i64, i64, v, i64, v, v],

@@ -145,6 +145,31 @@ static int32_t check_pair(const rsb200_pair_args* a) {
     return 0;
 }
 
+static void pair_bin_tables(const rsb200_pair_args* a, BinTable& ti, BinTable& tu) {
+    ti = BinTable{}; tu = BinTable{};
+    ti.nbins = (int)cdiv(a->num_items, (int64_t)1 << a->bin_shift); ti.shift = a->bin_shift; ti.num_rows = a->num_items;
+    tu.nbins = (int)cdiv(a->num_users, (int64_t)1 << a->bin_shift_user); tu.shift = a->bin_shift_user; tu.num_rows = a->num_users;
+    ti.cnt = a->bin_cnt; ti.off = a->bin_off; ti.cursor = a->bin_cursor; ti.status = a->bin_status; ti.ticket = a->bin_ticket;
+    ti.totals = a->totals;
+    tu.cnt = a->bin_cnt + ti.nbins; tu.off = a->bin_off + ti.nbins + 1; tu.cursor = a->bin_cursor + (size_t)ti.nbins * kCursorStride;
+    tu.status = a->bin_status + ti.nbins; tu.ticket = a->bin_ticket + 1; tu.totals = a->totals + 2;
+}
+
+extern "C" int32_t rsb200_pair_draw_count(const rsb200_pair_args* a, uint64_t* state_dev, uint64_t seed, uint64_t philox_offset,
+                                          int32_t sm_count_, int32_t max_threads_per_sm, int32_t* neg_out_i32, void* stream) {
+    int32_t rc = check_pair(a);
+    if (rc) return rc;
+    RSB_REQUIRE(a->grouping == 1, RSB200_EUNSUPPORTED, "rsb200_pair_draw_count needs the binned grouping (grouping = 1)");
+    RSB_REQUIRE(neg_out_i32 != nullptr && a->neg_i32 == neg_out_i32, RSB200_EINVAL, "neg_out_i32 must be the args' neg_i32 buffer");
+    RSB_REQUIRE(sm_count_ > 0 && max_threads_per_sm >= 256 && philox_offset % 4 == 0, RSB200_EINVAL, "bad draw policy / philox offset");
+    RSB_REQUIRE(a->num_items >= 2 && a->num_items - 1 < ((int64_t)1 << 28) && a->B * a->n * 8 < ((int64_t)1 << 31), RSB200_EUNSUPPORTED,
+                "draw outside ATen's 32-bit path (see rsb200_sample_uniform)");
+    BinTable ti, tu;
+    pair_bin_tables(a, ti, tu);
+    return launch_draw_bin_count(state_dev, seed, philox_offset, a->B, a->n, sm_count_, max_threads_per_sm, neg_out_i32, a->pos, a->B, ti,
+                                 a->user, a->B, tu, a->err_flag, (cudaStream_t)stream);
+}
+
 extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, void* stream) {
     int32_t rc = check_pair(a);
     if (rc) return rc;
@@ -154,14 +179,7 @@ extern "C" int32_t rsb200_pair_step(const rsb200_pair_args* a, int32_t phases, v
 
     const bool bins = a->grouping == 1;
     BinTable ti = {}, tu = {};
-    if (bins) {
-        ti.nbins = (int)cdiv(a->num_items, (int64_t)1 << a->bin_shift); ti.shift = a->bin_shift; ti.num_rows = a->num_items;
-        tu.nbins = (int)cdiv(a->num_users, (int64_t)1 << a->bin_shift_user); tu.shift = a->bin_shift_user; tu.num_rows = a->num_users;
-        ti.cnt = a->bin_cnt; ti.off = a->bin_off; ti.cursor = a->bin_cursor; ti.status = a->bin_status; ti.ticket = a->bin_ticket;
-        ti.totals = a->totals;
-        tu.cnt = a->bin_cnt + ti.nbins; tu.off = a->bin_off + ti.nbins + 1; tu.cursor = a->bin_cursor + (size_t)ti.nbins * kCursorStride;
-        tu.status = a->bin_status + ti.nbins; tu.ticket = a->bin_ticket + 1; tu.totals = a->totals + 2;
-    }
+    if (bins) pair_bin_tables(a, ti, tu);
     if (phases & RSB200_PHASE_COUNT) {
         if (bins) {
             if (a->neg_i32) rc = launch_bin_count<int32_t>(a->neg_i32, B * n, a->pos, B, ti, a->user, B, tu, nullptr, a->err_flag, st);

@@ -127,6 +127,92 @@ template int32_t launch_bin_count<int32_t>(const int32_t*, int64_t, const int64_
 template int32_t launch_bin_count<int64_t>(const int64_t*, int64_t, const int64_t*, int64_t, const BinTable&, const int64_t*, int64_t,
                                            const BinTable&, int32_t*, uint32_t*, cudaStream_t);
 
+// ------------------------------------------------------------------------------------------ DRAW + BIN_COUNT
+// The UniformSampler draw (sampler.cu: torch.randint's Philox element map) with the bin histogram taken while the ids are
+// still in registers: the 33 MB id matrix is written once and not re-read by a separate count pass.  (seed, offset) come
+// from device memory when state != null (CUDA-graph replays draw fresh ids), else from the arguments.
+__global__ void __launch_bounds__(256)
+draw_bin_count_kernel(const uint64_t* __restrict__ state, uint64_t seed_h, uint64_t ctr_h, int64_t T, int64_t rounds, int64_t numel,
+                      uint32_t range, uint64_t mod_magic, int32_t* __restrict__ out32, const int64_t* __restrict__ pos, int64_t B,
+                      const BinTable t0, const int64_t* __restrict__ ids1, int64_t B1, const BinTable t1, int use_smem,
+                      uint32_t* __restrict__ err_flag) {
+    extern __shared__ uint32_t s_hist[];
+    const int nb0 = t0.nbins, nb1 = t1.nbins;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < nb0 + nb1; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    uint32_t* h0 = use_smem ? s_hist : t0.cnt;
+    uint32_t* h1 = use_smem ? s_hist + nb0 : t1.cnt;
+    const uint64_t seed = state ? state[0] : seed_h, ctr_base = state ? state[1] / 4 : ctr_h;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t t = i0; t < T * rounds; t += stride) {
+        const int64_t r = t / T, idx = t - r * T;
+        const uint4 w = Philox::gen(seed, (uint64_t)idx, ctr_base + (uint64_t)r);
+        const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+        int64_t li = r * 4 * T + idx;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii, li += T) {
+            if (li < numel) {
+                const uint32_t v = (uint32_t)__umul64hi(mod_magic * (uint64_t)words[ii], (uint64_t)range) + 1u;   // words % range + 1
+                out32[li] = (int32_t)v;
+                atomicAdd(h0 + (v >> t0.shift), 1u);
+            }
+        }
+    }
+    bool bad = false;
+    for (int64_t i = i0; i < B; i += stride) {
+        const int64_t id = pos[i];
+        if (id > 0 && id < t0.num_rows) atomicAdd(h0 + (id >> t0.shift), 1u);
+        else if (id != 0) bad = true;
+    }
+    for (int64_t i = i0; i < B1; i += stride) {
+        const int64_t id = ids1[i];
+        if (id > 0 && id < t1.num_rows) atomicAdd(h1 + (id >> t1.shift), 1u);
+        else if (id != 0) bad = true;
+    }
+    if (bad) *err_flag = 1u;
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb0 + nb1; i += blockDim.x) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(i < nb0 ? t0.cnt + i : t1.cnt + (i - nb0), c);
+        }
+    }
+}
+
+__global__ void advance_philox_state_kernel(uint64_t* state, uint64_t inc) { state[1] += inc; }
+
+int32_t launch_draw_bin_count(uint64_t* state_dev, uint64_t seed, uint64_t philox_offset, int64_t num_queries, int64_t num_neg,
+                              int32_t sm_cnt, int32_t max_tpsm, int32_t* out32, const int64_t* pos, int64_t B, const BinTable& t0,
+                              const int64_t* ids1, int64_t B1, const BinTable& t1, uint32_t* err_flag, cudaStream_t st) {
+    RSB_CUDA(cudaMemsetAsync(t0.cnt, 0, sizeof(uint32_t) * (size_t)t0.nbins, st));
+    if (t1.nbins) RSB_CUDA(cudaMemsetAsync(t1.cnt, 0, sizeof(uint32_t) * (size_t)t1.nbins, st));
+    const int64_t numel = num_queries * num_neg;
+    // ATen's launch policy fixes the element <-> (thread, round, word) map (sampler.cu)
+    int64_t grid = (int64_t)sm_cnt * (max_tpsm / 256);
+    if (cdiv(numel, 256) < grid) grid = cdiv(numel, 256);
+    const int64_t T = 256 * (grid > 0 ? grid : 1);
+    const int64_t rounds = numel > 0 ? (numel - 1) / (T * 4) + 1 : 0;
+    const int use_smem = t0.nbins + t1.nbins <= 8192;
+    int64_t blocks = cdiv(T * rounds + B + B1, 256 * 4);
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const size_t smem = use_smem ? sizeof(uint32_t) * (size_t)(t0.nbins + t1.nbins) : 0;
+    const uint32_t range = (uint32_t)(t0.num_rows - 1);
+    const uint64_t magic = (~(uint64_t)0) / (uint64_t)range + 1;
+    draw_bin_count_kernel<<<(unsigned)blocks, 256, smem, st>>>(state_dev, seed, philox_offset / 4, T, rounds, numel, range, magic, out32,
+                                                               pos, B, t0, ids1, B1, t1, use_smem, err_flag);
+    RSB_LAUNCH_CHECK();
+    if (state_dev && rounds > 0) {
+        advance_philox_state_kernel<<<1, 1, 0, st>>>(state_dev, (uint64_t)(rounds * 4));
+        RSB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ BIN_SCAN
 // one CTA per table: exclusive scan of the bin counts -> off[nbins + 1]; arms the append cursors (cursor[b * stride] =
 // off[b]) and clears the look-back status words and the bin ticket for bin_scatter_kernel.

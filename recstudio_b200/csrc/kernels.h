@@ -94,6 +94,9 @@ template <typename IdT>
 int32_t launch_bin_count(const IdT* ids, int64_t M, const int64_t* pos, int64_t B, const BinTable& t0, const int64_t* ids1,
                          int64_t B1, const BinTable& t1, int32_t* ids32_out, uint32_t* err_flag, cudaStream_t st);
 int32_t launch_bin_scan(const BinTable& t0, const BinTable& t1, cudaStream_t st);
+int32_t launch_draw_bin_count(uint64_t* state_dev, uint64_t seed, uint64_t philox_offset, int64_t num_queries, int64_t num_neg,
+                              int32_t sm_cnt, int32_t max_tpsm, int32_t* out32, const int64_t* pos, int64_t B, const BinTable& t0,
+                              const int64_t* ids1, int64_t B1, const BinTable& t1, uint32_t* err_flag, cudaStream_t st);
 int32_t launch_bin_scatter(const BinScatterParams& p, cudaStream_t st);
 // group.cu
 int64_t scan_tmp_elems(int64_t num_rows);

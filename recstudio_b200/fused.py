@@ -111,8 +111,13 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
               dense_item_grad: Optional[torch.Tensor] = None, dense_user_grad: Optional[torch.Tensor] = None,
               variant: int = 0, grad_scale_dev: Optional[torch.Tensor] = None,
               item_vals: Optional[torch.Tensor] = None, user_vals: Optional[torch.Tensor] = None,
-              apply: Optional[dict] = None):
+              apply: Optional[dict] = None, draw: Optional[dict] = None):
     """Enqueue the selected phases of the fused step on the current stream.
+
+    ``draw`` (binned grouping only): fuse the UniformSampler draw into the step -- ``neg`` is then the int32 [B, n] OUTPUT
+    buffer, filled by rsb200_pair_draw_count with the ids ``torch.randint(1, num_items, (B, n), device=cuda)`` would return
+    for the generator state ``{'state_dev': int64[2] device tensor}`` (advanced on the device) or ``{'seed': s, 'offset': o}``,
+    and PHASE_COUNT (taken inside that kernel) is dropped from ``phases``.  The caller advances the torch generator.
 
     Returns the 0-dim loss tensor (a view of ``ws.loss``).  Gradients are left in
     ``ws.item_rows/item_vals`` and ``ws.user_rows/user_vals`` (first ``ws.totals[1]`` /
@@ -191,6 +196,15 @@ def pair_step(ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, use
     a.sink = _lib.SINK_APPLY if apply is not None else (SINK_DENSE if dense else SINK_COMPACT)
     a.accumulate, a.variant = int(bool(accumulate)), int(variant)
     with torch.cuda.device(w_item.device):
+        if draw is not None:
+            if not ws.grouping or neg.dtype != torch.int32:
+                raise _lib.Rsb200Error("draw= needs the binned grouping and an int32 [B, n] output buffer for the ids")
+            from . import sampling
+            sm, mt = sampling._policy(w_item.device)
+            st = draw.get("state_dev")
+            check(lib().rsb200_pair_draw_count(C.byref(a), ptr(st), int(draw.get("seed", 0)) & ((1 << 64) - 1), int(draw.get("offset", 0)),
+                                               sm, mt, ptr(neg), stream_ptr()), "pair_draw_count")
+            phases = int(phases) & ~_lib.PHASE_COUNT
         check(lib().rsb200_pair_step(C.byref(a), int(phases), stream_ptr()), "pair_step")
     # keep temporaries referenced by the async launch alive until the stream catches up
     ws._keepalive = (logq_pos, logq_neg, neg, user, pos, grad_scale_dev) + keep_states
@@ -240,6 +254,9 @@ class GraphedPairStep:
         sm, mt = sampling._policy(dev)
 
         def body():
+            if ws.grouping:        # draw + bin histogram in one kernel (rsb200_pair_draw_count)
+                pair_step(ws, w_item, w_user, self.user, self.pos, self.neg32, loss_kind, score_kind, draw={"state_dev": self.state})
+                return
             with torch.cuda.device(dev):
                 check(lib().rsb200_sample_uniform_dev(ptr(self.state), num_items, B, n, sm, mt, 0, ptr(self.neg32), stream_ptr()),
                       "sample_uniform_dev")

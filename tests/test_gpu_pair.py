@@ -492,3 +492,29 @@ def test_bins_apply_sink_matches_rows_update(kind, learner):
     else:
         assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     assert not torch.equal(res[0][0], wi)
+
+
+def test_fused_draw_and_count_host_state():
+    """rsb200_pair_draw_count with the generator state passed by value: same ids as torch.randint for that state, and the
+    step that follows (SCAN | FWD | SCATTER) equals the step fed with those ids."""
+    from recstudio_b200 import fused
+    dev = torch.device("cuda:0")
+    N, U, d, B, n = 7001, 101, 64, 40, 96
+    g = torch.Generator().manual_seed(12)
+    wi = (torch.randn(N, d, generator=g) * 0.3).to(dev); wi[0] = 0
+    wu = (torch.randn(U, d, generator=g) * 0.3).to(dev); wu[0] = 0
+    user = torch.randint(0, U, (B,), generator=g).to(dev); pos = torch.randint(0, N, (B,), generator=g).to(dev)
+    torch.manual_seed(31)
+    torch.rand(5, device=dev)
+    gen = torch.cuda.default_generators[0]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    want = torch.randint(1, N, (B, n), device=dev)
+    ws_a, ws_b = fused.PairWorkspace(N, U, B, n, d, dev), fused.PairWorkspace(N, U, B, n, d, dev)
+    neg32 = torch.zeros(B, n, dtype=torch.int32, device=dev)
+    la = fused.pair_step(ws_a, wi, wu, user, pos, neg32, R.SSM, R.IP, draw={"seed": seed, "offset": off}).item()
+    assert torch.equal(neg32.long(), want)
+    lb = fused.pair_step(ws_b, wi, wu, user, pos, want.int(), R.SSM, R.IP).item()
+    (ra, va), (rua, vua) = fused.sparse_grads(ws_a)
+    (rb, vb), (rub, vub) = fused.sparse_grads(ws_b)
+    assert la == lb and torch.equal(ra, rb) and torch.equal(va, vb) and torch.equal(rua, rub) and torch.equal(vua, vub)
+    assert ws_a.totals.tolist() == ws_b.totals.tolist()
