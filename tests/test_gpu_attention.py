@@ -197,12 +197,14 @@ def test_sasrec_rows_mode_steps_the_shared_table_with_head_and_encoder_gradients
     for mode in ("dense", "rows"):
         m = retriever.build_sasrec_synthetic(N, d, n, max_seq_len=Lq, fused_grad=mode, device=DEV, init_std=0.1, seed=3)
         m.config["train"].update({"learner": "sgd", "learning_rate": lr, "weight_decay": 0, "scheduler": None})
+        m.val_check = False                      # what fit() sets before it asks for the optimizers (recommender.py:129)
         models[mode] = m
     gen = torch.Generator(device=DEV).manual_seed(5)
     seqlen = torch.randint(1, Lq + 1, (B,), device=DEV, generator=gen)
     ids = torch.randint(1, N, (B, Lq), device=DEV, generator=gen) * (torch.arange(Lq, device=DEV)[None, :] < seqlen[:, None])
     batch = {"in_item_id": ids, "seqlen": seqlen, "item_id": torch.randint(1, N, (B,), device=DEV, generator=gen),
              "rating": torch.ones(B, device=DEV)}
+    models["rows"].load_state_dict(models["dense"].state_dict())      # biases are drawn from the CPU generator at construction
     before = models["dense"].item_encoder.weight.detach().clone()
     assert torch.equal(before, models["rows"].item_encoder.weight)
     for mode, m in models.items():

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--set", action="append", default=[], help="grouping:bin_shift:variant (bin_shift 0 = library default)")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--fused-draw", action="store_true", help="grouping 1: rsb200_pair_draw_count instead of draw + PHASE_COUNT")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(2022)
@@ -36,6 +37,7 @@ def main():
     pos = torch.randint(1, a.N, (a.B,), device=dev)
     settings = [tuple(int(x) for x in s.split(":")) for s in (a.set or ["0:0:0", "1:0:0"])]
     wss = [fused.PairWorkspace(a.N, a.U, a.B, a.n, a.d, dev, grouping=g, bin_shift=(sh or None)) for g, sh, _ in settings]
+    nbuf = torch.zeros(a.B, a.n, dtype=torch.int32, device=dev)
     names = ["sample", "count", "scan", "fwd", "scatter"]
     tot = [{k: 0.0 for k in names} for _ in settings]
     losses = [0.0] * len(settings)
@@ -44,10 +46,21 @@ def main():
         for k, ((g, sh, variant), ws) in enumerate(zip(settings, wss)):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             ev[0].record()
-            _, neg32 = sampling.uniform_draw(a.N, a.B, a.n, dev, want_i64=False, want_i32=True)
-            ev[1].record()
-            for i, ph in enumerate((P.PHASE_COUNT, P.PHASE_SCAN, P.PHASE_FWD, P.PHASE_SCATTER)):
-                loss = fused.pair_step(ws, wi, wu, user, pos, neg32, a.loss, a.score, phases=ph, variant=variant)
+            if a.fused_draw and g:           # draw + bin histogram in one kernel: reported under "sample", "count" = 0
+                gen = torch.cuda.default_generators[0]
+                neg32 = nbuf
+                fused.pair_step(ws, wi, wu, user, pos, neg32, a.loss, a.score, phases=0,
+                                draw={"seed": gen.initial_seed(), "offset": gen.get_offset()})
+                gen.set_offset(gen.get_offset() + sampling.counter_offset(a.B * a.n, dev))
+                ev[1].record()
+                phs = (0, P.PHASE_SCAN, P.PHASE_FWD, P.PHASE_SCATTER)
+            else:
+                _, neg32 = sampling.uniform_draw(a.N, a.B, a.n, dev, want_i64=False, want_i32=True)
+                ev[1].record()
+                phs = (P.PHASE_COUNT, P.PHASE_SCAN, P.PHASE_FWD, P.PHASE_SCATTER)
+            for i, ph in enumerate(phs):
+                if ph:
+                    loss = fused.pair_step(ws, wi, wu, user, pos, neg32, a.loss, a.score, phases=ph, variant=variant)
                 ev[2 + i].record()
             torch.cuda.synchronize()
             if it >= 3:
@@ -58,7 +71,7 @@ def main():
         ph = {nm: tot[k][nm] / a.steps for nm in names}
         step = sum(ph.values())
         t = ws.totals.tolist()
-        print(json.dumps({"tag": a.tag, "grouping": g, "bin_shift": ws.bin_shift, "variant": variant, "N": a.N, "B": a.B, "n": a.n,
+        print(json.dumps({"tag": a.tag, "fused_draw": bool(a.fused_draw and g), "grouping": g, "bin_shift": ws.bin_shift, "variant": variant, "N": a.N, "B": a.B, "n": a.n,
                           "d": a.d, "loss_kind": a.loss, "score_kind": a.score, "ms": {k2: round(v, 4) for k2, v in ph.items()},
                           "step_ms": round(step, 4), "interactions_per_s": a.B / (step / 1e3), "loss": losses[k],
                           "entries": t[0], "unique_rows": t[1]}), flush=True)
