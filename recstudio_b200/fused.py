@@ -230,58 +230,93 @@ def sparse_grads(ws: PairWorkspace):
 
 
 class GraphedPairStep:
-    """The whole fused step -- UniformSampler draw, COUNT, SCAN, FWD, SCATTER (17 launches) -- captured once in a CUDA
-    graph and replayed: the kernels between the two big streams are a few microseconds each, so launch gaps are ~5 % of
-    the step when they are issued one by one.  The draw reads the generator state from device memory
-    (rsb200_sample_uniform_dev), so every replay draws exactly what ``torch.randint(1, N, (B, n), device=cuda)`` would
-    return for the torch generator's current state, and the generator is advanced accordingly; if anything else consumed
-    the generator in between, the state is re-uploaded before the replay.  Gradients are left in ``ws`` as for
-    ``pair_step`` (compact sink)."""
+    """The whole fused step -- UniformSampler draw + bin histogram, SCAN, FWD, SCATTER -- captured once in a CUDA graph
+    and replayed: the kernels between the two big streams are a few microseconds each, so launch gaps are ~3 % of the
+    step when they are issued one by one.  The draw reads the generator state from device memory, so every replay draws
+    exactly what ``torch.randint(1, N, (B, n), device=cuda)`` would return for the torch generator's current state, and
+    the generator is advanced accordingly; if anything else consumed the generator in between, the state is re-uploaded
+    before the replay.  Gradients are left in ``ws`` as for ``pair_step`` (compact sink).
+
+    ``split=True`` captures TWO graphs, for an autograd hand-off: ``forward(user, pos)`` replays draw | COUNT | SCAN | FWD and
+    returns the loss, ``backward(grad_output)`` replays SCATTER scaled by the upstream gradient (read on the device).
+    ``FusedRetrieverMixin.training_step`` uses it when the retriever is built with ``fused_graph=True``."""
 
     def __init__(self, ws: PairWorkspace, w_item: torch.Tensor, w_user: torch.Tensor, loss_kind: int, score_kind: int,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, split: bool = False):
         from . import sampling
         num_items, num_users, B, n, d = ws.shape
         dev = ws.device
-        self.ws, self.dev, self.shape = ws, dev, (num_items, B, n)
+        self.ws, self.dev, self.shape, self.split = ws, dev, (num_items, B, n), split
+        self.key = (w_item.data_ptr(), w_user.data_ptr(), int(loss_kind), int(score_kind))
         self.gen = sampling._generator(dev, generator)
         self.inc = sampling.counter_offset(B * n, dev)
         self.user = torch.zeros(B, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(B, dtype=torch.int64, device=dev)
         self.neg32 = torch.empty(B, n, dtype=torch.int32, device=dev)
         self.state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.gscale = torch.ones(1, dtype=torch.float32, device=dev)
         self._tracked = None
         sm, mt = sampling._policy(dev)
+        if split and (ws.item_vals is None or ws.user_vals is None):
+            ws.item_vals = torch.empty(ws.cap_item, d, dtype=torch.float32, device=dev)
+            ws.user_vals = torch.empty(ws.cap_user, d, dtype=torch.float32, device=dev)
+        fwd_phases = _lib.PHASE_COUNT | _lib.PHASE_SCAN | _lib.PHASE_FWD
 
-        def body():
-            if ws.grouping:        # draw + bin histogram in one kernel (rsb200_pair_draw_count)
-                pair_step(ws, w_item, w_user, self.user, self.pos, self.neg32, loss_kind, score_kind, draw={"state_dev": self.state})
-                return
-            with torch.cuda.device(dev):
-                check(lib().rsb200_sample_uniform_dev(ptr(self.state), num_items, B, n, sm, mt, 0, ptr(self.neg32), stream_ptr()),
-                      "sample_uniform_dev")
-            pair_step(ws, w_item, w_user, self.user, self.pos, self.neg32, loss_kind, score_kind)
+        def body(phases):
+            if phases & _lib.PHASE_COUNT:
+                if ws.grouping:    # draw + bin histogram in one kernel (rsb200_pair_draw_count)
+                    pair_step(ws, w_item, w_user, self.user, self.pos, self.neg32, loss_kind, score_kind, phases=phases,
+                              draw={"state_dev": self.state}, grad_scale_dev=self.gscale if split else None)
+                    return
+                with torch.cuda.device(dev):
+                    check(lib().rsb200_sample_uniform_dev(ptr(self.state), num_items, B, n, sm, mt, 0, ptr(self.neg32), stream_ptr()),
+                          "sample_uniform_dev")
+            pair_step(ws, w_item, w_user, self.user, self.pos, self.neg32, loss_kind, score_kind, phases=phases,
+                      grad_scale_dev=self.gscale if split else None)
 
+        parts = [fwd_phases, _lib.PHASE_SCATTER] if split else [PHASE_ALL]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                 # warm-up outside the capture (lazy module loading, attributes)
-            body()
+            for ph in parts:
+                body(ph)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         l0 = lib().rsb200_launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        # thread_local: other threads (e.g. NCCL's watchdog polling events) must not invalidate the capture
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            body()
+        self.graphs = []
+        for ph in parts:
+            g = torch.cuda.CUDAGraph()
+            # thread_local: other threads (e.g. NCCL's watchdog polling events) must not invalidate the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                body(ph)
+            self.graphs.append(g)
+        self.graph = self.graphs[0]
         self.launches_per_step = int(lib().rsb200_launch_count() - l0)
+
+    def _sync_state(self):
+        seed, off = self.gen.initial_seed(), self.gen.get_offset()
+        if self._tracked != (seed, off):              # first call, or someone else used the generator: upload its state
+            self.state.copy_(torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, off], dtype=torch.int64))
+        self.gen.set_offset(off + self.inc)
+        self._tracked = (seed, off + self.inc)
 
     def __call__(self, user: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
         self.user.copy_(user, non_blocking=True)
         self.pos.copy_(pos, non_blocking=True)
-        seed, off = self.gen.initial_seed(), self.gen.get_offset()
-        if self._tracked != (seed, off):              # first call, or someone else used the generator: upload its state
-            self.state.copy_(torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, off], dtype=torch.int64))
-        self.graph.replay()
-        self.gen.set_offset(off + self.inc)
-        self._tracked = (seed, off + self.inc)
+        self._sync_state()
+        for g in self.graphs:
+            g.replay()
         return self.ws.loss[0]
+
+    def forward(self, user: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+        """split mode: draw | COUNT | SCAN | FWD; the loss is ``ws.loss[0]``"""
+        self.user.copy_(user, non_blocking=True)
+        self.pos.copy_(pos, non_blocking=True)
+        self._sync_state()
+        self.graphs[0].replay()
+        return self.ws.loss[0]
+
+    def backward(self, grad_output: torch.Tensor):
+        """split mode: SCATTER scaled by autograd's upstream gradient; rows in ``ws.item_rows / item_vals / user_rows / user_vals``"""
+        self.gscale.copy_(grad_output.reshape(1), non_blocking=True)
+        self.graphs[1].replay()

@@ -414,6 +414,26 @@ class _FusedStepFn(torch.autograd.Function):
         return gi, gu, None, None, None, None, None, None, None, None, None
 
 
+class _GraphedStepFn(torch.autograd.Function):
+    """``_FusedStepFn`` for ``fused_graph=True`` (two embedding towers, in-kernel UniformSampler draw, fused_grad='rows'):
+    forward and backward each replay ONE captured CUDA graph (fused.GraphedPairStep(split=True)), so a training step
+    issued through the reference's trainer loop (recommender.py:594-646) costs two graph launches instead of ~10 kernel
+    launches.  The gradient rows stay in the workspace for FusedRowOptimizer, exactly as in 'rows' mode."""
+
+    @staticmethod
+    def forward(ctx, w_item: Tensor, w_user: Tensor, host, step, user, pos):
+        loss = step.forward(user, pos)
+        ctx.host, ctx.step = host, step
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        step, ws = ctx.step, ctx.step.ws
+        step.backward(g.to(torch.float32))
+        ws.row_grads = (ws.item_rows, ws.item_vals, ws.user_rows, ws.user_vals, ws.totals)
+        return None, None, None, None, None, None
+
+
 class _FusedHeadFn(torch.autograd.Function):
     """The fused step for an arbitrary query encoder (SASRec, DSSM ...): the [B, d] encoder output is
     the query 'table' (row 0 = padding, query b at row b + 1), so the same kernels produce the loss,
@@ -676,6 +696,14 @@ class FusedRetrieverMixin:
                     raise _lib.Rsb200Error("fused sampling methods need a [B, d] query encoder output")
                 return super().training_step(batch)
             ws = self._fused_ws(B, n, B + 1)
+        if two_tables and in_kernel_draw and getattr(self, "fused_graph", False) and self.fused_grad == "rows" \
+                and type(self.sampler) is FusedUniformSampler:
+            gs = self.__dict__.get("_fused_graphed")
+            key = (wi.data_ptr(), wu.data_ptr(), int(loss_kind), int(score_kind))
+            if gs is None or gs.ws is not ws or gs.key != key:
+                gs = fused.GraphedPairStep(ws, wi.detach(), wu.detach(), loss_kind, score_kind, split=True)
+                self.__dict__["_fused_graphed"] = gs
+            return _GraphedStepFn.apply(wi, wu, self, gs, user, pos)
         if in_kernel_draw:
             if isinstance(self.sampler, FusedMaskedUniformSampler):
                 neg32, lqn = self.sampler.fused_draw(B, n, wi.device, user_hist=batch["user_hist"])
@@ -721,6 +749,9 @@ class FusedRetrieverMixin:
 
     def fused_last_neg_id(self):
         """int32 [B, n] negatives drawn by the last fused training_step (for inspection / parity tests)."""
+        gs = self.__dict__.get("_fused_graphed")
+        if gs is not None:
+            return gs.neg32
         cache = self.__dict__.get("_fused_ws_cache", {})
         for ws in cache.values():
             return ws._keepalive[2]

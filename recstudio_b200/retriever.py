@@ -22,12 +22,16 @@ class FusedRetriever(plugins.FusedRetrieverMixin, iface.BaseRetriever):
     sampler=, loss=`` -- any of them may be a reference plugin, the fused path engages when the
     combination is recognised."""
 
-    def __init__(self, config: Dict = None, fused_grad: str = "dense", device_loader: bool = False, **kwargs):
+    def __init__(self, config: Dict = None, fused_grad: str = "dense", device_loader: bool = False, fused_graph: bool = False,
+                 **kwargs):
         super().__init__(config, **kwargs)
         if fused_grad not in ("dense", "sparse", "rows", "apply"):
             raise ValueError("fused_grad must be 'dense', 'sparse', 'rows' or 'apply'")
         self.fused_grad = fused_grad
         self.device_loader = device_loader
+        # replay the fused step from two captured CUDA graphs (forward | backward) when the batch shape is stable:
+        # fused_grad='rows', two embedding towers, FusedUniformSampler (plugins._GraphedStepFn)
+        self.fused_graph = bool(fused_graph)
 
     def _get_train_loaders(self, train_data, ddp=False):
         """recommender.py:384-388.  With ``device_loader=True`` the interaction columns live on the GPU and
@@ -105,7 +109,7 @@ class FusedBPR(FusedRetriever):
 def build_synthetic(num_users: int, num_items: int, d: int, n, loss: str = "bpr", scorer: str = "ip",
                     sampler: str = "uniform", pop_count=None, fused_grad: str = "dense", device="cuda:0",
                     init_std: Optional[float] = None, seed: int = 2022, sampling_method: str = "none",
-                    excluding_hist: bool = False) -> FusedRetriever:
+                    excluding_hist: bool = False, fused_graph: bool = False) -> FusedRetriever:
     """A FusedRetriever over plain embedding towers without a dataset object (bench / tests):
     the kwargs construction of test/test_retriever.py with synthetic table sizes."""
     loss_m = plugins.FusedBPRLoss() if loss == "bpr" else plugins.FusedSampledSoftmaxLoss()
@@ -120,7 +124,7 @@ def build_synthetic(num_users: int, num_items: int, d: int, n, loss: str = "bpr"
     conf = get_model("BPR")[1]
     conf["train"].update({"negative_count": n, "gpu": None, "seed": seed, **extra})
     conf["model"]["embed_dim"] = d
-    m = FusedRetriever(conf, fused_grad=fused_grad, item_encoder=item, query_encoder=user, scorer=score_m,
+    m = FusedRetriever(conf, fused_grad=fused_grad, fused_graph=fused_graph, item_encoder=item, query_encoder=user, scorer=score_m,
                        sampler=samp_m, loss=loss_m)
     # what _init_model reads off the dataset object (recommender.py:66-77, baseretriever.py:54-68)
     m.fuid, m.fiid, m.frating = "user_id", "item_id", "rating"

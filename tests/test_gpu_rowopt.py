@@ -119,3 +119,31 @@ def test_row_optimizer_is_a_torch_optimizer_with_state_dict_and_scheduler():
     with pytest.raises(ValueError):
         m.config["train"]["learner"] = "rmsprop"
         m._get_optimizers()
+
+
+def test_graph_replay_behind_the_plugin_api():
+    """fused_graph=True: training_step + backward replay two captured CUDA graphs (draw | COUNT | SCAN | FWD and SCATTER).
+    Same negatives (the generator is advanced exactly like the eager path), same loss, bit-identical weights after
+    FusedRowOptimizer steps; a changed batch size re-captures."""
+    from recstudio_b200 import retriever, rowopt
+    U, N, d, B, n = 300, 4000, 128, 64, 96
+    models = [retriever.build_synthetic(U, N, d, n, loss="ssm", fused_grad="rows", fused_graph=g, device=DEV, init_std=0.2, seed=4)
+              for g in (False, True)]
+    opts = [rowopt.FusedRowOptimizer(m, "adagrad", lr=0.1) for m in models]
+    gen = torch.Generator().manual_seed(2)
+    for it, bsz in enumerate((B, B, B, 40, B)):
+        batch = {"user_id": torch.randint(1, U, (bsz,), generator=gen).to(DEV), "item_id": torch.randint(1, N, (bsz,), generator=gen).to(DEV),
+                 "rating": torch.ones(bsz, device=DEV)}
+        losses, negs, ends = [], [], []
+        for m, opt in zip(models, opts):
+            torch.manual_seed(50 + it)
+            opt.zero_grad()
+            loss = m.training_step(dict(batch))
+            assert type(loss.grad_fn).__name__.startswith("_GraphedStepFn" if m.fused_graph else "_FusedStepFn")
+            loss.backward()
+            opt.step()
+            losses.append(loss.item()); negs.append(m.fused_last_neg_id().clone()); ends.append(torch.rand(2, device=DEV))
+        assert torch.equal(negs[0], negs[1]) and torch.equal(ends[0], ends[1])
+        assert losses[0] == losses[1]
+        for name in ("item_encoder", "query_encoder"):
+            assert torch.equal(getattr(models[0], name).weight, getattr(models[1], name).weight), (it, name)
