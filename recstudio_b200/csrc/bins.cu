@@ -220,41 +220,44 @@ __global__ void __launch_bounds__(1024)
 bin_scan_kernel(const BinTable t0, const BinTable t1) {
     const BinTable& t = blockIdx.x == 0 ? t0 : t1;
     __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t s_carry;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nbins = t.nbins;
-    if (threadIdx.x == 0) s_carry = 0u;
-    __syncthreads();
-    for (int base = 0; base < nbins; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < nbins ? t.cnt[i] : 0u;
-        uint32_t inc = v;
+    const int per = (nbins + 1023) / 1024;                 // consecutive bins per thread: one pass, one block scan
+    const int b0 = threadIdx.x * per;
+    uint32_t local = 0;
+    for (int k = 0; k < per; ++k)
+        if (b0 + k < nbins) local += t.cnt[b0 + k];
+    uint32_t inc = local;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t x = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += x;
-        }
-        if (lane == 31) warp_tot[w] = inc;
-        __syncthreads();
-        uint32_t wbase = 0, tot = 0;
-        for (int k = 0; k < 32; ++k) {
-            const uint32_t x = warp_tot[k];
-            if (k < w) wbase += x;
-            tot += x;
-        }
-        const uint32_t ex = s_carry + wbase + inc - v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += x;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    uint32_t wv = warp_tot[lane];                          // 32 warps: scan their totals with one more warp scan
+    uint32_t winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(kFull, winc, o);
+        if (lane >= o) winc += x;
+    }
+    const uint32_t wbase = __shfl_sync(kFull, winc - wv, w);
+    const uint32_t total = __shfl_sync(kFull, winc, 31);
+    uint32_t ex = wbase + inc - local;
+    for (int k = 0; k < per; ++k) {
+        const int i = b0 + k;
         if (i < nbins) {
+            const uint32_t c = t.cnt[i];
             t.off[i] = ex;
             t.cursor[(size_t)i * kCursorStride] = ex;
             t.status[i] = 0ull;
+            ex += c;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry += tot;
-        __syncthreads();
     }
     if (threadIdx.x == 0) {
-        t.off[nbins] = s_carry;
-        t.totals[0] = s_carry;
+        t.off[nbins] = total;
+        t.totals[0] = total;
         t.ticket[0] = 0u;
     }
 }
