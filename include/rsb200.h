@@ -355,16 +355,20 @@ int32_t rsb200_fullsoftmax_fwd_bwd(const float* q /* [B,d] */, const float* w_it
  * hist: int64 [B, L] item ids (0 = padding key) or NULL; lse: [B, heads, L] or NULL.
  * Limits: head_dim == 64, L <= 256.  err_flag[0] is set if a tensor-core barrier timed out.
  * bf16 operands: results match an fp32 evaluation to ~1e-2 relative (not the 1e-5 of the fp32 paths).
+ * p_drop / drop_key: attention-probability dropout (nn.MultiheadAttention(dropout=p): out = (softmax(.) o M / (1 - p)) V with
+ * M ~ Bernoulli(1 - p)).  M is a counter-based hash of (drop_key, sequence, head, query, key): stateless, so rsb200_attn_bwd
+ * regenerates it from the same drop_key; p_drop = 0 disables it.  (The mask is NOT torch's Philox mask: dropout is random
+ * by definition; tests rebuild this hash on the host to check the arithmetic against a torch evaluation with the same mask.)
  */
 int32_t rsb200_attn_fwd(const float* q, const float* k, const float* v, const int64_t* hist, int64_t B, int64_t L,
-                        int64_t heads, int64_t head_dim, int32_t causal, float* out, float* lse, uint32_t* err_flag,
-                        void* stream);
+                        int64_t heads, int64_t head_dim, int32_t causal, float p_drop, uint64_t drop_key, float* out, float* lse,
+                        uint32_t* err_flag, void* stream);
 /* backward of rsb200_attn_fwd: o / lse are its outputs, d_o the upstream gradient [B, L, heads*head_dim];
- * writes dq, dk, dv (same layout, overwritten).  dV = P^T dO, dS = P o (dO V^T - rowsum(dO o O)) / sqrt(dh),
- * dQ = dS K, dK = dS^T Q, all five contractions on tcgen05. */
+ * writes dq, dk, dv (same layout, overwritten).  dV = P~^T dO, dS = P o (dP - rowsum(dO o O)) / sqrt(dh) with
+ * P~ = P o M / (1 - p), dP = (dO V^T) o M / (1 - p);  dQ = dS K, dK = dS^T Q, all five contractions on tcgen05. */
 int32_t rsb200_attn_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o, const float* lse,
                         const int64_t* hist, int64_t B, int64_t L, int64_t heads, int64_t head_dim, int32_t causal,
-                        float* dq, float* dk, float* dv, uint32_t* err_flag, void* stream);
+                        float p_drop, uint64_t drop_key, float* dq, float* dk, float* dv, uint32_t* err_flag, void* stream);
 /* validation hook for the tcgen05 plumbing: D[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T, fp32 accumulate */
 int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D, int64_t N, int64_t K, uint32_t* err_flag, void* stream);
 

@@ -134,8 +134,8 @@ def lib():
             "rsb200_gather_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_scatter_add_rows": [v, i64, i64, v, i64, v, v],
             "rsb200_rows_update": [i32, v, v, v, i64, i64, v, v, v, i64, i64, f32, f32, f32, f32, v],
-            "rsb200_attn_fwd": [v, v, v, v, i64, i64, i64, i64, i32, v, v, v, v],
-            "rsb200_attn_bwd": [v, v, v, v, v, v, v, i64, i64, i64, i64, i32, v, v, v, v, v],
+            "rsb200_attn_fwd": [v, v, v, v, i64, i64, i64, i64, i32, f32, u64, v, v, v, v],
+            "rsb200_attn_bwd": [v, v, v, v, v, v, v, i64, i64, i64, i64, i32, f32, u64, v, v, v, v, v],
             "rsb200_tc_gemm_test": [v, v, v, i64, i64, v, v],
             "rsb200_rows_coalesce": [v, v, i64, i64, i64, i32, v, v, i32, i32, v, v, v, v, v, i64, v, i64, v, v],
             "rsb200_score_ids": [i32, v, v, i64, i64, v, i64, i64, v, v],

@@ -132,9 +132,28 @@ __device__ __forceinline__ void stage_transposed(unsigned char* dst, const float
 constexpr int kNW = 4;
 constexpr int kNT = 128 * kNW;
 
+// Attention-probability dropout (nn.MultiheadAttention(dropout=p), sasrec.py:19-32 / seq/config/sasrec.yaml:5): the keep mask
+// of element (sequence-head bh, query i, key j) is a counter-based hash of (key, bh, i, j) -- no state, so the forward
+// kernel and BOTH roles of the backward kernel regenerate the very same mask from the 64-bit key (drawn from torch's CUDA
+// generator by the host).  lowbias32 (two xorshift-multiply rounds, full avalanche) twice: ~14 integer ops per element.
+struct DropSpec {
+    uint32_t key_lo, key_hi;
+    uint32_t thresh;        // drop iff hash < thresh;  thresh = round(p * 2^32), 0 = no dropout
+    float keep_scale;       // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ bool drop_keep(const DropSpec& ds, uint32_t bh, int qi, int kj) {
+    uint32_t x = lowbias32(((uint32_t)qi << 8 | (uint32_t)kj) ^ ds.key_lo);      // qi, kj < 256
+    x = lowbias32(x ^ (bh * 0x9E3779B1u) ^ ds.key_hi);
+    return x >= ds.thresh;
+}
+
 __global__ void __launch_bounds__(kNT, 1)
 attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                const int64_t* __restrict__ hist, int L, int heads, int causal, float scale,
+                const int64_t* __restrict__ hist, int L, int heads, int causal, float scale, const DropSpec drop,
                 float* __restrict__ out, float* __restrict__ lse_out, uint32_t* __restrict__ err) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sQ = smem_raw;                                  // 2 x [128 x 64] bf16 (one block per M tile)
@@ -219,6 +238,9 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
                     const float p = (ok && mx != -INFINITY) ? __expf(s[g8 * 8 + x] * scale - mx) : 0.f;
                     pk[x] = __float2bfloat16(p);
                     l += __bfloat162float(pk[x]);            // normalise by what the tensor core will actually sum
+                    // dropout acts on the NORMALISED probabilities: the denominator keeps every element, the P V product
+                    // only the kept ones (scaled by 1 / (1 - p) together with 1 / l below)
+                    if (drop.thresh && !drop_keep(drop, (uint32_t)blockIdx.x, gi, j)) pk[x] = __float2bfloat16(0.f);
                 }
                 *reinterpret_cast<uint4*>(sP + kmajor_off(row, c0 + g8 * 8, 128)) = *reinterpret_cast<const uint4*>(pk);
             }
@@ -242,7 +264,7 @@ attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
         for (int w = 0; w < kNW; ++w) l += s_sum[w][row];
         if (!mbar_wait(&bar_o, mt & 1)) failed = true;
         fence_after_sync();
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        const float inv = l > 0.f ? drop.keep_scale / l : 0.f;
         {
             float o[16];
             tmem_ld16(tO + lane_base + cq * OW, o);
@@ -282,7 +304,7 @@ template <bool KEYSIDE>
 __global__ void __launch_bounds__(kNT, 1)
 attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                 const float* __restrict__ o, const float* __restrict__ d_o, const float* __restrict__ lse,
-                const int64_t* __restrict__ hist, int L, int heads, int causal, float scale,
+                const int64_t* __restrict__ hist, int L, int heads, int causal, float scale, const DropSpec drop,
                 float* __restrict__ out_ds /* dQ | dK */, float* __restrict__ out_p /* - | dV */, uint32_t* __restrict__ err) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* sX = smem_raw;                                  // [128 x 64] rows operand of S
@@ -379,7 +401,11 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
                         float pv = 0.f, dsv = 0.f;
                         if (ok) {
                             pv = __expf(s[g8 * 8 + x] * scale - s_lse[qi]);
-                            dsv = pv * (dp[g8 * 8 + x] - s_D[qi]) * scale;
+                            // dropout: O = (P o M / (1 - p)) V  =>  dP = (dO V^T) o M / (1 - p), dV = (P o M / (1 - p))^T dO,
+                            // and D_i = sum_j P_ij dP_ij = dO_i . O_i is unchanged (O is the dropped output)
+                            const float m = (!drop.thresh || drop_keep(drop, (uint32_t)blockIdx.x, qi, kj)) ? drop.keep_scale : 0.f;
+                            dsv = pv * (dp[g8 * 8 + x] * m - s_D[qi]) * scale;
+                            pv *= m;
                         }
                         pk[x] = __float2bfloat16(pv); dk[x] = __float2bfloat16(dsv);
                     }
@@ -440,10 +466,21 @@ attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const 
 
 using namespace rsb;
 
+static int32_t make_drop(float p_drop, uint64_t drop_key, DropSpec* ds) {
+    RSB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, RSB200_EINVAL, "attention dropout probability must be in [0, 1), got %g", (double)p_drop);
+    ds->key_lo = (uint32_t)drop_key; ds->key_hi = (uint32_t)(drop_key >> 32);
+    const double t = (double)p_drop * 4294967296.0;
+    ds->thresh = p_drop > 0.f ? (uint32_t)(t < 1.0 ? 1.0 : (t > 4294967295.0 ? 4294967295.0 : t)) : 0u;
+    ds->keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+    return 0;
+}
+
 extern "C" int32_t rsb200_attn_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
                                    const float* lse, const int64_t* hist, int64_t B, int64_t L, int64_t heads,
-                                   int64_t head_dim, int32_t causal, float* dq, float* dk, float* dv, uint32_t* err_flag,
-                                   void* stream) {
+                                   int64_t head_dim, int32_t causal, float p_drop, uint64_t drop_key, float* dq, float* dk, float* dv,
+                                   uint32_t* err_flag, void* stream) {
+    DropSpec drop;
+    { int32_t rc = make_drop(p_drop, drop_key, &drop); if (rc) return rc; }
     RSB_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv && err_flag, RSB200_EINVAL, "null pointer");
     RSB_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) &&
                 aligned16(dk) && aligned16(dv), RSB200_EINVAL, "pointers must be 16-byte aligned");
@@ -454,9 +491,9 @@ extern "C" int32_t rsb200_attn_bwd(const float* q, const float* k, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     RSB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
     RSB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    attn_bwd_kernel<false><<<(unsigned)(B * heads), kNT, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dq, nullptr, err_flag);
+    attn_bwd_kernel<false><<<(unsigned)(B * heads), kNT, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, drop, dq, nullptr, err_flag);
     RSB_LAUNCH_CHECK();
-    attn_bwd_kernel<true><<<(unsigned)(B * heads), kNT, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, dk, dv, err_flag);
+    attn_bwd_kernel<true><<<(unsigned)(B * heads), kNT, kBwdSmem, st>>>(q, k, v, o, d_o, lse, hist, (int)L, (int)heads, causal, scale, drop, dk, dv, err_flag);
     RSB_LAUNCH_CHECK();
     return 0;
 }
@@ -473,8 +510,10 @@ extern "C" int32_t rsb200_tc_gemm_test(const float* A, const float* B, float* D,
 }
 
 extern "C" int32_t rsb200_attn_fwd(const float* q, const float* k, const float* v, const int64_t* hist, int64_t B, int64_t L,
-                                   int64_t heads, int64_t head_dim, int32_t causal, float* out, float* lse,
-                                   uint32_t* err_flag, void* stream) {
+                                   int64_t heads, int64_t head_dim, int32_t causal, float p_drop, uint64_t drop_key, float* out,
+                                   float* lse, uint32_t* err_flag, void* stream) {
+    DropSpec drop;
+    { int32_t rc = make_drop(p_drop, drop_key, &drop); if (rc) return rc; }
     RSB_REQUIRE(q && k && v && out && err_flag, RSB200_EINVAL, "null pointer");
     RSB_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), RSB200_EINVAL, "pointers must be 16-byte aligned");
     RSB_REQUIRE(head_dim == kDH, RSB200_EUNSUPPORTED, "attention kernel is built for head_dim = 64 (got %lld)", (long long)head_dim);
@@ -482,7 +521,7 @@ extern "C" int32_t rsb200_attn_fwd(const float* q, const float* k, const float* 
     RSB_REQUIRE(B >= 1 && heads >= 1 && B * heads < ((int64_t)1 << 31), RSB200_EINVAL, "bad shape");
     RSB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     attn_fwd_kernel<<<(unsigned)(B * heads), kNT, kAttnSmem, (cudaStream_t)stream>>>(
-        q, k, v, hist, (int)L, (int)heads, causal, 1.0f / sqrtf((float)head_dim), out, lse, err_flag);
+        q, k, v, hist, (int)L, (int)heads, causal, 1.0f / sqrtf((float)head_dim), drop, out, lse, err_flag);
     RSB_LAUNCH_CHECK();
     return 0;
 }

@@ -59,7 +59,7 @@ def test_attention_forward(Lq, causal):
     out = torch.full((B, Lq, d), float("nan"), device=DEV)
     lse = torch.empty(B, heads, Lq, device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
-    L.check(L.lib().rsb200_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(hist), B, Lq, heads, dh, causal, L.ptr(out),
+    L.check(L.lib().rsb200_attn_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(hist), B, Lq, heads, dh, causal, 0.0, 0, L.ptr(out),
                                     L.ptr(lse), L.ptr(err), L.stream_ptr()), "attn_fwd")
     torch.cuda.synchronize()
     assert int(err.item()) == 0
@@ -100,6 +100,74 @@ def test_attention_backward(Lq, causal):
         scale = ref.abs().max().item()
         err = (got - ref).abs().max().item()
         assert err <= 3e-2 * scale, (name, err, scale)
+
+
+@pytest.mark.parametrize("Lq,causal,p", [(200, 1, 0.5), (96, 0, 0.2), (256, 1, 0.5)])
+def test_attention_dropout_inside_the_kernel(Lq, causal, p):
+    """Attention-probability dropout (the reference's default: dropout_rate 0.5, seq/config/sasrec.yaml:5) runs in the
+    tcgen05 kernels.  The keep mask is a stateless hash; rebuilt on the host (attention.dropout_keep_mask) it gives a torch
+    evaluation with the SAME mask: out = (softmax(.) o M / (1 - p)) V, and dq / dk / dv through autograd."""
+    from recstudio_b200 import attention
+    B, heads, dh = 3, 2, 64
+    d = heads * dh
+    gen = torch.Generator(device=DEV).manual_seed(7 + Lq)
+    rb = lambda t: t.bfloat16().float()
+    q, k, v = (rb(torch.randn(B, Lq, d, device=DEV, generator=gen)) for _ in range(3))
+    seqlen = torch.randint(Lq // 2, Lq + 1, (B,), device=DEV, generator=gen)
+    hist = (torch.arange(Lq, device=DEV)[None, :] < seqlen[:, None]).long() * 3
+    go = rb(torch.randn(B, Lq, d, device=DEV, generator=gen))
+    valid_rows = (torch.arange(Lq, device=DEV)[None, :] < seqlen[:, None]) if not causal else torch.ones(B, Lq, dtype=torch.bool, device=DEV)
+    go = go * valid_rows[..., None]
+    key = 0x1234_5678_9ABC_DEF1
+    keep = attention.dropout_keep_mask(key, p, B, heads, Lq, DEV)
+    rate = keep.float().mean().item()
+    assert abs(rate - (1 - p)) < 0.01, rate                                  # ~1e5 .. 4e5 Bernoulli draws
+    assert abs(keep[0].float().mean().item() - keep[-1].float().mean().item()) < 0.02 and not torch.equal(keep[0], keep[1])
+    qf, kf, vf = (t.clone().requires_grad_(True) for t in (q, k, v))
+    out = attention.fused_attention(qf, kf, vf, hist, heads, bool(causal), p_drop=p, drop_key=key)
+    out.backward(go)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    qh, kh, vh = (t.reshape(B, Lq, heads, dh).transpose(1, 2) for t in (qr, kr, vr))
+    sc = (qh @ kh.transpose(-1, -2)) / dh ** 0.5
+    mask = torch.zeros(B, 1, Lq, Lq, dtype=torch.bool, device=DEV)
+    if causal:
+        mask |= torch.triu(torch.ones(Lq, Lq, dtype=torch.bool, device=DEV), 1)
+    mask |= (hist == 0)[:, None, None, :]
+    pr = torch.softmax(sc.masked_fill(mask, float("-inf")), -1)
+    pr = torch.nan_to_num(pr) * keep.float() / (1 - p)                       # F.dropout semantics on the probabilities
+    want = (pr @ vh).transpose(1, 2).reshape(B, Lq, d)
+    want.backward(go)
+    scale = want.abs().max().item()
+    assert (out - want.detach()).abs().max().item() <= 3e-2 * scale
+    for got, ref, name in ((qf.grad, qr.grad, "dq"), (kf.grad, kr.grad, "dk"), (vf.grad, vr.grad, "dv")):
+        ref = torch.nan_to_num(ref)
+        assert (got - ref).abs().max().item() <= 3e-2 * ref.abs().max().item(), name
+    # p = 0 is the plain kernel; a fresh key per call comes from torch's generator (same seed => same masks)
+    torch.manual_seed(5)
+    a1 = attention.fused_attention(q, k, v, hist, heads, bool(causal), p_drop=p)
+    a2 = attention.fused_attention(q, k, v, hist, heads, bool(causal), p_drop=p)
+    torch.manual_seed(5)
+    b1 = attention.fused_attention(q, k, v, hist, heads, bool(causal), p_drop=p)
+    assert torch.equal(a1, b1) and not torch.equal(a1, a2)
+
+
+def test_sasrec_stock_dropout_config_takes_the_fused_path():
+    """dropout 0.5 in training mode no longer falls back to nn.TransformerEncoder (VERDICT r1 missing-3)."""
+    from recstudio_b200 import attention, plugins
+    item = plugins.FusedEmbedding(501, 128, padding_idx=0).to(DEV)
+    enc = attention.FusedSASRecQueryEncoder(fiid="item_id", embed_dim=128, max_seq_len=50, n_head=2, hidden_size=128, dropout=0.5,
+                                            activation="gelu", layer_norm_eps=1e-12, n_layer=2, item_encoder=item).to(DEV)
+    enc.train()
+    assert enc._use_fused(50, torch.device(DEV))
+    ids = torch.randint(1, 501, (4, 50), device=DEV)
+    out = enc({"in_item_id": ids, "seqlen": torch.full((4,), 50, device=DEV)})
+    out.sum().backward()
+    assert out.shape == (4, 128) and torch.isfinite(out).all()
+    assert torch.isfinite(enc.transformer_layer.layers[0].self_attn.in_proj_weight.grad).all()
+    enc.eval()
+    with torch.no_grad():
+        e1, e2 = enc({"in_item_id": ids, "seqlen": torch.full((4,), 50, device=DEV)}), enc({"in_item_id": ids, "seqlen": torch.full((4,), 50, device=DEV)})
+    assert torch.equal(e1, e2)                                               # no dropout in eval
 
 
 @pytest.mark.parametrize("bidirectional", [False, True])
