@@ -221,7 +221,7 @@ class OwnerComputeCuda:
 
     def __init__(self, num_items: int, row0: int, local_rows: int, weight: torch.Tensor, world: int, rank: int,
                  G: int, n: int, with_logq: bool = False, grouping: Optional[int] = None, bin_shift: Optional[int] = None,
-                 expected_touches: Optional[int] = None):
+                 expected_touches: Optional[int] = None, slots: int = 1):
         import os
         _lib.require_cuda()
         dev, d = weight.device, weight.shape[1]
@@ -239,15 +239,21 @@ class OwnerComputeCuda:
             grouping = 0
         self.grouping, self.bin_shift = int(grouping), (int(bin_shift) if grouping else 0)
         self.cap = max(1, min(G * (n + 1), local_rows))
-        self.neg_c = E(max(G * n, 1), dtype=i32)
-        self.lq_c = E(max(G * n, 1)) if with_logq else None
-        self.ncount, self.pos_local = E(max(G, 1), dtype=i32), E(max(G, 1), dtype=i32)
+        # ``slots`` > 1: ping-pong copies of what PREP_NEG produces (compacted negatives, their log Q, per-query counts, the
+        # bin histogram), so that the negatives of step k + 1 can be prepared on a side stream while step k is still running
+        self.slots = int(slots)
+        self._neg_c = [E(max(G * n, 1), dtype=i32) for _ in range(self.slots)]
+        self._lq_c = [E(max(G * n, 1)) if with_logq else None for _ in range(self.slots)]
+        self._ncount = [E(max(G, 1), dtype=i32) for _ in range(self.slots)]
+        self.neg_c, self.lq_c, self.ncount = self._neg_c[0], self._lq_c[0], self._ncount[0]
+        self.pos_local = E(max(G, 1), dtype=i32)
         self.ent = E(max(G * (n + 1), 1), dtype=i64)
         self.loss_part, self.lse = E(max(G, 1)), E(max(G, 1))
         if self.grouping:
             nb = -(-max(local_rows, 1) // (1 << self.bin_shift))
             self.nbins = nb
-            self.bin_cnt, self.bin_off, self.bin_cursor = E(nb, dtype=i32), E(nb + 1, dtype=i32), E(nb * 8, dtype=i32)
+            self._bin_cnt = [E(nb, dtype=i32) for _ in range(self.slots)]
+            self.bin_cnt, self.bin_off, self.bin_cursor = self._bin_cnt[0], E(nb + 1, dtype=i32), E(nb * 8, dtype=i32)
             self.bin_status, self.bin_ticket = E(nb, dtype=i64), torch.zeros(1, dtype=i32, device=dev)
             self.bin_heavy = E(int(L.rsb200_bin_heavy_elems()), dtype=i32)
             self.slot_neg = self.slot_pos = self.off = self.urow = self.scan_tmp = None
@@ -267,7 +273,7 @@ class OwnerComputeCuda:
         self._sum_lqp = False
 
     def bind(self, q_all, pos_all, neg_all, loss_kind, score_kind, logq_pos=None, logq_neg=None, grad_scale: float = 1.0,
-             regen_state: Optional[torch.Tensor] = None, pop: Optional["PopularSlice"] = None):
+             regen_state: Optional[torch.Tensor] = None, pop: Optional["PopularSlice"] = None, slot: int = 0):
         """``neg_all`` [G, n] int32 GLOBAL ids -- or ``None`` with ``regen_state`` [world, 2] int64 (seed, philox offset of
         every rank's CUDA generator): the owner then recomputes every rank's draw itself (nothing id-sized crosses NVLink):
         ``torch.randint(1, N, (B, n))`` (UniformSampler), or with ``pop`` (this owner's ``PopularSlice``)
@@ -286,6 +292,9 @@ class OwnerComputeCuda:
         self._keep = [t.contiguous() if t is not None else None for t in (q_all, pos_all, neg_all, logq_pos, logq_neg, regen_state)]
         q_all, pos_all, neg_all, logq_pos, logq_neg, regen_state = self._keep
         self._pop = pop
+        self.neg_c, self.lq_c, self.ncount = self._neg_c[slot], self._lq_c[slot], self._ncount[slot]
+        if self.grouping:
+            self.bin_cnt = self._bin_cnt[slot]
         a = _lib.ShardArgs()
         P = _lib.ptr
         a.w_local, a.q_all, a.pos, a.neg = P(self.weight), P(q_all), P(pos_all), (P(neg_all) if neg_all is not None else None)
@@ -323,16 +332,23 @@ class OwnerComputeCuda:
             a.bin_status, a.bin_ticket, a.bin_heavy = P(self.bin_status), P(self.bin_ticket), P(self.bin_heavy)
         self._args = a
 
-    def _run(self, phases: int, what: str):
+    def _run(self, phases: int, what: str, args=None):
         with torch.cuda.device(self.weight.device):
-            _lib.check(_lib.lib().rsb200_shard_step(C.byref(self._args), phases, _lib.stream_ptr()), what)
+            _lib.check(_lib.lib().rsb200_shard_step(C.byref(args if args is not None else self._args), phases, _lib.stream_ptr()), what)
+
+    def take_args(self):
+        """the argument block of the last ``bind`` (detached: a later ``bind`` does not change it).  With ``slots`` > 1 this is
+        how the negatives of the NEXT step are prepared ahead: ``bind(..., slot=s)``, ``a = take_args()``, and later
+        ``prep_neg(a)`` on a side stream while the current step runs on the buffers of the other slot."""
+        a, self._args = self._args, None
+        return a, list(self._keep)
 
     def prep(self) -> torch.Tensor:            # -> sp[G] (or [2, G] with log Q(pos))   (all-reduce SUM next)
         self._run(_lib.SHARD_PREP, "shard_step(PREP)")
         return self.sp2[:, :self.G] if self._sum_lqp else self.sp[:self.G]
 
-    def prep_neg(self):                        # the half of PREP that does not need q_all / pos: may overlap their all-gather
-        self._run(_lib.SHARD_PREP_NEG, "shard_step(PREP_NEG)")
+    def prep_neg(self, args=None):             # the half of PREP that does not need q_all / pos: may overlap their all-gather
+        self._run(_lib.SHARD_PREP_NEG, "shard_step(PREP_NEG)", args)
 
     def prep_pos(self) -> torch.Tensor:        # the other half (+ the bin scan); same return value as prep()
         self._run(_lib.SHARD_PREP_POS, "shard_step(PREP_POS)")
