@@ -28,7 +28,7 @@ case "$task" in
     echo "rc=$?"; tail -2 gpurun_out/${tag}_launches.log | cut -c1-300 ;;
   ncu)
     tag=$1; kern=$2; shift 2
-    timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$kern" -s 3 -c 1 -f -o gpurun_out/${tag} \
+    timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$kern" -s ${RSB_SKIP:-3} -c 1 -f -o gpurun_out/${tag} \
         python bench.py --no-cpu --steps 3 --warmup 3 "$@" > gpurun_out/${tag}_ncu.log 2>&1
     echo "rc=$?"; tail -2 gpurun_out/${tag}_ncu.log | cut -c1-300
     ncu -i gpurun_out/${tag}.ncu-rep --page details > gpurun_out/${tag}_details.txt 2>/dev/null
