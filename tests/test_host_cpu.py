@@ -238,3 +238,16 @@ def test_every_declared_function_has_a_typed_binding(L):
         assert fn.argtypes is not None or n_params == 0, "no argtypes for %s" % name
         if fn.argtypes is not None:
             assert len(fn.argtypes) == n_params, "%s: binding has %d arguments, header declares %d" % (name, len(fn.argtypes), n_params)
+
+
+def test_popular_slice_tables_match_reference_golden():
+    """sharded.PopularSlice.tables (what every rank builds on the CPU before slicing) == PopularSamplerModel's buffers as the
+    unmodified reference produced them (tests/golden/popular.npz, sampler.py:225-241)."""
+    from conftest import load_golden
+    from recstudio_b200 import sharded
+    g = load_golden("popular")
+    for tag in ("small", "big"):
+        for mode in (0, 1, 2):
+            table, prob = sharded.PopularSlice.tables(g[f"{tag}_count"], mode)
+            np.testing.assert_array_equal(prob.numpy(), g[f"{tag}_m{mode}_prob"])
+            np.testing.assert_array_equal(table.numpy(), g[f"{tag}_m{mode}_table"])
