@@ -26,10 +26,6 @@
 
 namespace rsb {
 
-constexpr int kBsThreads = 256;
-constexpr int kBsWarps = kBsThreads / 32;
-constexpr int kEcap = 4096;                      // entries of one chunk held in shared memory
-constexpr int kMaxBinRows = 1 << kMaxBinShift;   // 4096
 constexpr uint64_t kStAgg = 1ull << 62;          // status word: own unique-row count published
 constexpr uint64_t kStPre = 2ull << 62;          // status word: inclusive prefix published
 constexpr uint32_t kLast = 0x8000u;              // idx flag: last entry of its row
@@ -269,24 +265,31 @@ int32_t launch_bin_scan(const BinTable& t0, const BinTable& t1, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------ BIN_SCATTER
-struct BinSmem {
-    unsigned long long stash[kEcap];   // 32 KB  entries of the current row range, arrival order
-    uint32_t cur[kMaxBinRows];         // 16 KB  row histogram -> exclusive starts -> (after placement) row ends
-    uint16_t urank[kMaxBinRows];       //  8 KB  rank of a row among the bin's touched rows
-    uint16_t idx[kEcap];               //  8 KB  row-sorted position -> stash index | kLast
-    uint16_t scratch[kEcap];           //  8 KB  permutation buffer of the long-segment sort
-    uint32_t warp_tot[kBsWarps];
-    uint32_t long_rows[192];           // rows with more than kShortSeg entries in the current range (<= kEcap / kShortSeg)
+// Two shapes of the kernel: A = 256 threads, chunks of 4096 entries, bins of up to 4096 rows (72 KB of shared memory, 3 CTAs/SM);
+// B = 128 threads, chunks of 2048 entries, bins of up to 1024 rows (31 KB, 6 CTAs/SM): twice as many independent CTAs per SM,
+// so that the barrier-separated grouping phases of one bin overlap the accumulation phases of five others.
+struct BsCfgA { static constexpr int kThreads = 256, kWarps = 8, kEcap = 4096, kMaxRows = 4096; };
+struct BsCfgB { static constexpr int kThreads = 128, kWarps = 4, kEcap = 2048, kMaxRows = 1024; };
+constexpr uint32_t kShortSeg = 24;
+
+template <class CF>
+struct BinSmemT {
+    unsigned long long stash[CF::kEcap];   // entries of the current row range, arrival order          (A: 32 KB)
+    uint32_t cur[CF::kMaxRows];            // row histogram -> exclusive starts -> (after placement) row ends  (16 KB)
+    uint16_t urank[CF::kMaxRows];          // rank of a row among the bin's touched rows               ( 8 KB)
+    uint16_t idx[CF::kEcap];               // row-sorted position -> stash index | kLast               ( 8 KB)
+    uint16_t scratch[CF::kEcap];           // permutation buffer of the long-segment sort              ( 8 KB)
+    uint32_t warp_tot[CF::kWarps];
+    uint32_t long_rows[CF::kEcap / kShortSeg + 8];   // rows with more than kShortSeg entries in the current range
     uint32_t bin, base, uniq, nst, nlong, ra, rb, giant;
 };
-constexpr uint32_t kShortSeg = 24;
 
 // exclusive scan over the R rows of sm.cur, packed as (count | touched << 16): cur[r] <- start offset of row r,
 // urank[r] <- number of touched rows before r (RANK).  Returns the packed total.  Counts must sum to < 65536.
-template <bool RANK>
-__device__ __forceinline__ uint32_t scan_rows(BinSmem& sm, int R) {
+template <class CF, bool RANK>
+__device__ __forceinline__ uint32_t scan_rows(BinSmemT<CF>& sm, int R) {
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int rpt = R >= kBsThreads ? R / kBsThreads : 1;      // rows per thread: 1, 2, 4, 8 or 16 (R is a power of two)
+    const int rpt = R >= CF::kThreads ? R / CF::kThreads : 1;      // rows per thread: 1, 2, 4, 8 or 16 (R is a power of two)
     const int r0 = t * rpt;
     uint32_t c[16];                                            // fully unrolled below: stays in registers
 #pragma unroll
@@ -313,7 +316,7 @@ __device__ __forceinline__ uint32_t scan_rows(BinSmem& sm, int R) {
     __syncthreads();
     uint32_t wbase = 0, total = 0;
 #pragma unroll
-    for (int k = 0; k < kBsWarps; ++k) {
+    for (int k = 0; k < CF::kWarps; ++k) {
         const uint32_t x = sm.warp_tot[k];
         if (k < w) wbase += x;
         total += x;
@@ -332,7 +335,8 @@ __device__ __forceinline__ uint32_t scan_rows(BinSmem& sm, int R) {
 }
 
 // ascending sort of sm.idx[lo, hi) by the 64-bit entry it points to: one thread, short segments
-__device__ __forceinline__ void sort_segment_small(BinSmem& sm, uint32_t lo, uint32_t hi) {
+template <class CF>
+__device__ __forceinline__ void sort_segment_small(BinSmemT<CF>& sm, uint32_t lo, uint32_t hi) {
     for (uint32_t i = lo + 1; i < hi; ++i) {
         const uint16_t xi = sm.idx[i];
         const unsigned long long key = sm.stash[xi];
@@ -344,7 +348,8 @@ __device__ __forceinline__ void sort_segment_small(BinSmem& sm, uint32_t lo, uin
 
 // the same for a long segment (a hot row), by one warp: final position = number of smaller keys (ties by stash index;
 // equal keys are equal entries, so their order cannot change the sum)
-__device__ __forceinline__ void sort_segment_warp(BinSmem& sm, uint32_t lo, uint32_t hi, int lane) {
+template <class CF>
+__device__ __forceinline__ void sort_segment_warp(BinSmemT<CF>& sm, uint32_t lo, uint32_t hi, int lane) {
     const uint32_t n = hi - lo;
     for (uint32_t i = lane; i < n; i += 32) {
         const uint16_t xi = sm.idx[lo + i];
@@ -366,7 +371,8 @@ __device__ __forceinline__ void sort_segment_warp(BinSmem& sm, uint32_t lo, uint
 // inclusive prefix.  The warp inspects 32 predecessors per round trip (all resident CTAs took their tickets at about the
 // same time, so a one-thread walk would cross ~300 unresolved bins at one L2 round trip each).  Bins are taken in ticket
 // order, so every predecessor is resident and publishes its own count without waiting for anybody: no deadlock.
-__device__ __forceinline__ void resolve_base(const BinScatterParams& p, BinSmem& sm, uint32_t bin, int lane) {
+template <class CF>
+__device__ __forceinline__ void resolve_base(const BinScatterParams& p, BinSmemT<CF>& sm, uint32_t bin, int lane) {
     uint32_t prefix = 0;
     int64_t j = (int64_t)bin - 1;
     while (j >= 0) {
@@ -393,8 +399,8 @@ __device__ __forceinline__ void resolve_base(const BinScatterParams& p, BinSmem&
 }
 
 // write (or apply) the finished gradient of local row lr
-template <int VPL, bool FULL, int OPT>
-__device__ __forceinline__ void flush_row(const BinScatterParams& p, const BinSmem& sm, float4 (&acc)[VPL], float& csum, uint32_t lr,
+template <class CF, int VPL, bool FULL, int OPT>
+__device__ __forceinline__ void flush_row(const BinScatterParams& p, const BinSmemT<CF>& sm, float4 (&acc)[VPL], float& csum, uint32_t lr,
                                           uint32_t row0, int lane, const bool (&act)[VPL]) {
     const int D = p.D;
     const uint32_t row = row0 + lr;
@@ -430,8 +436,8 @@ __device__ __forceinline__ void flush_row(const BinScatterParams& p, const BinSm
 // (WHOLE: the range is the whole bin, cur already holds the row starts, and the touched rows are reported here)
 // PLAIN: compact sink, inner product, overwrite, no optimizer -- the touched rows of a range have consecutive ranks, so
 // the output is a running pointer and a finished row costs one 16-byte store per lane.
-template <int VPL, bool FULL, int OPT, bool WHOLE, bool PLAIN, int DEPTH>
-__device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem& sm, uint32_t m, uint32_t row0, float gs,
+template <class CF, int VPL, bool FULL, int OPT, bool WHOLE, bool PLAIN, int DEPTH>
+__device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmemT<CF>& sm, uint32_t m, uint32_t row0, float gs,
                                               const bool (&act)[VPL]) {
     // query rows in flight per warp.  The loop is latency-bound (entry -> query row from L2 -> FMA, ~1.2 us per
     // round trip): throughput = rows in flight per SM / latency, so registers are spent on depth (2 CTAs/SM, 128 regs)
@@ -440,8 +446,8 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
     const int D = p.D;
     const int R = 1 << p.shift;
     const uint32_t rmask = (uint32_t)R - 1u, bmask = (1u << p.bbits) - 1u;
-    if (!WHOLE) scan_rows<false>(sm, R);                            // counts -> starts
-    for (uint32_t i = t; i < m; i += kBsThreads) {                  // placement: sorted position -> stash index
+    if (!WHOLE) scan_rows<CF, false>(sm, R);                            // counts -> starts
+    for (uint32_t i = t; i < m; i += CF::kThreads) {                  // placement: sorted position -> stash index
         const uint32_t lr = ((uint32_t)sm.stash[i] >> p.bbits) & rmask;
         sm.idx[atomicAdd(&sm.cur[lr], 1u)] = (uint16_t)i;
     }
@@ -449,24 +455,27 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
     __syncthreads();
     // per row: order its entries by their 64-bit encoding -- the arrival order of the forward kernel's atomics must not
     // reach the floating-point sums -- and flag its last entry
-    for (int r = t; r < R; r += kBsThreads) {
+    for (int r = t; r < R; r += CF::kThreads) {
         const uint32_t e1 = sm.cur[r], e0 = r ? sm.cur[r - 1] : 0u;
         if (e1 != e0) {
-            if (e1 - e0 > kShortSeg) sm.long_rows[atomicAdd(&sm.nlong, 1u)] = (uint32_t)r;
-            else if (e1 - e0 > 1) sort_segment_small(sm, e0, e1);
+            if (e1 - e0 == 2u) {                                      // the common multi-entry case: one compare-exchange
+                const uint16_t a = sm.idx[e0], b = sm.idx[e0 + 1];
+                if (sm.stash[a] > sm.stash[b]) { sm.idx[e0] = b; sm.idx[e0 + 1] = a; }
+            } else if (e1 - e0 > kShortSeg) sm.long_rows[atomicAdd(&sm.nlong, 1u)] = (uint32_t)r;
+            else if (e1 - e0 > 2u) sort_segment_small<CF>(sm, e0, e1);
         }
     }
     if (WHOLE && warp == 0) {                                       // as late as possible: predecessors have published by now
         __syncwarp();
-        resolve_base(p, sm, sm.bin, lane);
+        resolve_base<CF>(p, sm, sm.bin, lane);
     }
     __syncthreads();
-    for (uint32_t k = warp; k < sm.nlong; k += kBsWarps) {
+    for (uint32_t k = warp; k < sm.nlong; k += CF::kWarps) {
         const uint32_t r = sm.long_rows[k];
-        sort_segment_warp(sm, r ? sm.cur[r - 1] : 0u, sm.cur[r], lane);
+        sort_segment_warp<CF>(sm, r ? sm.cur[r - 1] : 0u, sm.cur[r], lane);
     }
     __syncthreads();
-    for (int r = t; r < R; r += kBsThreads) {
+    for (int r = t; r < R; r += CF::kThreads) {
         const uint32_t e1 = sm.cur[r], e0 = r ? sm.cur[r - 1] : 0u;
         if (e1 != e0) {
             sm.idx[e1 - 1] |= kLast;
@@ -477,8 +486,8 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
     __syncthreads();
     // warp w sums the sorted positions [bound(w), bound(w + 1)): equal shares of the range snapped to row ends
     auto bound = [&](int w) -> uint32_t {
-        if (w >= kBsWarps) return m;
-        uint32_t b = (uint32_t)(((uint64_t)m * (uint32_t)w) / kBsWarps);
+        if (w >= CF::kWarps) return m;
+        uint32_t b = (uint32_t)(((uint64_t)m * (uint32_t)w) / CF::kWarps);
         if (b > 0) b = sm.cur[((uint32_t)sm.stash[sm.idx[b - 1] & 0x7FFFu] >> p.bbits) & rmask];
         return b;
     };
@@ -535,7 +544,7 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
                         }
                         dst_run += D;
                     } else {
-                        flush_row<VPL, FULL, OPT>(p, sm, acc, csum, __shfl_sync(kFull, meta, t0 + k) & 0x7FFFFFFFu, row0, lane, act);
+                        flush_row<CF, VPL, FULL, OPT>(p, sm, acc, csum, __shfl_sync(kFull, meta, t0 + k) & 0x7FFFFFFFu, row0, lane, act);
                     }
                 }
             }
@@ -544,10 +553,10 @@ __device__ __forceinline__ void process_range(const BinScatterParams& p, BinSmem
     __syncthreads();
 }
 
-// a single row with more than kEcap entries: all warps stream the bin, sum the entries of row `lr` (arrival order),
+// a single row with more than CF::kEcap entries: all warps stream the bin, sum the entries of row `lr` (arrival order),
 // the eight partial sums are added in warp order
-template <int VPL, bool FULL, int OPT>
-__device__ __forceinline__ void process_giant_row(const BinScatterParams& p, BinSmem& sm, uint32_t beg, uint32_t cnt, uint32_t lr,
+template <class CF, int VPL, bool FULL, int OPT>
+__device__ __forceinline__ void process_giant_row(const BinScatterParams& p, BinSmemT<CF>& sm, uint32_t beg, uint32_t cnt, uint32_t lr,
                                                   uint32_t row0, float gs, const bool (&act)[VPL]) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int D = p.D;
@@ -557,7 +566,7 @@ __device__ __forceinline__ void process_giant_row(const BinScatterParams& p, Bin
 #pragma unroll
     for (int x = 0; x < VPL; ++x) acc[x] = make_float4(0, 0, 0, 0);
     float csum = 0.f;
-    for (uint32_t i0 = warp * 32; i0 < cnt; i0 += kBsThreads) {
+    for (uint32_t i0 = warp * 32; i0 < cnt; i0 += CF::kThreads) {
         const uint32_t i = i0 + lane;
         unsigned long long e = 0ull;
         bool mine = false;
@@ -583,7 +592,7 @@ __device__ __forceinline__ void process_giant_row(const BinScatterParams& p, Bin
             csum += cl;
         }
     }
-    float* part = reinterpret_cast<float*>(sm.stash);                 // [kBsWarps][D + 1]
+    float* part = reinterpret_cast<float*>(sm.stash);                 // [CF::kWarps][D + 1]
 #pragma unroll
     for (int x = 0; x < VPL; ++x)
         if (FULL || act[x]) *reinterpret_cast<float4*>(part + (size_t)warp * 516 + lane * 4 + x * 128) = acc[x];
@@ -593,7 +602,7 @@ __device__ __forceinline__ void process_giant_row(const BinScatterParams& p, Bin
         csum = 0.f;
 #pragma unroll
         for (int x = 0; x < VPL; ++x) acc[x] = make_float4(0, 0, 0, 0);
-        for (int w = 0; w < kBsWarps; ++w) {
+        for (int w = 0; w < CF::kWarps; ++w) {
 #pragma unroll
             for (int x = 0; x < VPL; ++x)
                 if (FULL || act[x]) {
@@ -602,16 +611,16 @@ __device__ __forceinline__ void process_giant_row(const BinScatterParams& p, Bin
                 }
             csum += part[(size_t)w * 516 + 512];
         }
-        flush_row<VPL, FULL, OPT>(p, sm, acc, csum, lr, row0, lane, act);
+        flush_row<CF, VPL, FULL, OPT>(p, sm, acc, csum, lr, row0, lane, act);
     }
     __syncthreads();
 }
 
-template <int VPL, bool FULL, int OPT, bool PLAIN, int DEPTH, int OCC>
-__global__ void __launch_bounds__(kBsThreads, OCC)
+template <class CF, int VPL, bool FULL, int OPT, bool PLAIN, int DEPTH, int OCC>
+__global__ void __launch_bounds__(CF::kThreads, OCC)
 bin_scatter_kernel(const BinScatterParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BinSmem& sm = *reinterpret_cast<BinSmem*>(smem_raw);
+    BinSmemT<CF>& sm = *reinterpret_cast<BinSmemT<CF>*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int R = 1 << p.shift;
     const uint32_t rmask = (uint32_t)R - 1u;
@@ -620,7 +629,7 @@ bin_scatter_kernel(const BinScatterParams p) {
 #pragma unroll
     for (int x = 0; x < VPL; ++x) act[x] = FULL || (lane * 4 + x * 128) < p.D;
     constexpr int UNR = 4;
-    uint32_t* gcount = p.heavy_counts + (size_t)blockIdx.x * kMaxBinRows;   // whole-bin row counts of a heavy bin
+    uint32_t* gcount = p.heavy_counts + (size_t)blockIdx.x * CF::kMaxRows;   // whole-bin row counts of a heavy bin
 
     for (;;) {
         __syncthreads();                                              // sm.bin of the previous bin is no longer read
@@ -631,21 +640,21 @@ bin_scatter_kernel(const BinScatterParams p) {
         const uint32_t beg = __ldg(p.bin_off + bin), end = __ldg(p.bin_off + bin + 1);
         const uint32_t cnt = end - beg;
         const uint32_t row0 = bin << p.shift;
-        const bool heavy = cnt > (uint32_t)kEcap;
+        const bool heavy = cnt > (uint32_t)CF::kEcap;
 
         // ---- whole-bin pass: per-row touch counts (and, for bins that fit one chunk, the entries themselves)
-        for (int r = t * 4; r < R; r += kBsThreads * 4) *reinterpret_cast<uint4*>(&sm.cur[r]) = make_uint4(0, 0, 0, 0);
+        for (int r = t * 4; r < R; r += CF::kThreads * 4) *reinterpret_cast<uint4*>(&sm.cur[r]) = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        for (uint32_t i0 = t; i0 < cnt; i0 += kBsThreads * UNR) {
+        for (uint32_t i0 = t; i0 < cnt; i0 += CF::kThreads * UNR) {
             unsigned long long e[UNR];
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
-                const uint32_t i = i0 + k * kBsThreads;
+                const uint32_t i = i0 + k * CF::kThreads;
                 e[k] = i < cnt ? __ldcs(reinterpret_cast<const unsigned long long*>(p.ent) + beg + i) : 0ull;
             }
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
-                const uint32_t i = i0 + k * kBsThreads;
+                const uint32_t i = i0 + k * CF::kThreads;
                 if (i < cnt) {
                     if (!heavy) sm.stash[i] = e[k];
                     atomicAdd(&sm.cur[((uint32_t)e[k] >> p.bbits) & rmask], 1u);
@@ -654,7 +663,7 @@ bin_scatter_kernel(const BinScatterParams p) {
         }
         __syncthreads();
         if (heavy) {                                                  // keep the counts, scan the presence flags
-            for (int r = t; r < R; r += kBsThreads) {
+            for (int r = t; r < R; r += CF::kThreads) {
                 const uint32_t c = sm.cur[r];
                 gcount[r] = c;
                 sm.cur[r] = c ? 1u : 0u;
@@ -663,29 +672,29 @@ bin_scatter_kernel(const BinScatterParams p) {
         }
         // ---- rank of every touched row inside the bin; publish the bin's unique-row count, then look back for the
         //      rank of its first row among all touched rows of the table (decoupled look-back over bins in ticket order)
-        const uint32_t tot = scan_rows<true>(sm, R);                  // heavy: cur is scratch after this
+        const uint32_t tot = scan_rows<CF, true>(sm, R);                  // heavy: cur is scratch after this
         if (t == 0) {
             sm.uniq = tot >> 16;
             *reinterpret_cast<volatile unsigned long long*>(p.status + bin) = (bin == 0 ? kStPre : kStAgg) | (unsigned long long)sm.uniq;
         }
         if (warp == 0 && (cnt == 0 || heavy)) {                       // else: resolved late, inside process_range
             __syncwarp();
-            resolve_base(p, sm, bin, lane);
+            resolve_base<CF>(p, sm, bin, lane);
         }
         if (cnt == 0) continue;
         if (!heavy) {                                                 // cur already holds the row starts
-            process_range<VPL, FULL, OPT, true, PLAIN, DEPTH>(p, sm, cnt, row0, gs, act);
+            process_range<CF, VPL, FULL, OPT, true, PLAIN, DEPTH>(p, sm, cnt, row0, gs, act);
             continue;
         }
         __syncthreads();                                              // sm.base
-        // ---- heavy bin: consecutive row ranges of <= kEcap entries, each gathered from the bin's list by its own pass
+        // ---- heavy bin: consecutive row ranges of <= CF::kEcap entries, each gathered from the bin's list by its own pass
         if (p.rows_out) {
-            for (int r = t; r < R; r += kBsThreads)
+            for (int r = t; r < R; r += CF::kThreads)
                 if (gcount[r] && (int64_t)sm.base + sm.urank[r] < p.cap) p.rows_out[(size_t)sm.base + sm.urank[r]] = (int64_t)(row0 + r);
         }
         uint32_t ra = 0;
         while (ra < (uint32_t)R) {
-            if (warp == 0) {                                          // longest range [ra, rb) with <= kEcap entries
+            if (warp == 0) {                                          // longest range [ra, rb) with <= CF::kEcap entries
                 uint32_t run = 0, rb = ra;
                 bool done = false;
                 while (!done && rb < (uint32_t)R) {
@@ -697,7 +706,7 @@ bin_scatter_kernel(const BinScatterParams p) {
                         const uint32_t v = __shfl_up_sync(kFull, inc, o);
                         if (lane >= o) inc += v;
                     }
-                    const uint32_t over = __ballot_sync(kFull, run + inc > (uint32_t)kEcap);
+                    const uint32_t over = __ballot_sync(kFull, run + inc > (uint32_t)CF::kEcap);
                     if (over) {
                         const int l = __ffs(over) - 1;                // first row that does not fit
                         rb += l;
@@ -714,13 +723,13 @@ bin_scatter_kernel(const BinScatterParams p) {
                     sm.ra = ra; sm.rb = (rb == ra) ? ra + 1 : rb; sm.nst = 0u;
                 }
             }
-            for (int r = t * 4; r < R; r += kBsThreads * 4) *reinterpret_cast<uint4*>(&sm.cur[r]) = make_uint4(0, 0, 0, 0);
+            for (int r = t * 4; r < R; r += CF::kThreads * 4) *reinterpret_cast<uint4*>(&sm.cur[r]) = make_uint4(0, 0, 0, 0);
             __syncthreads();
             const uint32_t rb = sm.rb;
             if (sm.giant) {
-                process_giant_row<VPL, FULL, OPT>(p, sm, beg, cnt, ra, row0, gs, act);
+                process_giant_row<CF, VPL, FULL, OPT>(p, sm, beg, cnt, ra, row0, gs, act);
             } else {
-                for (uint32_t i = t; i < cnt; i += kBsThreads) {
+                for (uint32_t i = t; i < cnt; i += CF::kThreads) {
                     const unsigned long long e = __ldg(reinterpret_cast<const unsigned long long*>(p.ent) + beg + i);
                     const uint32_t lr = ((uint32_t)e >> p.bbits) & rmask;
                     if (lr >= ra && lr < rb) {
@@ -730,7 +739,7 @@ bin_scatter_kernel(const BinScatterParams p) {
                 }
                 __syncthreads();
                 const uint32_t m = sm.nst;
-                if (m) process_range<VPL, FULL, OPT, false, PLAIN, DEPTH>(p, sm, m, row0, gs, act);
+                if (m) process_range<CF, VPL, FULL, OPT, false, PLAIN, DEPTH>(p, sm, m, row0, gs, act);
             }
             __syncthreads();
             ra = rb;
@@ -738,37 +747,41 @@ bin_scatter_kernel(const BinScatterParams p) {
     }
 }
 
-int64_t bin_scatter_grid() { return (int64_t)sm_count() * 3; }          // upper bound over the configurations below (sizes bin_heavy)
+int64_t bin_scatter_grid() { return (int64_t)sm_count() * 6; }          // upper bound over the configurations below (sizes bin_heavy)
 
-template <int VPL, bool FULL, int OPT, bool PLAIN, int DEPTH, int OCC>
+template <class CF, int VPL, bool FULL, int OPT, bool PLAIN, int DEPTH, int OCC>
 static int32_t launch_bs(const BinScatterParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(BinSmem);
+    RSB_REQUIRE((1 << p.shift) <= CF::kMaxRows, RSB200_EINVAL, "bin_shift %d exceeds the %d rows per bin of this kernel shape", p.shift, CF::kMaxRows);
+    const size_t smem = sizeof(BinSmemT<CF>);
     int64_t blocks = (int64_t)sm_count() * OCC;
     if (blocks > p.nbins) blocks = p.nbins;
     if (blocks < 1) blocks = 1;
-    RSB_CUDA(cudaFuncSetAttribute(bin_scatter_kernel<VPL, FULL, OPT, PLAIN, DEPTH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bin_scatter_kernel<VPL, FULL, OPT, PLAIN, DEPTH, OCC><<<(unsigned)blocks, kBsThreads, smem, st>>>(p);
+    RSB_CUDA(cudaFuncSetAttribute(bin_scatter_kernel<CF, VPL, FULL, OPT, PLAIN, DEPTH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bin_scatter_kernel<CF, VPL, FULL, OPT, PLAIN, DEPTH, OCC><<<(unsigned)blocks, CF::kThreads, smem, st>>>(p);
     RSB_LAUNCH_CHECK();
     return 0;
 }
 
 template <int VPL>
 static int32_t launch_bin_scatter_v(const BinScatterParams& p, cudaStream_t st) {
+    using A = BsCfgA;
     const bool full = p.D == 128 * VPL;
     const bool plain = !p.dense && !p.accumulate && !p.euclid && p.opt < 0;
     if (plain && full) {
-        if constexpr (VPL == 1) {                                     // the hot configuration; p.tune: A/B of depth x occupancy
-            if (p.tune == 1) return launch_bs<VPL, true, -1, true, 16, 2>(p, st);
-            if (p.tune == 2) return launch_bs<VPL, true, -1, true, 8, 2>(p, st);
-            if (p.tune == 3) return launch_bs<VPL, true, -1, true, 4, 3>(p, st);
+        if constexpr (VPL == 1) {                                     // the hot configuration; p.tune: A/B of shape x depth x occupancy
+            if (p.tune == 1) return launch_bs<A, VPL, true, -1, true, 16, 2>(p, st);
+            if (p.tune == 2) return launch_bs<A, VPL, true, -1, true, 8, 2>(p, st);
+            if (p.tune == 3) return launch_bs<A, VPL, true, -1, true, 4, 3>(p, st);
+            if (p.tune == 4 && p.shift <= 10) return launch_bs<BsCfgB, VPL, true, -1, true, 8, 6>(p, st);
+            if (p.tune == 5 && p.shift <= 10) return launch_bs<BsCfgB, VPL, true, -1, true, 4, 6>(p, st);
         }
-        return launch_bs<VPL, true, -1, true, kBsDepth, kBsOcc>(p, st);
+        return launch_bs<A, VPL, true, -1, true, kBsDepth, kBsOcc>(p, st);
     }
-    if (plain) return launch_bs<VPL, false, -1, true, kBsDepth, kBsOcc>(p, st);
-    if (p.opt == 0) return full ? launch_bs<VPL, true, 0, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, 0, false, kBsDepth, kBsOcc>(p, st);
-    if (p.opt == 1) return full ? launch_bs<VPL, true, 1, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, 1, false, kBsDepth, kBsOcc>(p, st);
-    if (p.opt == 2) return full ? launch_bs<VPL, true, 2, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, 2, false, kBsDepth, kBsOcc>(p, st);
-    return full ? launch_bs<VPL, true, -1, false, kBsDepth, kBsOcc>(p, st) : launch_bs<VPL, false, -1, false, kBsDepth, kBsOcc>(p, st);
+    if (plain) return launch_bs<A, VPL, false, -1, true, kBsDepth, kBsOcc>(p, st);
+    if (p.opt == 0) return full ? launch_bs<A, VPL, true, 0, false, kBsDepth, kBsOcc>(p, st) : launch_bs<A, VPL, false, 0, false, kBsDepth, kBsOcc>(p, st);
+    if (p.opt == 1) return full ? launch_bs<A, VPL, true, 1, false, kBsDepth, kBsOcc>(p, st) : launch_bs<A, VPL, false, 1, false, kBsDepth, kBsOcc>(p, st);
+    if (p.opt == 2) return full ? launch_bs<A, VPL, true, 2, false, kBsDepth, kBsOcc>(p, st) : launch_bs<A, VPL, false, 2, false, kBsDepth, kBsOcc>(p, st);
+    return full ? launch_bs<A, VPL, true, -1, false, kBsDepth, kBsOcc>(p, st) : launch_bs<A, VPL, false, -1, false, kBsDepth, kBsOcc>(p, st);
 }
 
 int32_t launch_bin_scatter(const BinScatterParams& p, cudaStream_t st) {

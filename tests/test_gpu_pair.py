@@ -102,7 +102,7 @@ def test_dense_sink_and_int32_ids(name):
     _check_grads(out, g["d_item"], g["d_user"])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 7, 17, 19, 22, 23, 31])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 7, 17, 19, 22, 23, 31, 51, 54, 55])
 @pytest.mark.parametrize("name", ["step_d128_bpr_ip", "step_d128_ssm_eu", "step_d64dup_ssm_ip"])
 def test_kernel_variants_match_golden(name, variant):
     """The experimental forward variants (rsb200_pair_args.variant: 1 pipelined, 2 TMA ring, 3 L2 prefetch,
