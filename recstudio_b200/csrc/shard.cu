@@ -350,30 +350,81 @@ shard_prep_bins_kernel(const PrepBinParams p) {
             const int total = __shfl_sync(kFull, inc, 31);
             const size_t out0 = base + kept_total + (inc - cnt);
             // -- C: resolve + write
-            for (int t = 0; t < cnt; ++t) {
-                const uint32_t v = my[t * 33 + lane];
-                int lid;
-                float lq = 0.f;
-                if (MODE == 2) {
-                    const float u = __uint_as_float(v);
-                    int lo = 0, hi = (int)p.local_rows - 1;
-                    if (p.pop_guide) {
-                        const int64_t k = (int64_t)(u * (float)(1 << p.pop_bits)) - p.pop_k0;    // exact: power-of-two scale
-                        lo = __ldg(p.pop_guide + k); hi = __ldg(p.pop_guide + k + 1);
+            if (MODE == 2) {
+                // popularity search on the kept draws, four at a time: the guide lookups, the bisection steps and the final
+                // <= 8-entry counts of four draws are independent loads, so their latencies overlap instead of adding up
+                constexpr int kW = 4, kLinear = 8;
+                for (int t0 = 0; t0 < cnt; t0 += kW) {
+                    float u[kW]; int lo[kW], hi[kW]; bool ok[kW];
+#pragma unroll
+                    for (int k = 0; k < kW; ++k) {
+                        ok[k] = t0 + k < cnt;
+                        u[k] = ok[k] ? __uint_as_float(my[(t0 + k) * 33 + lane]) : 0.f;
+                        lo[k] = 0; hi[k] = ok[k] ? (int)p.local_rows - 1 : 0;
                     }
-                    lid = local_lower_bound(p.pop_table, lo, hi, u);
-                    lq = logf(__ldg(p.pop_prob + lid));
-                } else if (MODE == 0) {
-                    int64_t gid = (int64_t)__ldg(p.neg + base + seg0 + v);
-                    if (gid < 0 || gid >= p.num_items) gid = 0;
-                    lid = (int)(gid - p.row0);
-                    if (p.logq_neg) lq = __ldg(p.logq_neg + base + seg0 + v);
-                } else {
-                    lid = (int)v;
+                    if (p.pop_guide) {
+#pragma unroll
+                        for (int k = 0; k < kW; ++k) {
+                            if (ok[k]) {
+                                const int64_t g0 = (int64_t)(u[k] * (float)(1 << p.pop_bits)) - p.pop_k0;   // exact: power-of-two scale
+                                lo[k] = __ldg(p.pop_guide + g0); hi[k] = __ldg(p.pop_guide + g0 + 1);
+                            }
+                        }
+                    }
+                    bool more = true;
+                    while (more) {                                    // bisection in lockstep, down to brackets of <= 8 entries
+                        more = false;
+                        float tv[kW]; int mid[kW];
+#pragma unroll
+                        for (int k = 0; k < kW; ++k) {
+                            mid[k] = lo[k] + ((hi[k] - lo[k]) >> 1);
+                            tv[k] = (hi[k] - lo[k] > kLinear) ? __ldg(p.pop_table + mid[k]) : 0.f;
+                        }
+#pragma unroll
+                        for (int k = 0; k < kW; ++k) {
+                            if (hi[k] - lo[k] > kLinear) {
+                                if (tv[k] < u[k]) lo[k] = mid[k] + 1; else hi[k] = mid[k];
+                                more |= hi[k] - lo[k] > kLinear;
+                            }
+                        }
+                    }
+                    int lid[kW];
+#pragma unroll
+                    for (int k = 0; k < kW; ++k) {
+                        lid[k] = lo[k];
+#pragma unroll
+                        for (int t = 0; t < kLinear; ++t)
+                            if (lo[k] + t < hi[k]) lid[k] += (__ldg(p.pop_table + lo[k] + t) < u[k]) ? 1 : 0;
+                    }
+                    float pr[kW];
+#pragma unroll
+                    for (int k = 0; k < kW; ++k) pr[k] = ok[k] ? __ldg(p.pop_prob + lid[k]) : 1.f;
+#pragma unroll
+                    for (int k = 0; k < kW; ++k) {
+                        if (ok[k]) {
+                            p.neg_c[out0 + t0 + k] = lid[k];
+                            if (p.lq_c) p.lq_c[out0 + t0 + k] = logf(pr[k]);
+                            if (p.row0 + lid[k] != 0) atomicAdd(hist + ((uint32_t)lid[k] >> p.bt.shift), 1u);
+                        }
+                    }
                 }
-                p.neg_c[out0 + t] = lid;
-                if (p.lq_c) p.lq_c[out0 + t] = lq;
-                if (p.row0 + lid != 0) atomicAdd(hist + ((uint32_t)lid >> p.bt.shift), 1u);   // padding row: scored, no gradient
+            } else {
+                for (int t = 0; t < cnt; ++t) {
+                    const uint32_t v = my[t * 33 + lane];
+                    int lid;
+                    float lq = 0.f;
+                    if (MODE == 0) {
+                        int64_t gid = (int64_t)__ldg(p.neg + base + seg0 + v);
+                        if (gid < 0 || gid >= p.num_items) gid = 0;
+                        lid = (int)(gid - p.row0);
+                        if (p.logq_neg) lq = __ldg(p.logq_neg + base + seg0 + v);
+                    } else {
+                        lid = (int)v;
+                    }
+                    p.neg_c[out0 + t] = lid;
+                    if (p.lq_c) p.lq_c[out0 + t] = lq;
+                    if (p.row0 + lid != 0) atomicAdd(hist + ((uint32_t)lid >> p.bt.shift), 1u);   // padding row: scored, no gradient
+                }
             }
             kept_total += total;
         }
