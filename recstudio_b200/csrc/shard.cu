@@ -184,6 +184,7 @@ struct PrepBinParams {
     int64_t num_items, row0, local_rows;
     int G, n, D, euclid, use_smem;
     uint64_t mod_magic;            // ceil(2^64 / (num_items - 1)): division-free v mod (num_items - 1)
+    uint64_t own_lo, own_hi;       // uniform regeneration: word v lands on a row of this owner  <=>  own_lo <= mod_magic * v <= own_hi
     int do_pos, do_neg;            // PREP may be split: negatives (independent of the batch's queries) | positives
     // regeneration
     const uint64_t* regen_state; int regen_B; int64_t regen_T; int t_per; int n_round_blocks;
@@ -247,9 +248,9 @@ shard_prep_bins_kernel(const PrepBinParams p) {
                 li0 = (int64_t)(g - r * p.regen_B) * n;
             }
         } else {
-            const int per_rank = p.n_round_blocks * p.t_per;
-            const int r = (int)(item / per_rank), rem = (int)(item % per_rank);
-            R = rem / p.t_per; x = rem % p.t_per;
+            const uint32_t per_rank = (uint32_t)(p.n_round_blocks * p.t_per), it32 = (uint32_t)item;     // nitems < 2^31
+            const int r = (int)(it32 / per_rank), rem = (int)(it32 - (uint32_t)r * per_rank);
+            R = (int)((uint32_t)rem / (uint32_t)p.t_per); x = rem - R * p.t_per;
             const int lb = 4 * p.t_per * R + x + p.t_per * warp;      // this warp's query inside rank r's batch
             g = lb < p.regen_B ? r * p.regen_B + lb : -1;
             seed = __ldg(p.regen_state + 2 * r); off = __ldg(p.regen_state + 2 * r + 1);
@@ -285,12 +286,13 @@ shard_prep_bins_kernel(const PrepBinParams p) {
         for (int seg0 = 0; seg0 < (p.do_neg ? n : 0); seg0 += kPrepSeg) {
             const int m = min(kPrepSeg, n - seg0);
             const int c = (m + 31) >> 5;                              // candidates per lane
+            const int cs = (c & (c - 1)) == 0 ? 31 - __clz(c) : -1;   // c a power of two (every full segment): shifts, no division
             __syncthreads();                                          // the previous segment's staging area is consumed
             // -- A: stage
             if (shared) {
                 for (int j = threadIdx.x; j < m; j += blockDim.x) {
                     const uint4 w = Philox::gen(seed, (uint64_t)((int64_t)x * n + seg0 + j), off / 4 + (uint64_t)R);
-                    const int slot = (j % c) * 33 + j / c;
+                    const int slot = cs >= 0 ? (j & (c - 1)) * 33 + (j >> cs) : (j % c) * 33 + j / c;
                     s_cand[0 * kPrepSegWords + slot] = w.x; s_cand[1 * kPrepSegWords + slot] = w.y;
                     s_cand[2 * kPrepSegWords + slot] = w.z; s_cand[3 * kPrepSegWords + slot] = w.w;
                 }
@@ -305,7 +307,7 @@ shard_prep_bins_kernel(const PrepBinParams p) {
                         const int ii = (int)(qq & 3);
                         v = ii == 0 ? w.x : (ii == 1 ? w.y : (ii == 2 ? w.z : w.w));
                     }
-                    my[(j % c) * 33 + j / c] = v;
+                    my[cs >= 0 ? (j & (c - 1)) * 33 + (j >> cs) : (j % c) * 33 + j / c] = v;
                 }
             }
             __syncthreads();
@@ -325,19 +327,19 @@ shard_prep_bins_kernel(const PrepBinParams p) {
                     if (u == 1.0f) u = 0.0f;                          // -> [0, 1)   (ATen uniform_, DistributionTemplates.h:485-506)
                     mine = u > p.cdf_lo && u <= p.cdf_hi;
                     keep = __float_as_uint(u);
+                } else if (MODE == 1) {
+                    // the id is v mod (N - 1) + 1 (ATen random_from_to, 32-bit path), by Lemire's fastmod (exact for every 32-bit
+                    // v:  M = ceil(2^64 / d),  v mod d = mulhi64((M * v) mod 2^64, d)).  Ownership only needs the low product
+                    // (monotone, see own_lo / own_hi); the kept words are turned into local rows in C.
+                    const uint64_t lb = p.mod_magic * (uint64_t)v;
+                    mine = lb >= p.own_lo && lb <= p.own_hi;
+                    keep = v;
                 } else {
-                    uint32_t gid;
-                    if (MODE == 0) {
-                        gid = v;
-                        if (gid >= (uint32_t)p.num_items) { bad = true; gid = 0u; }      // also catches negative ids
-                    } else {
-                        // v mod (N - 1) + 1 (ATen random_from_to, 32-bit path) without a division: Lemire's fastmod,
-                        // exact for every 32-bit v:  M = ceil(2^64 / d),  v mod d = mulhi64((M * v) mod 2^64, d)
-                        gid = (uint32_t)__umul64hi(p.mod_magic * (uint64_t)v, (uint64_t)(uint32_t)(p.num_items - 1)) + 1u;
-                    }
+                    uint32_t gid = v;
+                    if (gid >= (uint32_t)p.num_items) { bad = true; gid = 0u; }          // also catches negative ids
                     const uint32_t l = gid - (uint32_t)p.row0;        // wraps for rows below the block: fails the test
                     mine = l < (uint32_t)p.local_rows;
-                    keep = MODE == 0 ? (uint32_t)j : l;               // MODE 0 keeps the position: log Q is looked up in C
+                    keep = (uint32_t)j;                               // keeps the position: log Q is looked up in C
                 }
                 if (mine) { my[cnt * 33 + lane] = keep; ++cnt; }
             }
@@ -419,7 +421,8 @@ shard_prep_bins_kernel(const PrepBinParams p) {
                         lid = (int)(gid - p.row0);
                         if (p.logq_neg) lq = __ldg(p.logq_neg + base + seg0 + v);
                     } else {
-                        lid = (int)v;
+                        lid = (int)((uint32_t)__umul64hi(p.mod_magic * (uint64_t)v, (uint64_t)(uint32_t)(p.num_items - 1)) + 1u
+                                    - (uint32_t)p.row0);
                     }
                     p.neg_c[out0 + t] = lid;
                     if (p.lq_c) p.lq_c[out0 + t] = lq;
@@ -627,6 +630,18 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
             }
             p.do_neg = prep_neg ? 1 : 0; p.do_pos = prep_pos ? 1 : 0;       // one launch does whatever halves are requested
             p.mod_magic = a->num_items > 1 ? (~(uint64_t)0) / (uint64_t)(a->num_items - 1) + 1 : 0;
+            {
+                // v mod d = floor(low64(M v) * d / 2^64) is monotone in low64(M v): "row0 <= v mod d + 1 < row0 + local_rows" is a
+                // range test on low64(M v), and only the draws that pass it (1 / world of them) pay for the 64 x 64 high product
+                const int64_t d = a->num_items - 1, lo = a->row0 - 1, hi = a->row0 + a->local_rows - 1;    // lo <= v mod d < hi
+                p.own_lo = 1; p.own_hi = 0;                                                                // empty
+                if (d > 0 && hi > 0 && hi > lo) {
+                    const unsigned __int128 one = (unsigned __int128)1 << 64;
+                    p.own_lo = lo <= 0 ? 0 : (uint64_t)(((unsigned __int128)lo * one + (unsigned __int128)(d - 1)) / (unsigned __int128)d);
+                    p.own_hi = hi >= d ? ~(uint64_t)0
+                                       : (uint64_t)(((unsigned __int128)hi * one + (unsigned __int128)(d - 1)) / (unsigned __int128)d - 1);
+                }
+            }
             if (!p.do_neg) { p.t_per = 0; p.n_round_blocks = 0; mode = 0; }      // positives only: plain query-major mapping
             p.use_smem = bt.nbins <= 8192;
             const size_t smem = sizeof(uint32_t) * ((p.use_smem ? (size_t)bt.nbins : 0) + 4 * (size_t)kPrepSegWords);
