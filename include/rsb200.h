@@ -494,7 +494,8 @@ typedef struct rsb200_shard_args {
      * slot_neg / slot_pos / off / urow / scan_tmp are then unused and may be NULL. */
     int32_t   grouping;
     int32_t   bin_shift;
-    uint32_t* bin_cnt;                 /* [nbins], nbins = ceil(local_rows / 2^bin_shift)                        */
+    uint32_t* bin_cnt;                 /* [nbins + 1], nbins = ceil(local_rows / 2^bin_shift); the last word is    */
+                                       /* PREP_NEG's work counter (zeroed by the library together with the counts) */
     uint32_t* bin_off;                 /* [nbins + 1]                                                            */
     uint32_t* bin_cursor;              /* [nbins * 8]                                                            */
     uint64_t* bin_status;              /* [nbins]                                                                */

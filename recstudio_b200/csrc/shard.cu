@@ -184,6 +184,7 @@ struct PrepBinParams {
     int64_t num_items, row0, local_rows;
     int G, n, D, euclid, use_smem;
     uint64_t mod_magic;            // ceil(2^64 / (num_items - 1)): division-free v mod (num_items - 1)
+    uint32_t* work;                // PREP's work counter: bin_cnt[nbins] (zeroed with the counts)
     uint64_t own_lo, own_hi;       // uniform regeneration: word v lands on a row of this owner  <=>  own_lo <= mod_magic * v <= own_hi
     int do_pos, do_neg;            // PREP may be split: negatives (independent of the batch's queries) | positives
     // regeneration
@@ -234,7 +235,16 @@ shard_prep_bins_kernel(const PrepBinParams p) {
     // shared Philox blocks need T = t_per * n; any other shape regenerates per id (t_per = 0: every block computed 4x)
     const bool shared = MODE != 0 && p.t_per > 0;
     const int64_t nitems = !shared ? ((int64_t)p.G + 3) / 4 : (int64_t)(p.G / p.regen_B) * p.n_round_blocks * p.t_per;
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    // Work distribution: every CTA's first item is its block index; with negatives to prepare, the following ones come from a
+    // counter (p.work, zeroed by the launcher), fetched one item ahead so the atomic's latency is off the path.  A CTA that
+    // becomes resident late (the SMs are shared with an exchange kernel in the look-ahead schedule) then only takes what is
+    // left, instead of a fixed 1/gridDim share that would stretch the kernel to twice its length.
+    const bool dynamic = p.do_neg && n > 0 && p.work != nullptr;
+    __shared__ uint32_t s_next;
+    int64_t item = blockIdx.x;
+    while (item < nitems) {
+        uint32_t nxt = 0;
+        if (dynamic && threadIdx.x == 0) nxt = gridDim.x + atomicAdd(p.work, 1u);
         int g;                                                        // global query of this warp, -1 = none
         uint64_t seed = 0, off = 0;
         int64_t li0 = 0;                                              // per-id regeneration: first element of the query
@@ -432,6 +442,13 @@ shard_prep_bins_kernel(const PrepBinParams p) {
             kept_total += total;
         }
         if (g >= 0 && lane == 0 && p.do_neg) p.ncount[g] = kept_total;
+        if (dynamic) {
+            if (threadIdx.x == 0) s_next = nxt;
+            __syncthreads();                                          // (the next write of s_next is behind the segment loop's barriers)
+            item = s_next;
+        } else {
+            item += gridDim.x;
+        }
     }
     if (bad) atomicOr(p.err, 1u);
     if (p.use_smem) {
@@ -604,12 +621,14 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
     const bool prep_pos = (phases & (RSB200_SHARD_PREP | RSB200_SHARD_PREP_POS)) != 0;
     RSB_REQUIRE(bins || !(phases & (RSB200_SHARD_PREP_NEG | RSB200_SHARD_PREP_POS)), RSB200_EUNSUPPORTED, "split PREP needs grouping 1");
     if ((prep_neg || prep_pos) && bins) {
-        if (prep_neg) RSB_CUDA(cudaMemsetAsync(bt.cnt, 0, sizeof(uint32_t) * (size_t)bt.nbins, st));
+        // counts of this step's touches per bin (PREP_NEG starts them) + the word behind them: PREP's work counter
+        if (prep_neg) RSB_CUDA(cudaMemsetAsync(bt.cnt, 0, sizeof(uint32_t) * ((size_t)bt.nbins + 1), st));
         if (G > 0) {
             PrepBinParams p;
             p.w_local = a->w_local; p.q_all = a->q_all; p.pos = a->pos; p.neg = a->neg; p.logq_neg = a->logq_neg;
             p.neg_c = a->neg_c; p.lq_c = (a->logq_neg || (a->regen_state && a->regen_kind == 1)) ? a->lq_c : nullptr;
             p.ncount = a->ncount; p.pos_local = a->pos_local; p.sp = a->sp; p.lq_pos_out = a->lq_pos_out; p.err = a->err_flag;
+            p.work = bt.cnt + bt.nbins;
             p.bt = bt; p.num_items = a->num_items; p.row0 = a->row0; p.local_rows = a->local_rows;
             p.G = (int)G; p.n = (int)n; p.D = (int)a->d; p.euclid = eu;
             p.regen_state = a->regen_state; p.regen_B = (int)a->regen_B; p.regen_T = 0; p.t_per = 0; p.n_round_blocks = 0;

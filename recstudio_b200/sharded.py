@@ -252,7 +252,7 @@ class OwnerComputeCuda:
         if self.grouping:
             nb = -(-max(local_rows, 1) // (1 << self.bin_shift))
             self.nbins = nb
-            self._bin_cnt = [E(nb, dtype=i32) for _ in range(self.slots)]
+            self._bin_cnt = [E(nb + 1, dtype=i32) for _ in range(self.slots)]      # + PREP_NEG's work counter
             self.bin_cnt, self.bin_off, self.bin_cursor = self._bin_cnt[0], E(nb + 1, dtype=i32), E(nb * 8, dtype=i32)
             self.bin_status, self.bin_ticket = E(nb, dtype=i64), torch.zeros(1, dtype=i32, device=dev)
             self.bin_heavy = E(int(L.rsb200_bin_heavy_elems()), dtype=i32)
