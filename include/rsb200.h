@@ -507,6 +507,10 @@ typedef struct rsb200_shard_args {
  * per step from num_queries queries (0 = not supported: use grouping 0), and the size of the bin_heavy scratch */
 int32_t rsb200_bin_shift(int64_t num_rows, int64_t touches, int64_t num_queries);
 int64_t rsb200_bin_heavy_elems(void);
+/* host arithmetic behind the owner-side regeneration of UniformSampler draws (sampler.py:86-111: ids = randint(1, N)): a Philox
+ * word v is the id v mod (N - 1) + 1; it lands on rows [row0, row0 + local_rows) iff lo <= low64(magic * v) <= hi (exact for
+ * every 32-bit v; magic = ceil(2^64 / (N - 1))).  An empty block gives lo = 1, hi = 0.  No device work. */
+int32_t rsb200_uniform_owner_range(int64_t num_items, int64_t row0, int64_t local_rows, uint64_t* magic, uint64_t* lo, uint64_t* hi);
 /* guide entries k0 .. k0 + len - 1 of a table slice: out[i] = first j in [0, num_rows - 1] with table_local[j] >= (k0 + i) / 2^bits
  * (num_rows - 1 if none) */
 int32_t rsb200_popular_build_guide_range(const float* table_local, int64_t num_rows, int32_t guide_bits, int64_t k0, int64_t len,

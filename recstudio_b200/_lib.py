@@ -118,6 +118,7 @@ def lib():
             "rsb200_popular_build_guide": [v, i64, i32, v, v],
             "rsb200_popular_build_guide_range": [v, i64, i32, i64, i64, v, v],
             "rsb200_bin_shift": [i64, i64, i64],
+            "rsb200_uniform_owner_range": [i64, i64, i64, v, v, v],
             "rsb200_sample_popular": [u64, u64, v, v, i64, i64, i64, i32, i32, v, i32, v, v, v, v],
             "rsb200_popular_logq": [v, i64, v, i64, v, v],
             "rsb200_masked_workspace_elems": [i64, i64, v, v],

@@ -557,6 +557,26 @@ extern "C" int32_t rsb200_bin_shift(int64_t num_rows, int64_t touches, int64_t n
 extern "C" int64_t rsb200_bin_heavy_elems(void) { return bin_scatter_grid() * ((int64_t)1 << kMaxBinShift); }
 extern "C" int64_t rsb200_scan_tmp_elems(int64_t num_rows) { return scan_tmp_elems(num_rows); }
 
+// Host arithmetic of the owner-side regeneration of UniformSampler draws (no device work): a 32-bit Philox word v becomes the
+// id  v mod d + 1,  d = num_items - 1  (ATen random_from_to).  With M = ceil(2^64 / d), Lemire's fastmod gives
+// v mod d = floor(low64(M v) d / 2^64), which is monotone in low64(M v): "row0 <= id < row0 + local_rows" is the range test
+// lo <= low64(M v) <= hi, and only the draws that pass it pay for the 64 x 64 high product.  Empty block: lo = 1, hi = 0.
+extern "C" int32_t rsb200_uniform_owner_range(int64_t num_items, int64_t row0, int64_t local_rows, uint64_t* magic, uint64_t* lo,
+                                              uint64_t* hi) {
+    RSB_REQUIRE(magic && lo && hi, RSB200_EINVAL, "null output");
+    RSB_REQUIRE(num_items >= 1 && row0 >= 0 && local_rows >= 0 && num_items - 1 <= (int64_t)0xffffffffLL, RSB200_EINVAL,
+                "bad sizes (ids are drawn from 32-bit words: num_items - 1 <= 2^32 - 1)");
+    const int64_t d = num_items - 1, a = row0 - 1, b = row0 + local_rows - 1;          // a <= v mod d < b
+    *magic = d > 0 ? (~(uint64_t)0) / (uint64_t)d + 1 : 0;
+    *lo = 1; *hi = 0;
+    if (d > 0 && b > 0 && b > a) {
+        const unsigned __int128 one = (unsigned __int128)1 << 64;
+        *lo = a <= 0 ? 0 : (uint64_t)(((unsigned __int128)a * one + (unsigned __int128)(d - 1)) / (unsigned __int128)d);
+        *hi = b >= d ? ~(uint64_t)0 : (uint64_t)(((unsigned __int128)b * one + (unsigned __int128)(d - 1)) / (unsigned __int128)d - 1);
+    }
+    return RSB200_OK;
+}
+
 extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases, void* stream) {
     RSB_REQUIRE(a != nullptr, RSB200_EINVAL, "null args");
     RSB_REQUIRE(a->d >= 4 && a->d % 4 == 0 && a->d <= 512, a->d > 512 ? RSB200_EUNSUPPORTED : RSB200_EINVAL,
@@ -648,18 +668,10 @@ extern "C" int32_t rsb200_shard_step(const rsb200_shard_args* a, int32_t phases,
                 mode = a->regen_kind == 1 ? 2 : 1;
             }
             p.do_neg = prep_neg ? 1 : 0; p.do_pos = prep_pos ? 1 : 0;       // one launch does whatever halves are requested
-            p.mod_magic = a->num_items > 1 ? (~(uint64_t)0) / (uint64_t)(a->num_items - 1) + 1 : 0;
-            {
-                // v mod d = floor(low64(M v) * d / 2^64) is monotone in low64(M v): "row0 <= v mod d + 1 < row0 + local_rows" is a
-                // range test on low64(M v), and only the draws that pass it (1 / world of them) pay for the 64 x 64 high product
-                const int64_t d = a->num_items - 1, lo = a->row0 - 1, hi = a->row0 + a->local_rows - 1;    // lo <= v mod d < hi
-                p.own_lo = 1; p.own_hi = 0;                                                                // empty
-                if (d > 0 && hi > 0 && hi > lo) {
-                    const unsigned __int128 one = (unsigned __int128)1 << 64;
-                    p.own_lo = lo <= 0 ? 0 : (uint64_t)(((unsigned __int128)lo * one + (unsigned __int128)(d - 1)) / (unsigned __int128)d);
-                    p.own_hi = hi >= d ? ~(uint64_t)0
-                                       : (uint64_t)(((unsigned __int128)hi * one + (unsigned __int128)(d - 1)) / (unsigned __int128)d - 1);
-                }
+            p.mod_magic = 0; p.own_lo = 1; p.own_hi = 0;
+            if (mode == 1) {                                          // uniform regeneration: ownership thresholds of this block
+                const int32_t rc = rsb200_uniform_owner_range(a->num_items, a->row0, a->local_rows, &p.mod_magic, &p.own_lo, &p.own_hi);
+                if (rc != RSB200_OK) return rc;
             }
             if (!p.do_neg) { p.t_per = 0; p.n_round_blocks = 0; mode = 0; }      // positives only: plain query-major mapping
             p.use_smem = bt.nbins <= 8192;

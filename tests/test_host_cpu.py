@@ -251,3 +251,40 @@ def test_popular_slice_tables_match_reference_golden():
             table, prob = sharded.PopularSlice.tables(g[f"{tag}_count"], mode)
             np.testing.assert_array_equal(prob.numpy(), g[f"{tag}_m{mode}_prob"])
             np.testing.assert_array_equal(table.numpy(), g[f"{tag}_m{mode}_table"])
+
+
+def test_uniform_owner_range_is_exact(L):
+    """rsb200_uniform_owner_range (host arithmetic of the owner-side UniformSampler regeneration, sampler.py:86-111 =
+    randint(1, N)): for every 32-bit word v,  lo <= low64(magic * v) <= hi  <=>  row0 <= v mod (N - 1) + 1 < row0 + local_rows,
+    and mulhi64(low64(magic * v), N - 1) == v mod (N - 1).  Checked with Python integers on random and boundary words, every
+    owner of several world sizes, table sizes from 2 rows to 2^32."""
+    rng = np.random.default_rng(5)
+    sizes = [2, 3, 4, 10, 1000, 1575, 400_003, 1_000_001, 10_000_001, 100_000_001, 2 ** 31 - 5, 2 ** 31 + 1, 2 ** 32 - 1, 2 ** 32,
+             2 ** 20 + 1, 2 ** 24 + 1]
+    sizes += [int(x) for x in rng.integers(2, 2 ** 32, size=24)]
+    mask = (1 << 64) - 1
+    for N in sizes:
+        d = N - 1
+        for world in (1, 2, 3, 8):
+            per = -(-N // world)
+            for r in range(world):
+                row0 = r * per
+                local = max(0, min(per, N - row0))
+                if row0 > N:
+                    continue
+                mg, lo, hi = C.c_uint64(), C.c_uint64(), C.c_uint64()
+                assert L.rsb200_uniform_owner_range(N, row0, local, C.byref(mg), C.byref(lo), C.byref(hi)) == 0
+                M = mg.value
+                assert M == -(-(1 << 64) // d) or (d & (d - 1)) == 0 and M == ((1 << 64) // d) & mask
+                words = [int(x) for x in rng.integers(0, 2 ** 32, size=48)] + [0, 1, 2 ** 32 - 1, d % 2 ** 32, (d - 1) % 2 ** 32]
+                for b in (row0 - 2, row0 - 1, row0, row0 + local - 2, row0 + local - 1, row0 + local):   # ids around the block's ends
+                    if 0 <= b < d:
+                        words += [b, (b + d) % 2 ** 32] if b + d < 2 ** 32 else [b]
+                for v in words:
+                    low = (M * v) & mask
+                    assert (low * d) >> 64 == v % d, (N, v)
+                    owned = row0 <= v % d + 1 < row0 + local
+                    assert owned == (lo.value <= low <= hi.value), (N, world, r, v)
+    mg, lo, hi = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert L.rsb200_uniform_owner_range(2 ** 32 + 2, 0, 10, C.byref(mg), C.byref(lo), C.byref(hi)) == -1   # ids beyond 32-bit words
+    assert L.rsb200_uniform_owner_range(10, 0, 10, None, C.byref(lo), C.byref(hi)) == -1
