@@ -456,10 +456,50 @@ def golden_pooling():
     save("pooling", **out)
 
 
+def golden_sasrec_encoder():
+    """The reference's own SASRecQueryEncoder (recstudio/model/seq/sasrec.py:8-67; BERT4Rec uses it with
+    bidirectional=True, bert4rec.py) at the config-3 shape class: d = 128, 2 heads, FFN 128, GELU, LayerNorm eps 1e-12, 2 layers,
+    L = 200 (seq/config/sasrec.yaml:1-7), dropout 0 so the result is a function of the weights.  Weights, a right-padded id batch,
+    the pooled output ('last' pooling) for the causal and the bidirectional mask, and gradients of sum(out * g) with respect
+    to a spread of parameters (table, positions, first-layer attention, last-layer FFN and norms)."""
+    from recstudio.model.seq.sasrec import SASRecQueryEncoder
+    torch.manual_seed(31)
+    N, d, L, B = 300, 128, 200, 6
+    item = torch.nn.Embedding(N, d, padding_idx=0)
+    enc = SASRecQueryEncoder("item_id", d, L, 2, 128, 0.0, "gelu", 1e-12, 2, item, bidirectional=False)
+    with torch.no_grad():
+        item.weight.normal_(0, 0.5); item.weight[0] = 0
+        enc.position_emb.weight.normal_(0, 0.5)
+    seqlen = torch.tensor([1, 7, 64, 129, 199, 200])
+    ids = torch.randint(1, N, (B, L)) * (torch.arange(L)[None, :] < seqlen[:, None])
+    batch = {"in_item_id": ids, "seqlen": seqlen}
+    g = torch.randn(B, d)
+    watch = ["item_encoder.weight", "position_emb.weight", "transformer_layer.layers.0.self_attn.in_proj_weight",
+             "transformer_layer.layers.0.self_attn.out_proj.bias", "transformer_layer.layers.0.norm1.weight",
+             "transformer_layer.layers.1.linear2.weight", "transformer_layer.layers.1.norm2.bias"]
+    out = {"ids": ids, "seqlen": seqlen, "g": g, "watch": np.array(watch)}
+    for k, v in enc.state_dict().items():
+        out["w:" + k] = v
+    enc.train()
+    for tag, bidir in (("causal", False), ("bidir", True)):
+        enc.bidirectional = bidir
+        enc.zero_grad()
+        o = enc(batch)
+        (o * g).sum().backward()
+        out["out_" + tag] = o
+        params = dict(enc.named_parameters())
+        for k in watch:
+            out["grad_%s:%s" % (tag, k)] = params[k].grad.clone()
+    enc.eval()
+    enc.bidirectional = False
+    out["out_eval_causal"] = enc(batch)
+    save("sasrec_encoder", **out)
+
+
 if __name__ == "__main__":
     ALL = [golden_appendix_a, golden_training_steps, golden_popular, golden_uniform_cpu, golden_topk_eval,
            golden_full_softmax, golden_masked_uniform, golden_sampling_methods,
-           golden_midx, golden_pooling]
+           golden_midx, golden_pooling, golden_sasrec_encoder]
     want = sys.argv[1:]                       # optional: names of the generators to (re)run
     for fn in ALL:
         if not want or fn.__name__ in want:
