@@ -288,3 +288,40 @@ def test_uniform_owner_range_is_exact(L):
     mg, lo, hi = C.c_uint64(), C.c_uint64(), C.c_uint64()
     assert L.rsb200_uniform_owner_range(2 ** 32 + 2, 0, 10, C.byref(mg), C.byref(lo), C.byref(hi)) == -1   # ids beyond 32-bit words
     assert L.rsb200_uniform_owner_range(10, 0, 10, None, C.byref(lo), C.byref(hi)) == -1
+
+
+def test_device_batch_loader_yields_the_reference_loaders_batches():
+    """loader.DeviceBatchLoader (here on the CPU device: it is plain torch indexing) delivers, batch for batch and
+    bit for bit, what the REFERENCE's own `train_loader()` delivers for the same global seed -- ml-100k as bundled with the
+    reference, B = 512, two epochs incl. the ragged last batch (dataset.py:1083-1123,1687-1734: DataSampler's per-epoch CPU
+    randperm seeded from the global generator, after the DataLoader iterator drew its base seed)."""
+    code = r"""
+import sys, os, tempfile
+sys.path.insert(0, %r)
+os.chdir(tempfile.mkdtemp())
+import warnings; warnings.filterwarnings('ignore')
+import torch
+from recstudio_b200 import iface, loader
+from recstudio.data.dataset import TripletDataset
+from recstudio.utils import get_model
+conf = get_model('BPR')[1]
+data_conf = {'user_feat_name': None}; data_conf.update(conf['data'])
+trn = TripletDataset(name='ml-100k', config=data_conf).build(**conf['data'])[0]
+for bs, drop_last in ((512, False), (1000, True)):
+    torch.manual_seed(2022)
+    ref = [{k: v.clone() for k, v in b.items() if isinstance(v, torch.Tensor)}
+           for _ in range(2) for b in trn.train_loader(batch_size=bs, shuffle=True, num_workers=0, drop_last=drop_last)]
+    torch.manual_seed(2022)
+    dl = loader.DeviceBatchLoader.from_dataset(trn, bs, 'cpu', drop_last=drop_last)
+    mine = [b for _ in range(2) for b in dl]
+    assert len(ref) == len(mine) == 2 * len(dl) and len(ref) > 100 // (bs // 512), (len(ref), len(mine), len(dl))
+    for a, b in zip(ref, mine):
+        assert set(a) == set(b) == {'user_id', 'item_id', 'rating', 'timestamp'}
+        for k in a:
+            assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+    if not drop_last:
+        assert ref[len(dl) - 1]['user_id'].shape[0] == len(trn) %% bs           # the ragged tail batch
+print('OK', len(trn))
+""" % (REPO,)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
