@@ -62,4 +62,4 @@ def test_fused_core_against_the_reference_encoder_golden(tag):
     dev = torch.device("cuda", 0)
     g, enc, batch = _build(dev, lambda N, d: plugins.FusedEmbedding(N, d), tag == "bidir")
     assert enc._use_fused(batch["in_item_id"].size(1), batch["in_item_id"].device)
-    _check(g, enc, batch, tag, 4e-2, 8e-2)
+    _check(g, enc, batch, tag, 5e-2, 1e-1)            # bf16 operands in both layers' cores; the fp32 branch above holds 1e-5
